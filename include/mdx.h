@@ -1,0 +1,204 @@
+/*
+ * mdx.h -- C ABI of the B200-native batched marl-delivery environment path ("mdx").
+ *
+ * Plain C: pointers, sizes and PODs only (no torch / C++ types).  Every entry point returns 0 on
+ * success or a negative MDX_E_* code; mdx_last_error() gives the message of the calling thread's
+ * last failure.  No C++ exception crosses this boundary.  All "d_" pointers are DEVICE pointers owned
+ * by the caller (torch tensors); the library borrows them for the duration of the enqueue and never
+ * frees or reallocates them.  Kernels are enqueued on the caller's stream (`stream` is a
+ * cudaStream_t passed as void*; NULL = legacy default stream) and the call returns without
+ * synchronising unless stated otherwise.
+ *
+ * Each function names the reference interface (paths relative to nguyenduchuyiu/marl-delivery) it
+ * replaces.  One mdx_env owns the state of `n_envs` environments on ONE device; it is not
+ * thread-safe.  The host sampler (mdx_sampler_*) is re-entrant and needs no GPU.
+ *
+ * Encodings
+ *   cell        : r * W_out + c in the (possibly padded) output plane, 0-based; W_out = max map width
+ *   action (u8) : 0..14  -> move "DLRSU"[a % 5], package op a / 5   (sorted LabelEncoder order,
+ *                 MAPPO/trainer.py:84-89,199-204);  15..17 -> a move string that is none of
+ *                 S/L/R/U/D (env.py:333-334 leaves the robot in place) with package op a - 15;
+ *                 anything else -> stay, no package op
+ *   pkg status  : 0 'None' (not spawned), 1 'waiting', 2 'in_transit', 3 'delivered'  (env.py:16)
+ */
+#ifndef MDX_H_
+#define MDX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDX_VERSION 1
+#define MDX_MAX_ROBOTS 32 /* one warp per environment, robots are lanes */
+
+enum {
+  MDX_OK = 0,
+  MDX_E_INVALID = -1, /* bad argument / unsupported configuration (ValueError in the Python mirror) */
+  MDX_E_CUDA = -2,    /* CUDA runtime failure */
+  MDX_E_STARVED = -3, /* on-device auto-reset ran out of pre-sampled episodes */
+  MDX_E_NOMEM = -4
+};
+
+/* flags for mdx_step / mdx_step_featurize */
+#define MDX_F_AUTO_RESET 1u /* done envs advance to their next pre-sampled episode inside the kernel   \
+                               (MAPPO/trainer.py:229-234: reset, then featurise the reset state) */
+
+/* mdx_config.flags */
+#define MDX_CFG_BLANK 1 /* skip the constructor's reset draw: envs start empty (t = 0, robots on cell 0, no    \
+                           packages) and are filled with mdx_set_state -- used by the per-call helper drop-ins */
+
+/* Shaping constants of compute_shaped_rewards, in this order (MAPPO/helper.py:271-279,
+ * QMIX/helper.py:270-278). */
+typedef struct mdx_shaping {
+  float pickup, delivery_on_time, delivery_late, moved_closer, wasted_pickup, wasted_drop,
+      collision_or_stuck, idle_with_tasks, moved_away;
+} mdx_shaping;
+
+/* Everything Environment.__init__ (env.py:20-43), VectorizedEnv.__init__
+ * (MAPPO/env_vectorized.py:2-11) and the featuriser call sites (MAPPO/trainer.py:237-280) fix. */
+typedef struct mdx_config {
+  int32_t n_envs;         /* environments owned by this instance (this GPU's shard) */
+  int32_t n_robots;       /* <= MDX_MAX_ROBOTS */
+  int32_t n_packages;
+  int32_t max_time_steps; /* T */
+  double move_cost, delivery_reward, delay_reward; /* env.py:21 */
+  mdx_shaping shaping;
+  int32_t k_others;              /* max_other_robots_to_observe  (MAPPO/helper.py:70) */
+  int32_t k_packages;            /* max_packages_to_observe */
+  int32_t max_robots_in_state;   /* MAPPO/helper.py:169 */
+  int32_t max_packages_in_state;
+  int32_t n_maps;                /* >= 1 */
+  const int32_t* map_rows;       /* [n_maps] */
+  const int32_t* map_cols;       /* [n_maps] */
+  const uint8_t* const* map_cells; /* [n_maps] row-major rows*cols bytes, 0 free, 1 obstacle */
+  const int32_t* env_map;        /* [n_envs] map id per env, NULL = all map 0 (4-map notebook: idx % n_maps) */
+  const int64_t* env_seed;       /* [n_envs] RandomState seed per env; NULL = base_seed + i */
+  int64_t base_seed;             /* env i uses seed base_seed + i  (MAPPO/env_vectorized.py:7-9) */
+  int32_t device;                /* CUDA ordinal */
+  int32_t ring_episodes;         /* depth E of the per-env pre-sampled episode ring, >= 2 */
+  int32_t sampler_threads;       /* host threads for reset sampling, 0 = hardware concurrency */
+  int32_t flags;                 /* MDX_CFG_* */
+} mdx_config;
+
+typedef struct mdx_dims {
+  int32_t n_envs, n_robots, n_packages, max_time_steps;
+  int32_t rows_out, cols_out; /* padded plane size of obs / gstate */
+  int32_t vec_dim;            /* 6 + 5*k_others + 5*k_packages + 1 */
+  int32_t gvec_dim;           /* 6*max_robots_in_state + 7*max_packages_in_state + 1 */
+  int64_t bytes_per_env_step; /* 4*(R*6*H*W + R*D + 4*H*W + Dg) + 4 + 1 + R */
+  int32_t ring_episodes;
+  int32_t reserved;
+} mdx_dims;
+
+/* Host-side copy of one environment (the lazy dict / attribute views of the Python mirror:
+ * env.py:127-147 get_state, .robots[i].position/.carrying, .packages[j].*, .t, .total_reward). */
+typedef struct mdx_state_view {
+  int32_t t;
+  int32_t episode;          /* number of resets applied since construction (0 = the constructor's) */
+  int32_t map_id;
+  int32_t reserved;
+  double total_reward;
+  int32_t* robot_row;       /* [n_robots] 0-based, caller-allocated */
+  int32_t* robot_col;
+  int32_t* robot_carry;     /* 0 or package id (1-based) */
+  int32_t* pkg_start_row;   /* [n_packages] */
+  int32_t* pkg_start_col;
+  int32_t* pkg_target_row;
+  int32_t* pkg_target_col;
+  int32_t* pkg_start_time;
+  int32_t* pkg_deadline;
+  int32_t* pkg_status;
+} mdx_state_view;
+
+typedef struct mdx_env mdx_env;
+typedef struct mdx_sampler mdx_sampler;
+
+const char* mdx_last_error(void);
+int32_t mdx_version(void);
+
+/* Environment.__init__ x n_envs / VectorizedEnv.__init__ (env.py:20-43, MAPPO/env_vectorized.py:2-11).
+ * Like the reference constructor, this draws reset block 0 for every env and puts the envs in it. */
+int32_t mdx_create(const mdx_config* cfg, mdx_env** out);
+int32_t mdx_destroy(mdx_env* env);
+int32_t mdx_get_dims(const mdx_env* env, mdx_dims* out);
+
+/* Environment.reset / VectorizedEnv.reset(indices) (env.py:81-125, QMIX/env_vectorized.py:13-22):
+ * every listed env (HOST int32 ids, NULL = all) advances to its next reset block, drawn on the host
+ * from the env's own MT19937 stream in the reference's draw order.  Synchronises `stream` once (it
+ * has to read how many blocks on-device auto-resets consumed). */
+int32_t mdx_reset(mdx_env* env, const int32_t* h_env_ids, int32_t n, void* stream);
+
+/* Pre-sample and upload reset blocks so that every env has `episodes_ahead` blocks beyond its current
+ * one in the ring (needed before stepping with MDX_F_AUTO_RESET).  Synchronises `stream` once. */
+int32_t mdx_prefetch(mdx_env* env, int32_t episodes_ahead, void* stream);
+
+/* Environment.step / VectorizedEnv.step(actions, indices) (env.py:173-306,
+ * QMIX/env_vectorized.py:24-37) fused with compute_shaped_rewards (MAPPO/helper.py:257-369).
+ * d_actions [n, n_robots] u8; d_env_ids [n] int32 device ids or NULL (= all, n must be n_envs).
+ * Outputs (each may be NULL): d_reward [n] f64 env reward, d_shaped [n] f32 shaped team reward,
+ * d_done [n] u8.  Rows follow the order of d_env_ids. */
+int32_t mdx_step(mdx_env* env, const uint8_t* d_actions, const int32_t* d_env_ids, int32_t n,
+                 double* d_reward, float* d_shaped, uint8_t* d_done, uint32_t flags, void* stream);
+
+/* convert_observation / generate_vector_features / convert_global_state for every listed env and
+ * every robot (MAPPO/helper.py:6-255), written straight into the caller's tensors:
+ * d_obs [n, R, 6, rows_out, cols_out], d_vec [n, R, vec_dim], d_gstate [n, 4, rows_out, cols_out],
+ * d_gvec [n, gvec_dim], all f32, any may be NULL. */
+int32_t mdx_featurize(mdx_env* env, const int32_t* d_env_ids, int32_t n, float* d_obs, float* d_vec,
+                      float* d_gstate, float* d_gvec, void* stream);
+
+/* One launch for one iteration of MAPPO/trainer.py:172-286: step + shaped reward + (auto-reset) +
+ * featurisation of the state the next action is taken from. */
+int32_t mdx_step_featurize(mdx_env* env, const uint8_t* d_actions, const int32_t* d_env_ids, int32_t n,
+                           double* d_reward, float* d_shaped, uint8_t* d_done, float* d_obs,
+                           float* d_vec, float* d_gstate, float* d_gvec, uint32_t flags, void* stream);
+
+/* compute_shaped_rewards on caller-supplied "current" robots (MAPPO/helper.py:257-369) against the
+ * stored state as "previous": d_cur_robots [n, R] u32 = cell | carry << 16, d_cur_t [n] int32,
+ * d_global_reward [n] f64 -> d_out [n] f32.  Does not modify the environments. */
+int32_t mdx_shaped_reward(mdx_env* env, const uint32_t* d_cur_robots, const int32_t* d_cur_t,
+                          const uint8_t* d_actions, const double* d_global_reward, float* d_out,
+                          void* stream);
+
+/* Introspection (evaluation.py:50, main.py:86-103, IDQ/trainer.py:92): synchronous copies. */
+int32_t mdx_get_state(mdx_env* env, int32_t env_id, mdx_state_view* out, void* stream);
+/* State injection for hand-built cases (Group-Project.pdf worked example, helper drop-ins). */
+int32_t mdx_set_state(mdx_env* env, int32_t env_id, const mdx_state_view* in, void* stream);
+
+/* d_out8 [8] int64 = {episodes_done, robot_moves, on_time, late, pickups,
+ * env_steps, sum_episode_len, starved_envs} summed over this instance's envs (cumulative since
+ * creation).  The caller all-reduces it across ranks. */
+int32_t mdx_episode_stats(mdx_env* env, int64_t* d_out8, void* stream);
+
+/* ---- host-only pieces (no GPU needed) ------------------------------------------------------- */
+
+/* The reference's reset draw order on numpy's legacy RandomState(seed) stream (env.py:96-123,
+ * 150-170; numpy: init_genrand seeding + masked-rejection bounded integers, one 32-bit output per
+ * try).  Each mdx_sampler_next call produces the next reset block of ONE environment:
+ * robot_cell [R], pkg4 [4][P] = start cell, target cell, start_time, deadline in package-id order
+ * (cells are r * cols + c of the map itself). */
+int32_t mdx_sampler_create(uint32_t seed, const uint8_t* cells, int32_t rows, int32_t cols,
+                           int32_t n_robots, int32_t n_packages, int32_t max_time_steps,
+                           mdx_sampler** out);
+int32_t mdx_sampler_next(mdx_sampler* s, int32_t* robot_cell, int32_t* pkg4);
+int32_t mdx_sampler_destroy(mdx_sampler* s);
+/* raw generator access, for pinning against numpy: n draws of RandomState(seed).randint(lo, hi) */
+int32_t mdx_rng_randint(uint32_t seed, int64_t lo, int64_t hi, int32_t n, int64_t* out);
+
+/* Lookup tables the kernels read, exposed for parity tests against plain Python arithmetic:
+ * quotient q[d + (n_out-1)] = (float)((double)d / n) for d in [-(n_out-1), n_out-1], and the dense
+ * rank of the float64 sort key (dr/rows)**2 + (dc/cols)**2 (MAPPO/helper.py:139,158) over
+ * dr in [-(rows_out-1), rows_out-1] x dc in [-(cols_out-1), cols_out-1]. */
+int32_t mdx_lut_quotient(int32_t n, int32_t n_out, float* out /* [2*n_out-1] */);
+int32_t mdx_lut_rank(int32_t rows, int32_t cols, int32_t rows_out, int32_t cols_out,
+                     uint16_t* out /* [(2*rows_out-1)*(2*cols_out-1)] */, int32_t* n_ranks);
+/* numpy's float32 pairwise `.sum()` (MAPPO/helper.py:369) restated on the host, same routine the
+ * kernel implements with shuffles. */
+float mdx_np_sum_f32(const float* x, int32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDX_H_ */

@@ -1,0 +1,279 @@
+"""DeliveryBatch: N environments on one B200 behind the C ABI of include/mdx.h.
+
+This is the tensor-level fast path the drop-in wrappers (env.py, env_vectorized.py, helper.py) sit
+on.  PyTorch is used for what it is good at here -- owning the output tensors in HBM, streams,
+torch.distributed -- and nothing else: every transition, reward and feature is computed by the
+hand-written kernels in csrc/.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MDX_F_AUTO_RESET
+
+# compute_shaped_rewards constants (MAPPO/helper.py:271-279, QMIX/helper.py:270-278)
+MAPPO_SHAPING = (5.0, 200.0, 20.0, 0.02, 0.0, 0.0, -0.05, -0.05, -0.01)
+QMIX_SHAPING = (0.5, 2.0, 0.2, 0.02, -0.1, -0.1, -0.05, -0.02, -0.02)
+
+STATUS_NAMES = ("None", "waiting", "in_transit", "delivered")
+MOVE_CODES = {"D": 0, "L": 1, "R": 2, "S": 3, "U": 4}  # sorted LabelEncoder order, MAPPO/trainer.py:84-89
+STAT_NAMES = ("episodes_done", "robot_moves", "on_time", "late", "pickups", "env_steps", "sum_episode_len",
+              "starved_envs")
+
+
+def encode_action(move, pkg_act) -> int:
+    """(move_str, pkg_str) -> action code of include/mdx.h.  Mirrors the reference's comparisons:
+    moves other than S/L/R/U/D leave the robot in place (env.py:333-334), and only the STRINGS '1' and
+    '2' are package ops (env.py:264,277; ints are ignored)."""
+    op = 1 if (isinstance(pkg_act, str) and pkg_act == "1") else 2 if (isinstance(pkg_act, str) and pkg_act == "2") else 0
+    mv = MOVE_CODES.get(move) if isinstance(move, str) else None
+    if mv is None:
+        return 15 + op
+    return mv + 5 * op
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class DeliveryBatch:
+    """n_envs environments resident on one GPU."""
+
+    def __init__(self, grids: Sequence[np.ndarray], n_envs: int, n_robots: int = 5, n_packages: int = 20,
+                 max_time_steps: int = 100, move_cost: float = -0.01, delivery_reward: float = 10.0,
+                 delay_reward: float = 1.0, seeds=None, base_seed: int = 2025, env_map=None,
+                 k_others: int = 100, k_packages: int = 100, max_robots_in_state: int = 100,
+                 max_packages_in_state: int = 100, shaping=MAPPO_SHAPING, device=None, ring_episodes: int = 4,
+                 sampler_threads: int = 0, blank: bool = False):
+        L = _lib.lib()
+        if not torch.cuda.is_available():
+            raise _lib.MdxError("no CUDA device: marl-delivery_b200 runs on the GPU only (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.MdxError("marl-delivery_b200 needs a CUDA device")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        grids = [np.ascontiguousarray(np.asarray(g, dtype=np.uint8)) for g in grids]
+        for g in grids:
+            if g.ndim != 2:
+                raise ValueError("a map must be a 2-D grid of 0/1")
+        self.grids = grids
+        cfg = _lib.Config()
+        cfg.n_envs, cfg.n_robots, cfg.n_packages, cfg.max_time_steps = int(n_envs), int(n_robots), int(n_packages), int(max_time_steps)
+        cfg.move_cost, cfg.delivery_reward, cfg.delay_reward = float(move_cost), float(delivery_reward), float(delay_reward)
+        cfg.shaping = _lib.Shaping(*[float(x) for x in shaping])
+        cfg.k_others, cfg.k_packages = int(k_others), int(k_packages)
+        cfg.max_robots_in_state, cfg.max_packages_in_state = int(max_robots_in_state), int(max_packages_in_state)
+        cfg.n_maps = len(grids)
+        rows = (C.c_int32 * len(grids))(*[g.shape[0] for g in grids])
+        cols = (C.c_int32 * len(grids))(*[g.shape[1] for g in grids])
+        cells = (C.POINTER(C.c_uint8) * len(grids))(*[g.ctypes.data_as(C.POINTER(C.c_uint8)) for g in grids])
+        cfg.map_rows, cfg.map_cols, cfg.map_cells = rows, cols, cells
+        keep = [rows, cols, cells]
+        if env_map is not None:
+            em = np.ascontiguousarray(np.asarray(env_map, dtype=np.int32))
+            if em.shape != (n_envs,):
+                raise ValueError("env_map must have one entry per env")
+            cfg.env_map = em.ctypes.data_as(C.POINTER(C.c_int32))
+            keep.append(em)
+            self.env_map = em.copy()
+        else:
+            self.env_map = np.zeros(n_envs, np.int32)
+        if seeds is not None:
+            sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.int64))
+            if sd.shape != (n_envs,):
+                raise ValueError("seeds must have one entry per env")
+            cfg.env_seed = sd.ctypes.data_as(C.POINTER(C.c_int64))
+            keep.append(sd)
+        cfg.base_seed = int(base_seed)
+        cfg.device = int(self.device.index)
+        cfg.ring_episodes = int(ring_episodes)
+        cfg.sampler_threads = int(sampler_threads)
+        cfg.flags = _lib.MDX_CFG_BLANK if blank else 0
+        handle = C.c_void_p()
+        _lib.check(L.mdx_create(C.byref(cfg), C.byref(handle)))
+        self._h = handle
+        self._L = L
+        d = _lib.Dims()
+        _lib.check(L.mdx_get_dims(self._h, C.byref(d)))
+        self.n_envs, self.n_robots, self.n_packages, self.max_time_steps = d.n_envs, d.n_robots, d.n_packages, d.max_time_steps
+        self.rows_out, self.cols_out, self.vec_dim, self.gvec_dim = d.rows_out, d.cols_out, d.vec_dim, d.gvec_dim
+        self.bytes_per_env_step = int(d.bytes_per_env_step)
+        self.ring_episodes = d.ring_episodes
+        self.shaping = tuple(float(x) for x in shaping)
+        self._bufs = {}
+        self._version = 0  # bumped by every call that changes env state (invalidates EnvView snapshots)
+        self._grid_lists = [g.tolist() for g in self.grids]
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.mdx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _buf(self, name, shape, dtype):
+        key = (name, tuple(shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    def _ids(self, ids):
+        """-> (device int32 tensor or None, host list or None, n)"""
+        if ids is None:
+            return None, None, self.n_envs
+        if isinstance(ids, torch.Tensor):
+            d = ids.to(device=self.device, dtype=torch.int32).contiguous()
+            return d, None, int(d.numel())
+        h = [int(i) for i in ids]
+        for i in h:
+            if not 0 <= i < self.n_envs:
+                raise IndexError(f"env index {i} out of range")
+        return torch.tensor(h, dtype=torch.int32, device=self.device), h, len(h)
+
+    # ------------------------------------------------------------------ reset / prefetch
+    def reset(self, ids=None):
+        """Environment.reset for the listed envs (all when None): next host-drawn reset block."""
+        if ids is None:
+            _lib.check(self._L.mdx_reset(self._h, None, 0, self._stream()))
+            self._version += 1
+            return
+        h = np.ascontiguousarray(np.asarray([int(i) for i in ids], dtype=np.int32))
+        _lib.check(self._L.mdx_reset(self._h, h.ctypes.data_as(C.POINTER(C.c_int32)), int(h.size), self._stream()))
+        self._version += 1
+
+    def prefetch(self, episodes_ahead: int):
+        """Pre-sample reset blocks for on-device auto-reset (at most ring_episodes - 1 ahead)."""
+        _lib.check(self._L.mdx_prefetch(self._h, int(episodes_ahead), self._stream()))
+
+    # ------------------------------------------------------------------ step
+    def _check_actions(self, actions, n):
+        if not isinstance(actions, torch.Tensor):
+            actions = torch.as_tensor(np.asarray(actions, dtype=np.uint8))
+        if actions.dtype != torch.uint8:
+            actions = actions.to(torch.uint8)
+        actions = actions.to(self.device).contiguous()
+        if tuple(actions.shape) != (n, self.n_robots):
+            raise ValueError("The number of actions must match the number of robots.")  # env.py:182-183
+        return actions
+
+    def step(self, actions, ids=None, auto_reset: bool = False, want_shaped: bool = True, out=None):
+        """-> (reward f64 [n], shaped f32 [n] or None, done u8 [n]); rows follow `ids`."""
+        d_ids, _, n = self._ids(ids)
+        actions = self._check_actions(actions, n)
+        if out is None:
+            reward = self._buf("reward", (n,), torch.float64)
+            shaped = self._buf("shaped", (n,), torch.float32) if want_shaped else None
+            done = self._buf("done", (n,), torch.uint8)
+        else:
+            reward, shaped, done = out
+        _lib.check(self._L.mdx_step(self._h, _ptr(actions), _ptr(d_ids), n, _ptr(reward), _ptr(shaped), _ptr(done),
+                                    MDX_F_AUTO_RESET if auto_reset else 0, self._stream()))
+        self._version += 1
+        return reward, shaped, done
+
+    def alloc_features(self, n=None, obs=True, vec=True, gstate=True, gvec=True):
+        n = self.n_envs if n is None else n
+        R, H, W = self.n_robots, self.rows_out, self.cols_out
+        mk = lambda *s: torch.empty(s, dtype=torch.float32, device=self.device)  # noqa: E731
+        return (mk(n, R, 6, H, W) if obs else None, mk(n, R, self.vec_dim) if vec else None,
+                mk(n, 4, H, W) if gstate else None, mk(n, self.gvec_dim) if gvec else None)
+
+    def _feat_out(self, n, out):
+        if out is not None:
+            return out
+        key = ("feat", n)
+        if key not in self._bufs:
+            self._bufs[key] = self.alloc_features(n)
+        return self._bufs[key]
+
+    def featurize(self, ids=None, out=None):
+        """-> (obs [n,R,6,H,W], vec [n,R,D], gstate [n,4,H,W], gvec [n,Dg]) float32 on the GPU."""
+        d_ids, _, n = self._ids(ids)
+        obs, vec, gstate, gvec = self._feat_out(n, out)
+        _lib.check(self._L.mdx_featurize(self._h, _ptr(d_ids), n, _ptr(obs), _ptr(vec), _ptr(gstate), _ptr(gvec),
+                                         self._stream()))
+        return obs, vec, gstate, gvec
+
+    def step_featurize(self, actions, ids=None, auto_reset: bool = True, out=None, feat_out=None):
+        """One launch per MAPPO rollout iteration (MAPPO/trainer.py:172-286 minus the networks)."""
+        d_ids, _, n = self._ids(ids)
+        actions = self._check_actions(actions, n)
+        if out is None:
+            reward = self._buf("reward", (n,), torch.float64)
+            shaped = self._buf("shaped", (n,), torch.float32)
+            done = self._buf("done", (n,), torch.uint8)
+        else:
+            reward, shaped, done = out
+        obs, vec, gstate, gvec = self._feat_out(n, feat_out)
+        _lib.check(self._L.mdx_step_featurize(self._h, _ptr(actions), _ptr(d_ids), n, _ptr(reward), _ptr(shaped),
+                                              _ptr(done), _ptr(obs), _ptr(vec), _ptr(gstate), _ptr(gvec),
+                                              MDX_F_AUTO_RESET if auto_reset else 0, self._stream()))
+        self._version += 1
+        return reward, shaped, done, obs, vec, gstate, gvec
+
+    def shaped_reward(self, cur_robots, cur_t, actions, global_reward):
+        """compute_shaped_rewards with the stored state as 'previous' (MAPPO/helper.py:257-369)."""
+        n = self.n_envs
+        cur_robots = cur_robots.to(self.device, torch.int64).contiguous()
+        packed = (cur_robots[..., 0] | (cur_robots[..., 1] << 16)).to(torch.int32).contiguous()  # cell | carry << 16
+        cur_t = cur_t.to(self.device, torch.int32).contiguous()
+        actions = self._check_actions(actions, n)
+        gr = global_reward.to(self.device, torch.float64).contiguous()
+        out = torch.empty(n, dtype=torch.float32, device=self.device)
+        _lib.check(self._L.mdx_shaped_reward(self._h, _ptr(packed), _ptr(cur_t), _ptr(actions), _ptr(gr), _ptr(out),
+                                             self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ introspection
+    def get_state(self, i: int) -> dict:
+        R, P = self.n_robots, self.n_packages
+        arr = {k: np.zeros(R, np.int32) for k in ("robot_row", "robot_col", "robot_carry")}
+        arr.update({k: np.zeros(max(P, 1), np.int32) for k in (
+            "pkg_start_row", "pkg_start_col", "pkg_target_row", "pkg_target_col", "pkg_start_time", "pkg_deadline",
+            "pkg_status")})
+        v = _lib.StateView()
+        for k, a in arr.items():
+            setattr(v, k, a.ctypes.data_as(C.POINTER(C.c_int32)))
+        _lib.check(self._L.mdx_get_state(self._h, int(i), C.byref(v), self._stream()))
+        out = {k: a[:P] if k.startswith("pkg_") else a for k, a in arr.items()}
+        out.update(t=int(v.t), episode=int(v.episode), map_id=int(v.map_id), total_reward=float(v.total_reward))
+        return out
+
+    def set_state(self, i: int, t, total_reward, robots, packages):
+        """robots: [(row, col, carry)] 0-based; packages: [(start_row, start_col, target_row, target_col,
+        start_time, deadline, status_code)] in id order, exactly n_packages entries."""
+        R, P = self.n_robots, self.n_packages
+        if len(robots) != R or len(packages) != P:
+            raise ValueError("robots / packages must match n_robots / n_packages")
+        rb = np.ascontiguousarray(np.asarray(robots, dtype=np.int32).reshape(R, 3).T)
+        pk = np.ascontiguousarray(np.asarray(packages, dtype=np.int32).reshape(P, 7).T) if P else np.zeros((7, 1), np.int32)
+        v = _lib.StateView()
+        v.t, v.total_reward = int(t), float(total_reward)
+        p32 = C.POINTER(C.c_int32)
+        v.robot_row, v.robot_col, v.robot_carry = (rb[k].ctypes.data_as(p32) for k in range(3))
+        (v.pkg_start_row, v.pkg_start_col, v.pkg_target_row, v.pkg_target_col, v.pkg_start_time, v.pkg_deadline,
+         v.pkg_status) = (pk[k].ctypes.data_as(p32) for k in range(7))
+        _lib.check(self._L.mdx_set_state(self._h, int(i), C.byref(v), self._stream()))
+        self._version += 1
+
+    def episode_stats(self) -> torch.Tensor:
+        """int64[8] (STAT_NAMES) summed over this instance's envs; all-reduce it across ranks."""
+        out = torch.empty(8, dtype=torch.int64, device=self.device)
+        _lib.check(self._L.mdx_episode_stats(self._h, _ptr(out), self._stream()))
+        return out

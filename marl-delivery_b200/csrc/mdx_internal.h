@@ -1,0 +1,114 @@
+// Internal declarations shared by the host sampler, the C-ABI glue and the kernels.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace mdx {
+
+struct Mt19937 {
+  uint32_t mt[624];
+  int pos;
+  void seed(uint32_t s);
+  void refill();
+  inline uint32_t next32() {
+    if (pos == 624) refill();
+    uint32_t y = mt[pos++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+  }
+  bool randint(int64_t lo, int64_t hi, int64_t* out);
+};
+
+struct EpisodeSampler {
+  struct Rec {
+    int start, target, start_time, deadline;
+  };
+  Mt19937 rng;
+  int rows = 0, cols = 0, R = 0, P = 0, T = 0;
+  std::vector<int> free_cells;
+  std::vector<int> scratch_avail;
+  std::vector<Rec> scratch_rec;
+  bool init(uint32_t seed, const uint8_t* cells, int rows, int cols, int R, int P, int T);
+  bool next(int32_t* robot_cell, int32_t* pkg4);
+  bool draw(Mt19937& g, const std::vector<int>& free_cells, int rows, int R, int P, int T, int32_t* robot_cell,
+            int32_t* pkg4);
+};
+
+void build_quotient_lut(int n, int n_out, float* out);
+int build_rank_lut(int rows, int cols, int rows_out, int cols_out, uint16_t* out);
+float np_sum_f32(const float* a, int n);
+
+// ---- device-side views ------------------------------------------------------------------------
+
+enum : uint8_t { ST_NONE = 0, ST_WAITING = 1, ST_IN_TRANSIT = 2, ST_DELIVERED = 3 };
+enum : int { MV_D = 0, MV_L = 1, MV_R = 2, MV_S = 3, MV_U = 4, MV_BAD = 5 };
+
+// counters[env][8], cumulative since creation
+enum : int { C_EPISODES = 0, C_MOVES = 1, C_ONTIME = 2, C_LATE = 3, C_PICKUPS = 4, C_STEPS = 5, C_EPLEN = 6, C_STARVED = 7 };
+
+struct MapDev {
+  int32_t H, W;               // true map size (rows, cols)
+  int32_t nranks;
+  int32_t pad;
+  const uint32_t* grid_bits;  // [W32] obstacle bits in output-plane cell coordinates
+  const float* qr;            // [2*H_out-1]  qr[d + H_out-1] = (float)((double)d / H)
+  const float* qc;            // [2*W_out-1]
+  const uint16_t* rank;       // [(2*H_out-1) * (2*W_out-1)] dense rank of the float64 sort key
+};
+
+struct KParams {
+  // shape
+  int32_t n_envs, R, P, T;
+  int32_t Pp8;    // P rounded up to 8  (u16 rows of the schedule block are 16-byte aligned)
+  int32_t Pp16;   // P rounded up to 16 (status row)
+  int32_t H_out, W_out, HW, W32;
+  int32_t K_o, K_p, MR, MP, D, Dg;
+  int32_t E;      // ring depth
+  int32_t key_wbits;     // bits reserved for the waiting-list index inside the 32-bit selection key
+  int32_t nranks_max;
+  int32_t tq_len;
+  int32_t vec_rows_per_flush;
+  uint32_t mul_plane;    // ceil(2^32 / HW)       : e / HW        for e < 2^32 / HW
+  uint32_t mul_wout;     // ceil(2^32 / W_out)    : cell / W_out
+  // smem carve-up (bytes from the warp's base)
+  int32_t off_sched, off_status, off_wlist, off_wdl, off_alist, off_wkey, off_masks, off_rinfo, off_stage;
+  int32_t smem_per_warp;
+  // rewards
+  double move_cost, delivery_reward, delay_reward;
+  float shaping[9];
+  int32_t pad0;
+  // state
+  int32_t* t;
+  int32_t* ep;
+  const int32_t* ep_avail;
+  double* total_reward;
+  uint32_t* robots;        // [n_envs][R]  cell | carry << 16
+  uint8_t* status;         // [n_envs][Pp16]
+  uint16_t* sched;         // [E][n_envs][4][Pp8]
+  uint16_t* sched_robots;  // [E][n_envs][32]
+  uint32_t* counters;      // [n_envs][8]
+  const int32_t* env_map;  // [n_envs]
+  const MapDev* maps;
+  const float* tq;         // tq[k] = (float)((double)k / T)
+  // call arguments
+  const uint8_t* actions;
+  const int32_t* env_ids;
+  int32_t n;
+  uint32_t flags;
+  double* out_reward;
+  float* out_shaped;
+  uint8_t* out_done;
+  float* obs;
+  float* vec;
+  float* gstate;
+  float* gvec;
+  // shaped-reward-only call
+  const uint32_t* cur_robots;
+  const int32_t* cur_t;
+  const double* global_reward;
+};
+
+}  // namespace mdx

@@ -1,0 +1,130 @@
+"""Drop-in for `MAPPO/env_vectorized.py` (== IDQ/, qmix/) and `QMIX/env_vectorized.py` (adds
+`indices=`): `VectorizedEnv(env_cls, num_envs, **env_kwargs)` with `.envs`, `.num_envs`, `reset`,
+`step`.  All environments live in ONE DeliveryBatch on the GPU; the list-of-dicts returns are the
+reference-compatible slow path, `step_tensor` / `featurize` / `rollout_step` are the fast path.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .batch import MAPPO_SHAPING, DeliveryBatch, encode_action
+from .env import EnvView
+from .maps import load_map
+
+_ENV_KW = ("map_file", "max_time_steps", "n_robots", "n_packages", "move_cost", "delivery_reward", "delay_reward", "seed")
+
+
+class VectorizedEnv:
+    def __init__(self, env_cls, num_envs, k_others=100, k_packages=100, max_robots_in_state=100,
+                 max_packages_in_state=100, shaping=MAPPO_SHAPING, device=None, ring_episodes=4, first_env_index=0,
+                 **env_kwargs):
+        """`env_cls` is accepted for signature compatibility (the reference passes its Environment
+        class); the environments are always slots of one CUDA batch.  Seeds follow
+        MAPPO/env_vectorized.py:4-10: env idx uses seed + idx (all envs share the default seed 2025 when
+        no seed is given, exactly like the reference).  `map_file` may be a list, then env idx uses
+        map_files[idx % len] (4-map notebook).  `first_env_index` offsets idx for multi-GPU sharding so
+        that results do not depend on the number of ranks."""
+        unknown = set(env_kwargs) - set(_ENV_KW)
+        if unknown:
+            raise TypeError(f"unexpected Environment arguments: {sorted(unknown)}")
+        if "map_file" not in env_kwargs:
+            raise TypeError("Environment.__init__() missing 1 required positional argument: 'map_file'")
+        map_file = env_kwargs["map_file"]
+        files = list(map_file) if isinstance(map_file, (list, tuple)) and not _is_grid(map_file) else [map_file]
+        grids = [load_map(f) for f in files]
+        gidx = np.arange(first_env_index, first_env_index + num_envs)
+        base_seed = env_kwargs.get("seed", None)
+        seeds = np.full(num_envs, 2025, np.int64) if base_seed is None else (int(base_seed) + gidx).astype(np.int64)
+        self.batch = DeliveryBatch(
+            grids, num_envs, env_kwargs.get("n_robots", 5), env_kwargs.get("n_packages", 20),
+            env_kwargs.get("max_time_steps", 100), env_kwargs.get("move_cost", -0.01),
+            env_kwargs.get("delivery_reward", 10.), env_kwargs.get("delay_reward", 1.), seeds=seeds,
+            env_map=(gidx % len(grids)).astype(np.int32) if len(grids) > 1 else None, k_others=k_others,
+            k_packages=k_packages, max_robots_in_state=max_robots_in_state,
+            max_packages_in_state=max_packages_in_state, shaping=shaping, device=device, ring_episodes=ring_episodes)
+        self.num_envs = num_envs
+        self.envs = _EnvList(self.batch, [files[int(g) % len(files)] for g in gidx] if len(files) > 1 else files * 1)
+
+    # ------------------------------------------------------------------ reference API (lists of dicts)
+    def reset(self, indices=None):
+        idx = list(range(self.num_envs)) if indices is None else [int(i) for i in indices]
+        self.batch.reset(None if indices is None else idx)
+        for i in idx:
+            self.envs[i]._invalidate()
+            self.envs[i].done = False
+        return [self.envs[i].get_state() for i in idx]
+
+    def step(self, actions, indices=None):
+        idx = list(range(self.num_envs)) if indices is None else [int(i) for i in indices]
+        idx = idx[:len(actions)]  # zip() semantics of the reference
+        if not idx:
+            raise ValueError("not enough values to unpack (expected 4, got 0)")
+        R = self.batch.n_robots
+        codes = np.zeros((len(idx), R), np.uint8)
+        for k, acts in enumerate(actions[:len(idx)]):
+            if len(acts) != R:
+                raise ValueError("The number of actions must match the number of robots.")
+            codes[k] = [encode_action(m, p) for (m, p) in acts]
+        reward, _, done = self.batch.step(torch.from_numpy(codes), ids=None if indices is None and len(idx) == self.num_envs else idx,
+                                          want_shaped=False)
+        rewards = reward.cpu().tolist()
+        dones = [bool(x) for x in done.cpu().tolist()]
+        states, infos = [], []
+        for k, i in enumerate(idx):
+            e = self.envs[i]
+            e._invalidate()
+            info = {}
+            if dones[k]:
+                info["total_reward"] = e.total_reward
+                info["total_time_steps"] = e.t
+            states.append(e.get_state())
+            infos.append(info)
+        return states, rewards, dones, infos
+
+    def render(self, indices=None):
+        raise NotImplementedError("rendering is not part of the B200 hot path")
+
+    # ------------------------------------------------------------------ tensor fast path
+    def step_tensor(self, actions, indices=None, auto_reset=False):
+        """actions: uint8 [n, R] codes (a % 5 -> 'DLRSU', a // 5 -> package op).  -> reward f64, shaped f32,
+        done u8 tensors on the GPU."""
+        return self.batch.step(actions, ids=indices, auto_reset=auto_reset)
+
+    def featurize(self, indices=None, out=None):
+        return self.batch.featurize(ids=indices, out=out)
+
+    def rollout_step(self, actions, auto_reset=True, out=None, feat_out=None):
+        """One fused launch per MAPPO rollout iteration (MAPPO/trainer.py:172-286 without the nets)."""
+        return self.batch.step_featurize(actions, auto_reset=auto_reset, out=out, feat_out=feat_out)
+
+
+class _EnvList:
+    """`.envs` of the reference is a list of Environment objects; here the per-env views are created on
+    first access (a 65k-env batch should not build 65k Python objects up front)."""
+
+    def __init__(self, batch, files):
+        self._b, self._files, self._cache = batch, files, {}
+
+    def __len__(self):
+        return self._b.n_envs
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        i = int(i)
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError("list index out of range")
+        v = self._cache.get(i)
+        if v is None:
+            v = self._cache[i] = EnvView(self._b, i, self._files[i % len(self._files)])
+        return v
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+def _is_grid(x):
+    return isinstance(x, np.ndarray) or (len(x) > 0 and isinstance(x[0], (list, tuple, np.ndarray)))
