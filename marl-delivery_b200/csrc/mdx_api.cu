@@ -122,11 +122,11 @@ struct mdx_env {
 namespace {
 
 int smem_for_mode(const mdx_env* e, int mode) {
-  return (mode & 2) ? e->base.smem_per_warp : e->base.off_stage;
+  return (mode & 2) ? e->base.smem_per_warp : e->base.off_alist;
 }
 
 int pick_wpb(const mdx_env* e, int smem_per_warp) {
-  if (e->wpb_override > 0) return e->wpb_override;
+  if (e->wpb_override > 0) return std::min(4, e->wpb_override);  // kernels are compiled for <= 128 threads
   int wpb = 4;
   while (wpb > 1 && wpb * smem_per_warp > 200 * 1024) wpb >>= 1;
   return wpb;
@@ -208,7 +208,7 @@ template <int kMode>
 int launch_env_kernel(mdx_env* e, const KParams& kp, cudaStream_t st) {
   const int spw = smem_for_mode(e, kMode);
   const int wpb = pick_wpb(e, spw);
-  const size_t smem = (size_t)wpb * spw;
+  const size_t smem = (size_t)kLutBytes + (size_t)wpb * spw;
   size_t* configured = e->smem_configured;
   if (smem > configured[kMode]) {
     CU(cudaFuncSetAttribute(mdx_env_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
@@ -372,6 +372,11 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
     float* tq = reinterpret_cast<float*>(blob.data() + off_tq);
     for (int k = 0; k < b.tq_len; ++k) tq[k] = e->T > 0 ? (float)((double)k / (double)e->T) : 0.0f;
   }
+  const size_t off_cq = reserve(sizeof(float) * 32);
+  {
+    float* cq = reinterpret_cast<float*>(blob.data() + off_cq);
+    for (int i = 0; i < 32; ++i) cq[i] = b.MR > 1 ? (float)((double)i / (double)(b.MR - 1)) : 0.0f;
+  }
   const size_t off_maps = reserve(sizeof(MapDev) * (size_t)cfg->n_maps);
 
   // selection key: (remaining * nranks + rank) << wbits | waiting-list index must fit 32 bits
@@ -392,17 +397,19 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   };
   b.off_sched = take(8 * b.Pp8);
   b.off_status = take(b.Pp16);
-  b.off_wlist = take(2 * b.Pp8);
-  b.off_wdl = take(2 * b.Pp8);
-  b.off_alist = take(2 * std::max(8, round_up(std::min(b.MP, std::max(1, e->P)), 8)));
+  b.off_wlist = take(3 * 2 * b.Pp8);  // wlist, wrc, wdl
   b.off_wkey = take(4 * b.Pp8);
-  b.off_masks = take(4 * 3 * b.W32);
-  b.off_rinfo = take(2 * 4 * 32);
-  b.off_stage = off;
+  b.off_rinfo = take(2 * 5 * 32);
+  b.off_alist = take(2 * std::max(8, round_up(std::min(b.MP, std::max(1, e->P)), 8)));
   int rpf = e->R;
   while (rpf > 1 && rpf * b.D * 4 > 8192) --rpf;
   b.vec_rows_per_flush = rpf;
-  const int stage_floats = std::max(rpf * b.D, b.Dg) + 8;
+  b.sel_k = std::min(b.K_p, e->P);
+  b.off_sel = take(2 * std::max(8, round_up(rpf * std::max(1, b.sel_k), 8)));
+  b.off_masks = take(4 * 10 * b.W32);
+  b.off_stage = off;
+  b.stage_b = round_up(6 * std::min(e->R, b.MR) + 12, 4);
+  const int stage_floats = std::max(rpf * b.D + 8, b.stage_b + 7 * std::min(e->P, b.MP) + 12);
   off = round_up(off + 4 * stage_floats, 16);
   b.smem_per_warp = off;
   if (b.smem_per_warp > 220 * 1024)
@@ -453,6 +460,7 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
     raw->d_maps = reinterpret_cast<MapDev*>(dbase + off_maps);
     b.maps = raw->d_maps;
     b.tq = reinterpret_cast<const float*>(dbase + off_tq);
+    b.cq = reinterpret_cast<const float*>(dbase + off_cq);
   }
   CUX(cudaMalloc(&raw->d_t, sizeof(int32_t) * n));
   CUX(cudaMalloc(&raw->d_ep, sizeof(int32_t) * n));
@@ -667,10 +675,10 @@ int32_t mdx_shaped_reward(mdx_env* e, const uint32_t* d_cur_robots, const int32_
   kp.global_reward = d_global_reward;
   kp.out_shaped = d_out;
   kp.n = e->n;
-  const int spw = e->base.off_stage;
+  const int spw = e->base.off_alist;
   const int wpb = pick_wpb(e, spw);
   kp.smem_per_warp = spw;
-  const size_t smem = (size_t)wpb * spw;
+  const size_t smem = (size_t)kLutBytes + (size_t)wpb * spw;
   CU(cudaFuncSetAttribute(mdx_shape_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
   mdx_shape_kernel<<<(unsigned)((e->n + wpb - 1) / wpb), wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(kp);
   CU(cudaGetLastError());

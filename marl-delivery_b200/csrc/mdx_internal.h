@@ -74,8 +74,11 @@ struct KParams {
   uint32_t mul_plane;    // ceil(2^32 / HW)       : e / HW        for e < 2^32 / HW
   uint32_t mul_wout;     // ceil(2^32 / W_out)    : cell / W_out
   // smem carve-up (bytes from the warp's base)
-  int32_t off_sched, off_status, off_wlist, off_wdl, off_alist, off_wkey, off_masks, off_rinfo, off_stage;
+  // step-only launches need [0, off_alist); the featuriser adds alist, sel, planes and the stage
+  int32_t off_sched, off_status, off_wlist, off_wkey, off_rinfo, off_alist, off_sel, off_masks, off_stage;
   int32_t smem_per_warp;
+  int32_t sel_k;      // min(K_p, P): selection slots per robot
+  int32_t stage_b;    // float offset of the gvec package segment inside the stage
   // rewards
   double move_cost, delivery_reward, delay_reward;
   float shaping[9];
@@ -93,6 +96,7 @@ struct KParams {
   const int32_t* env_map;  // [n_envs]
   const MapDev* maps;
   const float* tq;         // tq[k] = (float)((double)k / T)
+  const float* cq;         // cq[i] = (float)((double)i / (MR - 1)), i < 32 (MAPPO/helper.py:247)
   // call arguments
   const uint8_t* actions;
   const int32_t* env_ids;

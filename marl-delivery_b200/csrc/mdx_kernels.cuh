@@ -7,6 +7,12 @@
 // out of a shared-memory copy of the environment, and the feature tensors are written straight into
 // the caller's (torch-owned) HBM tensors with 128-bit coalesced streaming stores.
 //
+// The kernel is bound by HBM writes (19.9 KB of mostly-zero float32 per env-step for map1/5 robots)
+// and, below that, by instruction issue, so the code is organised to spend few warp-instructions per
+// output byte: 0/1 planes live as bit masks in shared memory and are expanded four cells at a time
+// through a 16-entry nibble -> float4 table; sparse rows (gvec) are flushed as "data prefix + zero
+// tail" segments; per-robot searches over packages run package-parallel with warp reductions.
+//
 // Exactness: integers everywhere except (a) the env reward, accumulated in float64 in the reference's
 // order (env.py:181,256,288-291), (b) the shaped reward, float32 adds in the reference's order of terms
 // plus numpy's pairwise float32 sum, and (c) feature quotients, which are host-built float32 tables
@@ -22,14 +28,17 @@
 namespace mdx {
 
 #define MDX_FULL 0xffffffffu
+#define MDX_NONE32 0xffffffffu
+constexpr int kLutBytes = 256;  // block-shared nibble -> float4 table at the start of dynamic smem
 
 struct Warp {
   uint16_t *start, *target, *t0, *dl;  // [Pp8] current episode schedule
   uint8_t* status;                     // [Pp16]
-  uint16_t *wlist, *wdl, *alist;       // compact waiting list (+ remaining-deadline), active list
+  uint16_t *wlist, *wrc, *wdl;         // compact waiting list: package index, start (r << 8 | c), remaining deadline
+  uint16_t *alist, *sel;               // active list (gvec); selected waiting-list indices per robot (vec)
   uint32_t* wkey;                      // per-robot selection keys of the waiting list
-  uint32_t* masks;                     // [3][W32] robots / waiting starts / active targets
-  uint16_t *rcell, *rcarry, *rtgt, *rdl;  // [32] per robot
+  uint32_t* planes;                    // [10][W32] grid, robots, waiting starts, active targets, 2 x (self, others, own target)
+  uint16_t *rcell, *rcarry, *rtgt, *rdl, *rrc;  // [32] per robot
   float* stage;                        // 16-byte aligned staging for vec / gvec rows
 };
 
@@ -41,38 +50,36 @@ __device__ __forceinline__ Warp carve(const KParams& p, unsigned char* base) {
   w.t0 = s + 2 * p.Pp8;
   w.dl = s + 3 * p.Pp8;
   w.status = base + p.off_status;
-  w.wlist = reinterpret_cast<uint16_t*>(base + p.off_wlist);
-  w.wdl = reinterpret_cast<uint16_t*>(base + p.off_wdl);
+  uint16_t* wl = reinterpret_cast<uint16_t*>(base + p.off_wlist);
+  w.wlist = wl;
+  w.wrc = wl + p.Pp8;
+  w.wdl = wl + 2 * p.Pp8;
   w.alist = reinterpret_cast<uint16_t*>(base + p.off_alist);
+  w.sel = reinterpret_cast<uint16_t*>(base + p.off_sel);
   w.wkey = reinterpret_cast<uint32_t*>(base + p.off_wkey);
-  w.masks = reinterpret_cast<uint32_t*>(base + p.off_masks);
+  w.planes = reinterpret_cast<uint32_t*>(base + p.off_masks);
   uint16_t* ri = reinterpret_cast<uint16_t*>(base + p.off_rinfo);
   w.rcell = ri;
   w.rcarry = ri + 32;
   w.rtgt = ri + 64;
   w.rdl = ri + 96;
+  w.rrc = ri + 128;
   w.stage = reinterpret_cast<float*>(base + p.off_stage);
   return w;
 }
 
-__device__ __forceinline__ float one_if(uint32_t bit) { return __uint_as_float((0u - (bit & 1u)) & 0x3f800000u); }
-
-__device__ __forceinline__ void st_stream4(float* ptr, float a, float b, float c, float d) {
-  __stcs(reinterpret_cast<float4*>(ptr), make_float4(a, b, c, d));
-}
-
 // max(0, deadline - t) / T  and  t / T  (MAPPO/helper.py:107,155,163): table of correctly rounded
 // float64 quotients, IEEE double division beyond the table (t keeps running past T).
+__device__ __noinline__ float tnorm_slow(int k, int T) { return __double2float_rn(__ddiv_rn((double)k, (double)T)); }
 __device__ __forceinline__ float tnorm(const KParams& p, int k) {
-  if (p.T <= 0) return 0.0f;
-  if (k < p.tq_len) return __ldg(p.tq + k);
-  return __double2float_rn(__ddiv_rn((double)k, (double)p.T));
+  if (k < p.tq_len) return __ldg(p.tq + k);  // tq is all zeros when T <= 0
+  return p.T > 0 ? tnorm_slow(k, p.T) : 0.0f;
 }
 
 __device__ __forceinline__ void load_episode(const KParams& p, const Warp& w, int env, int slot, int lane) {
   const uint4* src = reinterpret_cast<const uint4*>(p.sched + ((size_t)slot * p.n_envs + env) * 4 * p.Pp8);
   uint4* dst = reinterpret_cast<uint4*>(w.start);
-  const int n16 = p.Pp8 / 2;  // 4 rows * Pp8 u16 * 2 B / 16 B
+  const int n16 = p.Pp8 >> 1;  // 4 rows * Pp8 u16 * 2 B / 16 B
   for (int i = lane; i < n16; i += 32) dst[i] = __ldg(src + i);
 }
 
@@ -98,84 +105,137 @@ __device__ __forceinline__ float warp_np_sum(float v, int R) {
   return res;
 }
 
-// Copy n staged floats to global memory.  `stage` is 16-byte aligned and the row starts at
-// stage[off] with off == (global float index & 3), so shared and global addresses are congruent
-// modulo 16 bytes and the body moves as aligned float4.
-__device__ __forceinline__ void flush_row(float* gdst, const float* stage, int off, int n, int lane) {
+// Write n_total floats to global memory: the first n_data come from the staged row, the rest are
+// zeros.  `stage` is 16-byte aligned, the row starts at stage[off] with off == (global float index
+// & 3) so shared and global addresses are congruent modulo 16 bytes and the body moves as aligned
+// float4; the stage must be zero for at least 4 floats past n_data.
+__device__ __forceinline__ void flush_seg(float* gdst, const float* stage, int off, int n_data, int n_total, int lane) {
   const float* s = stage + off;
   int head = (4 - off) & 3;
-  if (head > n) head = n;
-  if (lane < head) __stcs(gdst + lane, s[lane]);
-  const int body = (n - head) >> 2;
+  if (head > n_total) head = n_total;
+  if (lane < head) __stcs(gdst + lane, lane < n_data ? s[lane] : 0.0f);
+  const int body = (n_total - head) >> 2;
   const float4* s4 = reinterpret_cast<const float4*>(s + head);
   float4* g4 = reinterpret_cast<float4*>(gdst + head);
-  for (int i = lane; i < body; i += 32) __stcs(g4 + i, s4[i]);
+  const int live = n_data > head ? (n_data - head + 3) >> 2 : 0;  // float4s that carry data
+  for (int i = lane; i < body; i += 32) __stcs(g4 + i, i < live ? s4[i] : make_float4(0.f, 0.f, 0.f, 0.f));
   const int done = head + (body << 2);
-  if (lane < n - done) __stcs(gdst + done + lane, s[done + lane]);
+  if (lane < n_total - done) __stcs(gdst + done + lane, done + lane < n_data ? s[done + lane] : 0.0f);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Shaped team reward of one transition (MAPPO/helper.py:257-369), evaluated by the warp that owns
-// the env.  Inputs per lane (robot): previous cell / carried id, new cell / carried id, decoded
-// action.  `nw` entries of w.wlist hold the packages that were 'waiting' (start_time <= t) in the
-// PREVIOUS state, in id order; w.status still holds the PREVIOUS statuses.
-__device__ __forceinline__ float shaped_team_reward(const KParams& p, const Warp& w, int lane, int t_prev,
-                                                    int t_cur, int cell0, int k0, int cell1, int k1, int mv,
-                                                    int op, int nw, double env_reward) {
-  const int R = p.R;
-  const bool active = lane < R;
-  float acc = 0.0f;
-  const int r0 = __umulhi((uint32_t)cell0, p.mul_wout), c0 = cell0 - r0 * p.W_out;
-  const int r1 = __umulhi((uint32_t)cell1, p.mul_wout), c1 = cell1 - r1 * p.W_out;
-  // one pass over the previous waiting list, lanes = robots
-  int best_d = 0x7fffffff, best_cell = -1;
-  bool idle_near = false, at_new = false;
-  for (int k = 0; k < nw; ++k) {
-    const int sc = w.start[w.wlist[k]];
-    const int sr = __umulhi((uint32_t)sc, p.mul_wout), scol = sc - sr * p.W_out;
-    const int d = abs(sr - r0) + abs(scol - c0);
-    if (d < best_d) {  // first minimum in id order, MAPPO/helper.py:346-349
-      best_d = d;
-      best_cell = sc;
+__device__ __forceinline__ void zero_stage(float* stage, int n_floats, int lane) {
+  float4* s4 = reinterpret_cast<float4*>(stage);
+  const int n4 = (n_floats + 3) >> 2;
+  for (int i = lane; i < n4; i += 32) s4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// Compact list of packages that are 'waiting' with start_time <= t, in id order: package index and
+// packed start position.  Returns the count.
+__device__ __forceinline__ int build_waiting(const KParams& p, const Warp& w, int lane, int t) {
+  int nw = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int base = 0; base < p.P; base += 32) {
+    const int j = base + lane;
+    const bool wait = j < p.P && w.status[j] == ST_WAITING && (int)w.t0[j] <= t;
+    const unsigned m = __ballot_sync(MDX_FULL, wait);
+    if (wait) {
+      const int k = nw + __popc(m & lt);
+      const uint32_t sc = w.start[j];
+      const uint32_t sr = __umulhi(sc, p.mul_wout);
+      w.wlist[k] = (uint16_t)j;
+      w.wrc[k] = (uint16_t)((sr << 8) | (sc - sr * p.W_out));
     }
-    idle_near |= (d <= 3);
-    at_new |= (sc == cell1);
+    nw += __popc(m);
   }
-  if (active) {
+  __syncwarp();
+  return nw;
+}
+
+struct Scan {
+  uint32_t best;   // (manhattan distance << 16 | list index) of the nearest waiting start, first minimum in id order
+  uint32_t at_new; // lowest list index whose start is the robot's NEW cell, MDX_NONE32 if none
+  bool near;       // some waiting start within manhattan distance 3 of the OLD cell
+};
+
+// For every robot: nearest waiting package from its old cell (MAPPO/helper.py:346-349), "waiting
+// package within 3" (:360-365) and the lowest-id waiting package on its new cell (env.py:267-274,
+// MAPPO/helper.py:312-317).  Package-parallel: lanes own list entries, one warp reduction per robot.
+__device__ __forceinline__ Scan scan_waiting(const Warp& w, int lane, int R, int nw, int r0, int c0, int r1, int c1) {
+  Scan mine{MDX_NONE32, MDX_NONE32, false};
+  if (nw == 0) return mine;
+  const uint32_t rc1 = ((uint32_t)r1 << 8) | (uint32_t)c1;
+  for (int i = 0; i < R; ++i) {
+    const int ri = __shfl_sync(MDX_FULL, r0, i), ci = __shfl_sync(MDX_FULL, c0, i);
+    const uint32_t rci = __shfl_sync(MDX_FULL, rc1, i);
+    uint32_t best = MDX_NONE32, at_new = MDX_NONE32;
+    bool near = false;
+    for (int k = lane; k < nw; k += 32) {
+      const uint32_t rc = w.wrc[k];
+      const int d = abs((int)(rc >> 8) - ri) + abs((int)(rc & 255u) - ci);
+      best = min(best, ((uint32_t)d << 16) | (uint32_t)k);
+      near |= d <= 3;
+      if (rc == rci) at_new = min(at_new, (uint32_t)k);
+    }
+    best = __reduce_min_sync(MDX_FULL, best);
+    at_new = __reduce_min_sync(MDX_FULL, at_new);
+    near = __any_sync(MDX_FULL, near);
+    if (lane == i) {
+      mine.best = best;
+      mine.at_new = at_new;
+      mine.near = near;
+    }
+  }
+  return mine;
+}
+
+// Shaped team reward of one transition (MAPPO/helper.py:257-369).  Per lane (robot): old / new
+// position and carried id, decoded action, the scan above; w.status still holds the PREVIOUS statuses.
+__device__ __forceinline__ float shaped_team_reward(const KParams& p, const Warp& w, int lane, int t_cur, int r0, int c0,
+                                                    int k0, int r1, int c1, int k1, int mv, int op, int nw,
+                                                    const Scan& sc, double env_reward) {
+  float acc = 0.0f;
+  if (lane < p.R) {
     const uint8_t st0 = k0 ? w.status[k0 - 1] : (uint8_t)ST_NONE;
     const bool tracked = k0 != 0 && (st0 == ST_WAITING || st0 == ST_IN_TRANSIT);
-    const int tgt0 = k0 ? (int)w.target[k0 - 1] : -1;
-    const int dl0 = k0 ? (int)w.dl[k0 - 1] : 0;
+    int gr = -1, gc = 0, dl0 = 0;
+    if (k0) {
+      const uint32_t tg = w.target[k0 - 1];
+      gr = (int)__umulhi(tg, p.mul_wout);
+      gc = (int)tg - gr * p.W_out;
+      dl0 = w.dl[k0 - 1];
+    }
+    const bool at_target = k0 != 0 && r1 == gr && c1 == gc;
     // 1. successful pickup / delivery (:295-305)
     if (k0 == 0 && k1 != 0) {
       acc = __fadd_rn(acc, p.shaping[0]);
     } else if (k0 != 0 && k1 == 0) {
-      if (tracked && cell1 == tgt0) acc = __fadd_rn(acc, (t_cur <= dl0) ? p.shaping[1] : p.shaping[2]);
+      if (tracked && at_target) acc = __fadd_rn(acc, (t_cur <= dl0) ? p.shaping[1] : p.shaping[2]);
     }
     // 2. wasted package ops (:308-327)
     if (op == 1) {
       if (k0 != 0) {
         acc = __fadd_rn(acc, p.shaping[4]);
       } else if (k1 == 0) {
-        if (!at_new) acc = __fadd_rn(acc, p.shaping[4]);
+        if (sc.at_new == MDX_NONE32) acc = __fadd_rn(acc, p.shaping[4]);
       }
     } else if (op == 2) {
       if (k0 == 0) {
         acc = __fadd_rn(acc, p.shaping[5]);
       } else if (k1 != 0) {
-        if (tracked && cell1 != tgt0) acc = __fadd_rn(acc, p.shaping[5]);
+        if (tracked && !at_target) acc = __fadd_rn(acc, p.shaping[5]);
       }
     }
     // 3. movement (:330-356)
-    const bool moved = cell0 != cell1;
+    const bool moved = r0 != r1 || c0 != c1;
     if (mv != MV_S && !moved) acc = __fadd_rn(acc, p.shaping[6]);
-    int goal = -1;
-    if (tracked)
-      goal = tgt0;
-    else if (nw > 0)
-      goal = best_cell;
-    if (goal >= 0 && moved) {
-      const int gr = __umulhi((uint32_t)goal, p.mul_wout), gc = goal - gr * p.W_out;
+    bool have_goal = tracked;
+    if (!tracked && nw > 0) {  // nearest waiting start, first minimum in id order
+      const uint32_t rc = w.wrc[sc.best & 0xffffu];
+      gr = (int)(rc >> 8);
+      gc = (int)(rc & 255u);
+      have_goal = true;
+    }
+    if (have_goal && moved) {
       const int d_before = abs(r0 - gr) + abs(c0 - gc);
       const int d_after = abs(r1 - gr) + abs(c1 - gc);
       if (d_after < d_before)
@@ -184,76 +244,86 @@ __device__ __forceinline__ float shaped_team_reward(const KParams& p, const Warp
         acc = __fadd_rn(acc, p.shaping[8]);
     }
     // 4. idle next to work (:359-367)
-    if (!moved && mv == MV_S && k0 == 0 && idle_near) acc = __fadd_rn(acc, p.shaping[7]);
+    if (!moved && mv == MV_S && k0 == 0 && sc.near) acc = __fadd_rn(acc, p.shaping[7]);
   }
-  (void)t_prev;
-  const float s = warp_np_sum(acc, R);
+  const float s = warp_np_sum(acc, p.R);
   // python float + np.float32 -> float32 under numpy >= 2
   return __fadd_rn(__double2float_rn(env_reward), s);
 }
 
-// Compact list of packages that are 'waiting' with start_time <= t, in id order.  Returns the count.
-__device__ __forceinline__ int build_waiting(const KParams& p, const Warp& w, int lane, int t) {
-  int nw = 0;
-  const unsigned lt = (1u << lane) - 1u;
-  for (int base = 0; base < p.P; base += 32) {
-    const int j = base + lane;
-    const bool wait = j < p.P && w.status[j] == ST_WAITING && (int)w.t0[j] <= t;
-    const unsigned m = __ballot_sync(MDX_FULL, wait);
-    if (wait) w.wlist[nw + __popc(m & lt)] = (uint16_t)j;
-    nw += __popc(m);
+__device__ __forceinline__ void decode_action(int a, int& mv, int& op) {
+  if (a < 15) {
+    mv = a % 5;
+    op = a / 5;
+  } else if (a < 18) {
+    mv = MV_BAD;
+    op = a - 15;
+  } else {
+    mv = MV_BAD;
+    op = 0;
   }
-  __syncwarp();
-  return nw;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Featurisation of the env held in shared memory (statuses, schedule) and registers (cell / carry of
 // robot `lane`), MAPPO/helper.py:6-255.  `row` selects the output row.
-__device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, const MapDev& map, int lane,
-                                              int row, int t, int cell, int carry) {
+__device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, const float4* lut, const MapDev& map,
+                                              int lane, int row, int t, int cell, int carry) {
   const int R = p.R, P = p.P, W32 = p.W32, HW = p.HW, Wo = p.W_out;
   const int Hm1 = p.H_out - 1, Wm1 = p.W_out - 1, NC = 2 * p.W_out - 1;
   const unsigned lt = (1u << lane) - 1u;
   const bool active = lane < R;
   const int r = active ? (int)__umulhi((uint32_t)cell, p.mul_wout) : 0;
   const int c = active ? cell - r * Wo : 0;
+  const float* qr = map.qr;
+  const float* qc = map.qc;
 
-  // ---- per-robot info + plane masks ----------------------------------------------------------
+  // ---- per-robot info, shared planes, waiting / active lists -----------------------------------
   bool carrying_it = false;
-  int own_tgt = 0xFFFF, own_rem = 0;
+  int own_tgt = 0xFFFF, own_rem = 0, tr_own = 0, tc_own = 0;
   if (active) {
     if (carry != 0 && w.status[carry - 1] == ST_IN_TRANSIT) {
       carrying_it = true;
       own_tgt = w.target[carry - 1];
       own_rem = max(0, (int)w.dl[carry - 1] - t);
+      tr_own = (int)__umulhi((uint32_t)own_tgt, p.mul_wout);
+      tc_own = own_tgt - tr_own * Wo;
     }
     w.rcell[lane] = (uint16_t)cell;
     w.rcarry[lane] = (uint16_t)carry;
     w.rtgt[lane] = (uint16_t)own_tgt;
     w.rdl[lane] = (uint16_t)own_rem;
+    w.rrc[lane] = (uint16_t)((r << 8) | c);
   }
-  for (int i = lane; i < 3 * W32; i += 32) w.masks[i] = 0u;
+  for (int i = lane; i < W32; i += 32) {
+    w.planes[i] = __ldg(map.grid_bits + i);
+    w.planes[W32 + i] = 0u;
+    w.planes[2 * W32 + i] = 0u;
+    w.planes[3 * W32 + i] = 0u;
+  }
   __syncwarp();
-  if (active) atomicOr(&w.masks[cell >> 5], 1u << (cell & 31));
+  if (active) atomicOr(&w.planes[W32 + (cell >> 5)], 1u << (cell & 31));
   int nw = 0, na = 0;
   for (int base = 0; base < P; base += 32) {
     const int j = base + lane;
     const uint8_t st = j < P ? w.status[j] : (uint8_t)ST_NONE;
     const bool wait = j < P && st == ST_WAITING && (int)w.t0[j] <= t;
     const bool act = wait || (j < P && st == ST_IN_TRANSIT);
+    uint32_t sc = 0;
     if (wait) {
-      const int sc = w.start[j];
-      atomicOr(&w.masks[W32 + (sc >> 5)], 1u << (sc & 31));
+      sc = w.start[j];
+      atomicOr(&w.planes[2 * W32 + (sc >> 5)], 1u << (sc & 31));
     }
     if (act) {
       const int tc = w.target[j];
-      atomicOr(&w.masks[2 * W32 + (tc >> 5)], 1u << (tc & 31));
+      atomicOr(&w.planes[3 * W32 + (tc >> 5)], 1u << (tc & 31));
     }
     const unsigned wm = __ballot_sync(MDX_FULL, wait), am = __ballot_sync(MDX_FULL, act);
     if (wait) {
       const int k = nw + __popc(wm & lt);
+      const uint32_t sr = __umulhi(sc, p.mul_wout);
       w.wlist[k] = (uint16_t)j;
+      w.wrc[k] = (uint16_t)((sr << 8) | (sc - sr * Wo));
       w.wdl[k] = (uint16_t)max(0, (int)w.dl[j] - t);
     }
     if (act) {
@@ -265,232 +335,211 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
   }
   __syncwarp();
 
-  const uint32_t* gridb = map.grid_bits;
-  const uint32_t* m_rob = w.masks;
-  const uint32_t* m_ws = w.masks + W32;
-  const uint32_t* m_at = w.masks + 2 * W32;
-
-  // ---- obs [R,6,H,W] and gstate [4,H,W] ------------------------------------------------------
-  if ((HW & 3) == 0) {
-    // fast path: planes are whole float4s; 4 consecutive cells never straddle a mask word
-    if (p.obs != nullptr) {
-      const int n4 = (6 * HW) >> 2;
-      for (int i = 0; i < R; ++i) {
-        float* out = p.obs + ((size_t)row * R + i) * 6 * HW;
-        const uint32_t rc = w.rcell[i], tg = w.rtgt[i];
-        for (int q = lane; q < n4; q += 32) {
-          const uint32_t e = (uint32_t)q << 2;
-          const uint32_t ch = __umulhi(e, p.mul_plane);
-          const uint32_t cl = e - ch * HW;
-          const uint32_t wi = cl >> 5, sh = cl & 31u;
-          const uint32_t oh_r = ((rc >> 2) == (cl >> 2)) ? (1u << (rc & 3u)) : 0u;
-          const uint32_t oh_t = ((tg >> 2) == (cl >> 2)) ? (1u << (tg & 3u)) : 0u;
-          uint32_t nib;
-          if (ch == 0)
-            nib = (__ldg(gridb + wi) >> sh) & 15u;
-          else if (ch == 1)
-            nib = oh_r;
-          else if (ch == 2)
-            nib = ((m_rob[wi] >> sh) & 15u) & ~oh_r;
-          else if (ch == 3)
-            nib = (m_ws[wi] >> sh) & 15u;
-          else if (ch == 4)
-            nib = (m_at[wi] >> sh) & 15u;
-          else
-            nib = oh_t;
-          st_stream4(out + e, one_if(nib), one_if(nib >> 1), one_if(nib >> 2), one_if(nib >> 3));
-        }
-      }
-    }
-    if (p.gstate != nullptr) {
-      float* out = p.gstate + (size_t)row * 4 * HW;
-      const int n4 = HW;  // 4 planes * HW / 4
-      for (int q = lane; q < n4; q += 32) {
+  // ---- gstate [4,H,W]: planes 0..3 are exactly its channels --------------------------------------
+  if (p.gstate != nullptr) {
+    float* out = p.gstate + (size_t)row * 4 * HW;
+    if ((HW & 3) == 0) {
+      float4* out4 = reinterpret_cast<float4*>(out);
+      for (int q = lane; q < HW; q += 32) {  // 4 planes * HW / 4 float4s
         const uint32_t e = (uint32_t)q << 2;
         const uint32_t ch = __umulhi(e, p.mul_plane);
         const uint32_t cl = e - ch * HW;
-        const uint32_t wi = cl >> 5, sh = cl & 31u;
-        uint32_t word;
-        if (ch == 0)
-          word = __ldg(gridb + wi);
-        else if (ch == 1)
-          word = m_rob[wi];
-        else if (ch == 2)
-          word = m_ws[wi];
-        else
-          word = m_at[wi];
-        const uint32_t nib = (word >> sh) & 15u;
-        st_stream4(out + e, one_if(nib), one_if(nib >> 1), one_if(nib >> 2), one_if(nib >> 3));
+        const uint32_t nib = (w.planes[ch * W32 + (cl >> 5)] >> (cl & 31u)) & 15u;
+        __stcs(out4 + q, lut[nib]);
       }
-    }
-  } else {
-    // generic path (e.g. the 7x7 map): one coalesced scalar store per element
-    if (p.obs != nullptr) {
-      const int n = 6 * HW;
-      for (int i = 0; i < R; ++i) {
-        float* out = p.obs + ((size_t)row * R + i) * 6 * HW;
-        const uint32_t rc = w.rcell[i], tg = w.rtgt[i];
-        for (int e = lane; e < n; e += 32) {
-          const uint32_t ch = __umulhi((uint32_t)e, p.mul_plane);
-          const uint32_t cl = (uint32_t)e - ch * HW;
-          const uint32_t wi = cl >> 5, sh = cl & 31u;
-          uint32_t b;
-          if (ch == 0)
-            b = __ldg(gridb + wi) >> sh;
-          else if (ch == 1)
-            b = (rc == cl);
-          else if (ch == 2)
-            b = (m_rob[wi] >> sh) & (rc != cl ? 1u : 0u);
-          else if (ch == 3)
-            b = m_ws[wi] >> sh;
-          else if (ch == 4)
-            b = m_at[wi] >> sh;
-          else
-            b = (tg == cl);
-          __stcs(out + e, one_if(b));
-        }
-      }
-    }
-    if (p.gstate != nullptr) {
-      float* out = p.gstate + (size_t)row * 4 * HW;
-      const int n = 4 * HW;
-      for (int e = lane; e < n; e += 32) {
+    } else {
+      for (int e = lane; e < 4 * HW; e += 32) {
         const uint32_t ch = __umulhi((uint32_t)e, p.mul_plane);
         const uint32_t cl = (uint32_t)e - ch * HW;
-        const uint32_t wi = cl >> 5, sh = cl & 31u;
-        uint32_t word;
-        if (ch == 0)
-          word = __ldg(gridb + wi);
-        else if (ch == 1)
-          word = m_rob[wi];
-        else if (ch == 2)
-          word = m_ws[wi];
-        else
-          word = m_at[wi];
-        __stcs(out + e, one_if(word >> sh));
+        __stcs(out + e, ((w.planes[ch * W32 + (cl >> 5)] >> (cl & 31u)) & 1u) ? 1.0f : 0.0f);
       }
     }
   }
 
-  const float* qr = map.qr;
-  const float* qc = map.qc;
+  // ---- obs [R,6,H,W]: per robot three private planes (self, others, own target), double-buffered --
+  if (p.obs != nullptr) {
+    for (int i = 0; i < R; ++i) {
+      const int b = 4 + 3 * (i & 1);
+      const uint32_t rc = w.rcell[i], tg = w.rtgt[i];
+      for (int x = lane; x < W32; x += 32) {
+        const uint32_t self = ((rc >> 5) == (uint32_t)x) ? (1u << (rc & 31u)) : 0u;
+        w.planes[b * W32 + x] = self;
+        w.planes[(b + 1) * W32 + x] = w.planes[W32 + x] & ~self;
+        w.planes[(b + 2) * W32 + x] = ((tg >> 5) == (uint32_t)x) ? (1u << (tg & 31u)) : 0u;  // tg = 0xFFFF: no plane word matches
+      }
+      __syncwarp();
+      // channel -> plane: 0 grid, 1 self, 2 others, 3 waiting starts, 4 active targets, 5 own target
+      const uint32_t pmap = 0u | ((uint32_t)b << 4) | ((uint32_t)(b + 1) << 8) | (2u << 12) | (3u << 16) | ((uint32_t)(b + 2) << 20);
+      float* out = p.obs + ((size_t)row * R + i) * 6 * HW;
+      if ((HW & 3) == 0) {
+        float4* out4 = reinterpret_cast<float4*>(out);
+        const int n4 = (6 * HW) >> 2;
+        for (int q = lane; q < n4; q += 32) {
+          const uint32_t e = (uint32_t)q << 2;
+          const uint32_t ch = __umulhi(e, p.mul_plane);
+          const uint32_t cl = e - ch * HW;
+          const uint32_t pl = (pmap >> (ch << 2)) & 15u;
+          const uint32_t nib = (w.planes[pl * W32 + (cl >> 5)] >> (cl & 31u)) & 15u;
+          __stcs(out4 + q, lut[nib]);
+        }
+      } else {
+        for (int e = lane; e < 6 * HW; e += 32) {
+          const uint32_t ch = __umulhi((uint32_t)e, p.mul_plane);
+          const uint32_t cl = (uint32_t)e - ch * HW;
+          const uint32_t pl = (pmap >> (ch << 2)) & 15u;
+          __stcs(out + e, ((w.planes[pl * W32 + (cl >> 5)] >> (cl & 31u)) & 1u) ? 1.0f : 0.0f);
+        }
+      }
+    }
+  }
 
   // ---- vec [R, D]  (generate_vector_features, MAPPO/helper.py:68-165) -------------------------
   if (p.vec != nullptr) {
-    const int D = p.D, K_o = p.K_o, K_p = p.K_p;
+    const int D = p.D, K_o = p.K_o, Ksel = p.sel_k;
     const float tfrac = tnorm(p, t);
-    // the two "target relative to the carrier itself" entries of an other-robot row (:125-136)
+    // an other-robot row ends with "target relative to the carrier itself" (:125-136)
     float ot_r = 0.0f, ot_c = 0.0f;
     if (carrying_it) {
-      const int tr = __umulhi((uint32_t)own_tgt, p.mul_wout), tc = own_tgt - tr * Wo;
-      ot_r = __ldg(qr + (tr - r + Hm1));
-      ot_c = __ldg(qc + (tc - c + Wm1));
+      ot_r = __ldg(qr + (tr_own - r + Hm1));
+      ot_c = __ldg(qc + (tc_own - c + Wm1));
     }
+    const float cflag = carry != 0 ? 1.0f : 0.0f;
     const uint32_t wmask = (1u << p.key_wbits) - 1u;
+    const int nsel = min(Ksel, nw);
     const int rpf = p.vec_rows_per_flush;
+    // lanes as (robot, other) pairs for the stable sort of the other robots
+    const int G = 32 / R;                 // robots per pass
+    const int gi = lane / R, gj = lane - gi * R;
     for (int i0 = 0; i0 < R; i0 += rpf) {
       const int nrows = min(rpf, R - i0);
       const size_t g0 = ((size_t)row * R + i0) * D;
       const int off = (int)(g0 & 3);
-      for (int x = lane; x < nrows * D + 4; x += 32) w.stage[x] = 0.0f;
+      zero_stage(w.stage, nrows * D + 4, lane);
       __syncwarp();
-      for (int i = i0; i < i0 + nrows; ++i) {
-        float* rowp = w.stage + off + (i - i0) * D;
-        const int ri = __shfl_sync(MDX_FULL, r, i), ci = __shfl_sync(MDX_FULL, c, i);
-        if (lane == i) {  // own block (:93-112) and global time (:163)
-          rowp[0] = __ldg(qr + (r + Hm1));
-          rowp[1] = __ldg(qc + (c + Wm1));
-          rowp[2] = carry != 0 ? 1.0f : 0.0f;
-          if (carrying_it) {
-            const int tr = __umulhi((uint32_t)own_tgt, p.mul_wout), tc = own_tgt - tr * Wo;
-            rowp[3] = __ldg(qr + (tr - r + Hm1));
-            rowp[4] = __ldg(qc + (tc - c + Wm1));
-            rowp[5] = tnorm(p, own_rem);
+      float* chunk = w.stage + off;
+      // own block (:93-112) and global time (:163)
+      if (lane >= i0 && lane < i0 + nrows) {
+        float* rowp = chunk + (lane - i0) * D;
+        rowp[0] = __ldg(qr + (r + Hm1));
+        rowp[1] = __ldg(qc + (c + Wm1));
+        rowp[2] = cflag;
+        if (carrying_it) {
+          rowp[3] = __ldg(qr + (tr_own - r + Hm1));
+          rowp[4] = __ldg(qc + (tc_own - c + Wm1));
+          rowp[5] = tnorm(p, own_rem);
+        }
+        rowp[D - 1] = tfrac;
+      }
+      // other robots, stable-sorted by the float64 key rank (:115-141)
+      if (K_o > 0 && R > 1) {
+        for (int ib = i0; ib < i0 + nrows; ib += G) {
+          const int i = ib + gi;
+          const bool valid = gi < G && i < i0 + nrows && gj != i;
+          uint32_t okey = MDX_NONE32;
+          int dr = 0, dc = 0;
+          if (valid) {
+            const uint32_t rci = w.rrc[i], rcj = w.rrc[gj];
+            dr = (int)(rcj >> 8) - (int)(rci >> 8);
+            dc = (int)(rcj & 255u) - (int)(rci & 255u);
+            okey = ((uint32_t)__ldg(map.rank + (dr + Hm1) * NC + (dc + Wm1)) << 5) | (uint32_t)gj;
           }
-          rowp[D - 1] = tfrac;
+          int pos = 0;
+          for (int k = 0; k < R; ++k) pos += (__shfl_sync(MDX_FULL, okey, gi * R + k) < okey) ? 1 : 0;
+          const float cf_j = __shfl_sync(MDX_FULL, cflag, gj);
+          const float otr_j = __shfl_sync(MDX_FULL, ot_r, gj), otc_j = __shfl_sync(MDX_FULL, ot_c, gj);
+          if (valid && pos < K_o) {
+            float* o = chunk + (i - i0) * D + 6 + pos * 5;
+            o[0] = __ldg(qr + (dr + Hm1));
+            o[1] = __ldg(qc + (dc + Wm1));
+            o[2] = cf_j;
+            o[3] = otr_j;
+            o[4] = otc_j;
+          }
         }
-        // other robots, stable-sorted by the float64 key rank (:115-141)
-        const int dr = r - ri, dc = c - ci;
-        uint32_t okey = 0xffffffffu;
-        if (active && lane != i) okey = ((uint32_t)__ldg(map.rank + (dr + Hm1) * NC + (dc + Wm1)) << 5) | (uint32_t)lane;
-        int pos = 0;
-        for (int k = 0; k < R; ++k) pos += (__shfl_sync(MDX_FULL, okey, k) < okey) ? 1 : 0;
-        if (active && lane != i && pos < K_o) {
-          float* o = rowp + 6 + pos * 5;
-          o[0] = __ldg(qr + (dr + Hm1));
-          o[1] = __ldg(qc + (dc + Wm1));
-          o[2] = carry != 0 ? 1.0f : 0.0f;
-          o[3] = ot_r;
-          o[4] = ot_c;
-        }
-        // waiting packages, stable-sorted by (remaining deadline, key rank) (:143-160): repeated
-        // warp arg-min over 32-bit keys (rem * nranks + rank) << wbits | list index
-        const int nsel = min(K_p, nw);
-        if (nsel > 0) {
-          uint32_t lm = 0xffffffffu;
+      }
+      // waiting packages, stable-sorted by (remaining deadline, key rank) (:143-160): per robot a
+      // repeated warp arg-min over 32-bit keys (rem * nranks + rank) << wbits | list index records
+      // the winners; the rows are written afterwards, one lane per (robot, slot)
+      if (nsel > 0) {
+        for (int i = i0; i < i0 + nrows; ++i) {
+          const uint32_t rci = w.rrc[i];
+          const int ri = (int)(rci >> 8), ci = (int)(rci & 255u);
+          uint32_t lm = MDX_NONE32;
           for (int k = lane; k < nw; k += 32) {
-            const int sc = w.start[w.wlist[k]];
-            const int sr = __umulhi((uint32_t)sc, p.mul_wout), scol = sc - sr * Wo;
-            const uint32_t rk = __ldg(map.rank + (sr - ri + Hm1) * NC + (scol - ci + Wm1));
+            const uint32_t rc = w.wrc[k];
+            const uint32_t rk = __ldg(map.rank + ((int)(rc >> 8) - ri + Hm1) * NC + ((int)(rc & 255u) - ci + Wm1));
             const uint32_t key = (((uint32_t)w.wdl[k] * (uint32_t)p.nranks_max + rk) << p.key_wbits) | (uint32_t)k;
             w.wkey[k] = key;
             lm = min(lm, key);
           }
+          uint16_t* selp = w.sel + (i - i0) * Ksel;
           for (int q = 0; q < nsel; ++q) {
             const uint32_t best = __reduce_min_sync(MDX_FULL, lm);
             if (lm == best) {  // exactly one lane: keys are unique
-              const int k = (int)(best & wmask);
-              const int j = w.wlist[k];
-              const int sc = w.start[j], tc_ = w.target[j];
-              const int sr = __umulhi((uint32_t)sc, p.mul_wout), scol = sc - sr * Wo;
-              const int tr = __umulhi((uint32_t)tc_, p.mul_wout), tcol = tc_ - tr * Wo;
-              float* o = rowp + 6 + K_o * 5 + q * 5;
-              o[0] = __ldg(qr + (sr - ri + Hm1));
-              o[1] = __ldg(qc + (scol - ci + Wm1));
-              o[2] = __ldg(qr + (tr - ri + Hm1));
-              o[3] = __ldg(qc + (tcol - ci + Wm1));
-              o[4] = tnorm(p, (int)w.wdl[k]);
-              w.wkey[k] = 0xffffffffu;
-              lm = 0xffffffffu;
+              const uint32_t k = best & wmask;
+              selp[q] = (uint16_t)k;
+              w.wkey[k] = MDX_NONE32;
+              lm = MDX_NONE32;
               for (int kk = lane; kk < nw; kk += 32) lm = min(lm, w.wkey[kk]);
             }
           }
         }
+        __syncwarp();
+        const int nslot = nrows * nsel;
+        for (int x = lane; x < nslot; x += 32) {
+          const int ii = x / nsel, q = x - ii * nsel;
+          const uint32_t rci = w.rrc[i0 + ii];
+          const int ri = (int)(rci >> 8), ci = (int)(rci & 255u);
+          const int k = w.sel[ii * Ksel + q];
+          const int j = w.wlist[k];
+          const uint32_t rc = w.wrc[k];
+          const uint32_t tc_ = w.target[j];
+          const int tr = (int)__umulhi(tc_, p.mul_wout), tcol = (int)tc_ - tr * Wo;
+          float* o = chunk + ii * D + 6 + K_o * 5 + q * 5;
+          o[0] = __ldg(qr + ((int)(rc >> 8) - ri + Hm1));
+          o[1] = __ldg(qc + ((int)(rc & 255u) - ci + Wm1));
+          o[2] = __ldg(qr + (tr - ri + Hm1));
+          o[3] = __ldg(qc + (tcol - ci + Wm1));
+          o[4] = tnorm(p, (int)w.wdl[k]);
+        }
       }
       __syncwarp();
-      flush_row(p.vec + g0, w.stage, off, nrows * D, lane);
+      flush_seg(p.vec + g0, w.stage, off, nrows * D, nrows * D, lane);
       __syncwarp();
     }
   }
 
   // ---- gvec [Dg]  (convert_global_state vector part, MAPPO/helper.py:199-255) ------------------
+  // three segments: robots (6*MR floats, first 6*min(R,MR) carry data), packages (7*MP floats, first
+  // 7*min(n_active,MP) carry data), global time.  Only the data prefixes are staged.
   if (p.gvec != nullptr) {
     const int Dg = p.Dg, MR = p.MR, MP = p.MP;
-    const size_t g0 = (size_t)row * Dg;
-    const int off = (int)(g0 & 3);
-    for (int x = lane; x < Dg + 4; x += 32) w.stage[x] = 0.0f;
+    const size_t gA = (size_t)row * Dg, gB = gA + 6 * (size_t)MR;
+    const int offA = (int)(gA & 3), offB = (int)(gB & 3);
+    const int nA = 6 * min(R, MR), nrow = min(na, MP), nB = 7 * nrow;
+    float* stA = w.stage;
+    float* stB = w.stage + p.stage_b;
+    zero_stage(stA, nA + 8, lane);
+    zero_stage(stB, nB + 8, lane);
     __syncwarp();
-    float* g = w.stage + off;
     if (active && lane < MR) {
-      float* o = g + lane * 6;
+      float* o = stA + offA + lane * 6;
       o[0] = __ldg(qr + (r + Hm1));
       o[1] = __ldg(qc + (c + Wm1));
       o[2] = carry != 0 ? 1.0f : 0.0f;
       if (carrying_it) {
-        const int tr = __umulhi((uint32_t)own_tgt, p.mul_wout), tc = own_tgt - tr * Wo;
-        o[3] = __ldg(qr + (tr + Hm1));
-        o[4] = __ldg(qc + (tc + Wm1));
+        o[3] = __ldg(qr + (tr_own + Hm1));
+        o[4] = __ldg(qc + (tc_own + Wm1));
         o[5] = tnorm(p, own_rem);
       }
     }
-    const int nrow = min(na, MP);
     for (int k = lane; k < nrow; k += 32) {
       const int j = w.alist[k];
       const bool wait = w.status[j] == ST_WAITING;
-      const int sc = w.start[j], tc_ = w.target[j];
-      const int sr = __umulhi((uint32_t)sc, p.mul_wout), scol = sc - sr * Wo;
-      const int tr = __umulhi((uint32_t)tc_, p.mul_wout), tcol = tc_ - tr * Wo;
-      float* o = g + 6 * MR + 7 * k;
+      const uint32_t sc = w.start[j], tc_ = w.target[j];
+      const int sr = (int)__umulhi(sc, p.mul_wout), scol = (int)sc - sr * Wo;
+      const int tr = (int)__umulhi(tc_, p.mul_wout), tcol = (int)tc_ - tr * Wo;
+      float* o = stB + offB + 7 * k;
       if (wait) {
         o[0] = __ldg(qr + (sr + Hm1));
         o[1] = __ldg(qc + (scol + Wm1));
@@ -503,15 +552,16 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
       if (!wait) {
         for (int ridx = 0; ridx < R; ++ridx)
           if ((int)w.rcarry[ridx] == j + 1) {
-            cn = MR > 1 ? __double2float_rn(__ddiv_rn((double)ridx, (double)(MR - 1))) : 0.0f;
+            cn = __ldg(p.cq + ridx);  // ridx / (MR - 1), or 0 when MR <= 1
             break;
           }
       }
       o[6] = cn;
     }
-    if (lane == 0) g[Dg - 1] = tnorm(p, t);
     __syncwarp();
-    flush_row(p.gvec + g0, w.stage, off, Dg, lane);
+    flush_seg(p.gvec + gA, stA, offA, nA, 6 * MR, lane);
+    flush_seg(p.gvec + gB, stB, offB, nB, 7 * MP, lane);
+    if (lane == 0) __stcs(p.gvec + gA + Dg - 1, tnorm(p, t));
     __syncwarp();
   }
 }
@@ -519,13 +569,22 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
 // ------------------------------------------------------------------------------------------------
 // kMode bit 0: step (+ shaped reward, + optional auto-reset);  bit 1: featurise.
 template <int kMode>
-__global__ void __launch_bounds__(256) mdx_env_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(128, (kMode & 2) ? 7 : 8) mdx_env_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const float4* lut = reinterpret_cast<const float4*>(smem_raw);
+  if (kMode & 2) {
+    if (threadIdx.x < 16) {
+      const unsigned n = threadIdx.x;
+      reinterpret_cast<float4*>(smem_raw)[n] =
+          make_float4((n & 1u) ? 1.f : 0.f, (n & 2u) ? 1.f : 0.f, (n & 4u) ? 1.f : 0.f, (n & 8u) ? 1.f : 0.f);
+    }
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int widx = blockIdx.x * (blockDim.x >> 5) + wib;
   if (widx >= p.n) return;
-  const Warp w = carve(p, smem_raw + (size_t)wib * p.smem_per_warp);
+  const Warp w = carve(p, smem_raw + kLutBytes + (size_t)wib * p.smem_per_warp);
   const int env = p.env_ids ? __ldg(p.env_ids + widx) : widx;
   const int R = p.R, P = p.P, Wo = p.W_out;
   const bool active = lane < R;
@@ -546,18 +605,8 @@ __global__ void __launch_bounds__(256) mdx_env_kernel(const __grid_constant__ KP
 
   if (kMode & 1) {
     // ---------------- decode ----------------
-    const int a = active ? (int)__ldg(p.actions + (size_t)widx * R + lane) : 3;
     int mv, op;
-    if (a < 15) {
-      mv = a % 5;
-      op = a / 5;
-    } else if (a < 18) {
-      mv = MV_BAD;
-      op = a - 15;
-    } else {
-      mv = MV_BAD;
-      op = 0;
-    }
+    decode_action(active ? (int)__ldg(p.actions + (size_t)widx * R + lane) : 3, mv, op);
     // ---------------- proposals (env.py:193-201) ----------------
     const int r = active ? (int)__umulhi((uint32_t)cell, p.mul_wout) : 0;
     const int c = active ? cell - r * Wo : 0;
@@ -589,18 +638,16 @@ __global__ void __launch_bounds__(256) mdx_env_kernel(const __grid_constant__ KP
     }
     const bool moved = (mm >> lane) & 1u;
     const int cell1 = moved ? tgt : cell;
+    const int r1 = moved ? nr : r, c1 = moved ? nc : c;
     const int n_moved = __popc(mm);  // every mover used one of L/R/U/D (env.py:255)
 
     // ---------------- package ops in robot order (env.py:260-292) ----------------
+    // robots stand on distinct cells, so pickups never contend across robots: each takes the
+    // lowest-id waiting package on its own cell
     const int nw_prev = build_waiting(p, w, lane, t);
+    const Scan sc = scan_waiting(w, lane, R, nw_prev, r, c, r1, c1);
     const bool want_pick = active && op == 1 && carry == 0;
-    int picked = -1;
-    if (__any_sync(MDX_FULL, want_pick)) {
-      for (int k = 0; k < nw_prev; ++k) {
-        const int j = w.wlist[k];
-        if (want_pick && picked < 0 && (int)w.start[j] == cell1) picked = j;  // lowest id first
-      }
-    }
+    const int picked = (want_pick && sc.at_new != MDX_NONE32) ? (int)w.wlist[sc.at_new] : -1;
     const int tgt0 = carry ? (int)w.target[carry - 1] : -1;
     const int dl0 = carry ? (int)w.dl[carry - 1] : 0;
     const bool delivered = active && op == 2 && carry != 0 && cell1 == tgt0;
@@ -617,7 +664,7 @@ __global__ void __launch_bounds__(256) mdx_env_kernel(const __grid_constant__ KP
     // shaped reward reads the PREVIOUS statuses, so evaluate it before they change
     float shaped = 0.0f;
     if (p.out_shaped != nullptr)
-      shaped = shaped_team_reward(p, w, lane, t, t + 1, cell, carry, cell1, carry1, mv, op, nw_prev, rew);
+      shaped = shaped_team_reward(p, w, lane, t + 1, r, c, carry, r1, c1, carry1, mv, op, nw_prev, sc, rew);
     __syncwarp();
     if (delivered) w.status[carry - 1] = ST_DELIVERED;
     if (picked >= 0) w.status[picked] = ST_IN_TRANSIT;
@@ -644,17 +691,20 @@ __global__ void __launch_bounds__(256) mdx_env_kernel(const __grid_constant__ KP
     // cumulative per-env counters
     {
       const int n_pick = __popc(__ballot_sync(MDX_FULL, picked >= 0));
-      uint32_t* cn = p.counters + (size_t)env * 8;
       if (lane == 0) {
-        cn[C_MOVES] += (uint32_t)n_moved;
-        cn[C_ONTIME] += (uint32_t)__popc(omask);
-        cn[C_LATE] += (uint32_t)__popc(dmask & ~omask);
-        cn[C_PICKUPS] += (uint32_t)n_pick;
-        cn[C_STEPS] += 1u;
+        uint4* cn = reinterpret_cast<uint4*>(p.counters + (size_t)env * 8);
+        uint4 a = cn[0], b = cn[1];
+        a.y += (uint32_t)n_moved;                 // C_MOVES
+        a.z += (uint32_t)__popc(omask);           // C_ONTIME
+        a.w += (uint32_t)__popc(dmask & ~omask);  // C_LATE
+        b.x += (uint32_t)n_pick;                  // C_PICKUPS
+        b.y += 1u;                                // C_STEPS
         if (done) {
-          cn[C_EPISODES] += 1u;
-          cn[C_EPLEN] += (uint32_t)t1;
+          a.x += 1u;            // C_EPISODES
+          b.z += (uint32_t)t1;  // C_EPLEN
         }
+        cn[0] = a;
+        cn[1] = b;
       }
     }
     cell = active ? cell1 : cell;
@@ -695,17 +745,17 @@ __global__ void __launch_bounds__(256) mdx_env_kernel(const __grid_constant__ KP
     }
   }
 
-  if (kMode & 2) featurize_env(p, w, map, lane, widx, t, cell, carry);
+  if (kMode & 2) featurize_env(p, w, lut, map, lane, widx, t, cell, carry);
 }
 
 // compute_shaped_rewards on injected "current" robots against the stored state as "previous".
-__global__ void __launch_bounds__(256) mdx_shape_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(128) mdx_shape_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int env = blockIdx.x * (blockDim.x >> 5) + wib;
   if (env >= p.n) return;
-  const Warp w = carve(p, smem_raw + (size_t)wib * p.smem_per_warp);
+  const Warp w = carve(p, smem_raw + kLutBytes + (size_t)wib * p.smem_per_warp);
   const int R = p.R;
   const bool active = lane < R;
   const int t = p.t[env];
@@ -718,26 +768,19 @@ __global__ void __launch_bounds__(256) mdx_shape_kernel(const __grid_constant__ 
   __syncwarp();
   const uint32_t rob0 = active ? p.robots[(size_t)env * R + lane] : 0u;
   const uint32_t rob1 = active ? p.cur_robots[(size_t)env * R + lane] : 0u;
-  const int a = active ? (int)p.actions[(size_t)env * R + lane] : 3;
   int mv, op;
-  if (a < 15) {
-    mv = a % 5;
-    op = a / 5;
-  } else if (a < 18) {
-    mv = MV_BAD;
-    op = a - 15;
-  } else {
-    mv = MV_BAD;
-    op = 0;
-  }
+  decode_action(active ? (int)p.actions[(size_t)env * R + lane] : 3, mv, op);
+  const int r0 = (int)__umulhi(rob0 & 0xffffu, p.mul_wout), c0 = (int)(rob0 & 0xffffu) - r0 * p.W_out;
+  const int r1 = (int)__umulhi(rob1 & 0xffffu, p.mul_wout), c1 = (int)(rob1 & 0xffffu) - r1 * p.W_out;
   const int nw = build_waiting(p, w, lane, t);
-  const float s = shaped_team_reward(p, w, lane, t, p.cur_t[env], (int)(rob0 & 0xffffu), (int)(rob0 >> 16),
-                                     (int)(rob1 & 0xffffu), (int)(rob1 >> 16), mv, op, nw, p.global_reward[env]);
+  const Scan sc = scan_waiting(w, lane, R, nw, r0, c0, r1, c1);
+  const float s = shaped_team_reward(p, w, lane, p.cur_t[env], r0, c0, (int)(rob0 >> 16), r1, c1, (int)(rob1 >> 16), mv, op,
+                                     nw, sc, p.global_reward[env]);
   if (lane == 0) p.out_shaped[env] = s;
 }
 
 // Apply uploaded reset blocks: env ids[i] advances to its next episode (env.py:81-125 minus the draws,
-// which happened on the host).  One thread per (env, package slot) would be overkill; one warp per env.
+// which happened on the host).  One warp per env.
 __global__ void __launch_bounds__(256) mdx_reset_kernel(const __grid_constant__ KParams p) {
   const int lane = threadIdx.x & 31;
   const int widx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
