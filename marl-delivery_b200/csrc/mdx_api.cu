@@ -116,7 +116,8 @@ struct mdx_env {
   uint16_t* d_stage = nullptr;
   int32_t* d_ids = nullptr;     // [2][n]
   int wpb_override = 0;
-  size_t smem_configured[4] = {0, 0, 0, 0};
+  size_t smem_configured[24] = {};
+  int force_generic = 0;  // MDX_GENERIC=1: always take the generic featuriser path (tests)
 };
 
 namespace {
@@ -204,22 +205,35 @@ int refresh_ep(mdx_env* e, cudaStream_t st) {
   return MDX_OK;
 }
 
-template <int kMode>
-int launch_env_kernel(mdx_env* e, const KParams& kp, cudaStream_t st) {
+template <int kMode, int kS, bool kSmall>
+int launch_variant(mdx_env* e, const KParams& kp, cudaStream_t st) {
   const int spw = smem_for_mode(e, kMode);
   const int wpb = pick_wpb(e, spw);
   const size_t smem = (size_t)kLutBytes + (size_t)wpb * spw;
-  size_t* configured = e->smem_configured;
-  if (smem > configured[kMode]) {
-    CU(cudaFuncSetAttribute(mdx_env_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-    configured[kMode] = smem;
+  const int slot = kMode * 6 + (kS == 1 ? 0 : kS == 4 ? 2 : 4) + (kSmall ? 1 : 0);
+  if (smem > e->smem_configured[slot]) {
+    CU(cudaFuncSetAttribute(mdx_env_kernel<kMode, kS, kSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)std::max<size_t>(smem, 48 * 1024)));
+    e->smem_configured[slot] = smem;
   }
   KParams q = kp;
   q.smem_per_warp = spw;
   const unsigned grid = (unsigned)((kp.n + wpb - 1) / wpb);
-  mdx_env_kernel<kMode><<<grid, wpb * 32, smem, st>>>(q);
+  mdx_env_kernel<kMode, kS, kSmall><<<grid, wpb * 32, smem, st>>>(q);
   CU(cudaGetLastError());
   return MDX_OK;
+}
+
+// plane slices: H*W <= 128 -> 1, <= 512 -> 4 (both need H*W % 4 == 0), otherwise the generic path
+template <int kMode>
+int launch_env_kernel(mdx_env* e, const KParams& kp, cudaStream_t st) {
+  if (kMode == 1) return launch_variant<1, 0, false>(e, kp, st);  // step only: no featuriser variants
+  const int HW = e->base.HW;
+  const bool small = e->P <= 64;
+  const int ks = e->force_generic ? 0 : ((HW & 3) == 0 && HW <= 128) ? 1 : ((HW & 3) == 0 && HW <= 512) ? 4 : 0;
+  if (ks == 1) return small ? launch_variant<kMode, 1, true>(e, kp, st) : launch_variant<kMode, 1, false>(e, kp, st);
+  if (ks == 4) return small ? launch_variant<kMode, 4, true>(e, kp, st) : launch_variant<kMode, 4, false>(e, kp, st);
+  return small ? launch_variant<kMode, 0, true>(e, kp, st) : launch_variant<kMode, 0, false>(e, kp, st);
 }
 
 int check_ptr16(const void* p, const char* name) {
@@ -281,6 +295,7 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   e->E = cfg->ring_episodes;
   e->threads = cfg->sampler_threads > 0 ? cfg->sampler_threads : (int)std::max(1u, std::thread::hardware_concurrency());
   if (const char* s = getenv("MDX_WPB")) e->wpb_override = atoi(s);
+  if (const char* s = getenv("MDX_GENERIC")) e->force_generic = atoi(s);
 
   // ---- maps
   int Ho = 0, Wo = 0;
@@ -327,6 +342,8 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   b.E = e->E;
   b.mul_plane = magic((uint32_t)b.HW);
   b.mul_wout = magic((uint32_t)Wo);
+  b.mul_r = magic((uint32_t)e->R);
+  b.pair_g = 32 / e->R;
   b.move_cost = cfg->move_cost;
   b.delivery_reward = cfg->delivery_reward;
   b.delay_reward = cfg->delay_reward;
@@ -405,6 +422,7 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   while (rpf > 1 && rpf * b.D * 4 > 8192) --rpf;
   b.vec_rows_per_flush = rpf;
   b.sel_k = std::min(b.K_p, e->P);
+  b.mul_ksel = magic((uint32_t)std::max(1, b.sel_k));
   b.off_sel = take(2 * std::max(8, round_up(rpf * std::max(1, b.sel_k), 8)));
   b.off_masks = take(4 * 10 * b.W32);
   b.off_stage = off;

@@ -73,6 +73,9 @@ struct KParams {
   int32_t vec_rows_per_flush;
   uint32_t mul_plane;    // ceil(2^32 / HW)       : e / HW        for e < 2^32 / HW
   uint32_t mul_wout;     // ceil(2^32 / W_out)    : cell / W_out
+  uint32_t mul_r;        // ceil(2^32 / R)        : lane / R
+  uint32_t mul_ksel;     // ceil(2^32 / sel_k)
+  int32_t pair_g;        // 32 / R: robots ranked per pass of the (robot, other) pair layout
   // smem carve-up (bytes from the warp's base)
   // step-only launches need [0, off_alist); the featuriser adds alist, sel, planes and the stage
   int32_t off_sched, off_status, off_wlist, off_wkey, off_rinfo, off_alist, off_sel, off_masks, off_stage;

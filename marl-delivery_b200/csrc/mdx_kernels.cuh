@@ -80,6 +80,7 @@ __device__ __forceinline__ void load_episode(const KParams& p, const Warp& w, in
   const uint4* src = reinterpret_cast<const uint4*>(p.sched + ((size_t)slot * p.n_envs + env) * 4 * p.Pp8);
   uint4* dst = reinterpret_cast<uint4*>(w.start);
   const int n16 = p.Pp8 >> 1;  // 4 rows * Pp8 u16 * 2 B / 16 B
+#pragma unroll 1
   for (int i = lane; i < n16; i += 32) dst[i] = __ldg(src + i);
 }
 
@@ -118,6 +119,7 @@ __device__ __forceinline__ void flush_seg(float* gdst, const float* stage, int o
   const float4* s4 = reinterpret_cast<const float4*>(s + head);
   float4* g4 = reinterpret_cast<float4*>(gdst + head);
   const int live = n_data > head ? (n_data - head + 3) >> 2 : 0;  // float4s that carry data
+#pragma unroll 1
   for (int i = lane; i < body; i += 32) __stcs(g4 + i, i < live ? s4[i] : make_float4(0.f, 0.f, 0.f, 0.f));
   const int done = head + (body << 2);
   if (lane < n_total - done) __stcs(gdst + done + lane, done + lane < n_data ? s[done + lane] : 0.0f);
@@ -126,6 +128,7 @@ __device__ __forceinline__ void flush_seg(float* gdst, const float* stage, int o
 __device__ __forceinline__ void zero_stage(float* stage, int n_floats, int lane) {
   float4* s4 = reinterpret_cast<float4*>(stage);
   const int n4 = (n_floats + 3) >> 2;
+#pragma unroll 1
   for (int i = lane; i < n4; i += 32) s4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
@@ -164,11 +167,13 @@ __device__ __forceinline__ Scan scan_waiting(const Warp& w, int lane, int R, int
   Scan mine{MDX_NONE32, MDX_NONE32, false};
   if (nw == 0) return mine;
   const uint32_t rc1 = ((uint32_t)r1 << 8) | (uint32_t)c1;
+#pragma unroll 1
   for (int i = 0; i < R; ++i) {
     const int ri = __shfl_sync(MDX_FULL, r0, i), ci = __shfl_sync(MDX_FULL, c0, i);
     const uint32_t rci = __shfl_sync(MDX_FULL, rc1, i);
     uint32_t best = MDX_NONE32, at_new = MDX_NONE32;
     bool near = false;
+#pragma unroll 1
     for (int k = lane; k < nw; k += 32) {
       const uint32_t rc = w.wrc[k];
       const int d = abs((int)(rc >> 8) - ri) + abs((int)(rc & 255u) - ci);
@@ -267,6 +272,12 @@ __device__ __forceinline__ void decode_action(int a, int& mv, int& op) {
 // ------------------------------------------------------------------------------------------------
 // Featurisation of the env held in shared memory (statuses, schedule) and registers (cell / carry of
 // robot `lane`), MAPPO/helper.py:6-255.  `row` selects the output row.
+//   kS     > 0: a plane is kS slices of 32 float4 (H*W <= 128*kS, H*W % 4 == 0); the four shared planes'
+//               nibbles are hoisted into registers and every robot costs 6 table loads + 6 stores per slice.
+//          = 0: generic flat loops over per-robot bit planes (any H*W).
+//   kSmall:     P <= 64, so a lane owns at most two waiting-list entries and keeps their selection keys
+//               in registers.
+template <int kS, bool kSmall>
 __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, const float4* lut, const MapDev& map,
                                               int lane, int row, int t, int cell, int carry) {
   const int R = p.R, P = p.P, W32 = p.W32, HW = p.HW, Wo = p.W_out;
@@ -295,6 +306,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
     w.rdl[lane] = (uint16_t)own_rem;
     w.rrc[lane] = (uint16_t)((r << 8) | c);
   }
+#pragma unroll 1
   for (int i = lane; i < W32; i += 32) {
     w.planes[i] = __ldg(map.grid_bits + i);
     w.planes[W32 + i] = 0u;
@@ -304,6 +316,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
   __syncwarp();
   if (active) atomicOr(&w.planes[W32 + (cell >> 5)], 1u << (cell & 31));
   int nw = 0, na = 0;
+#pragma unroll 1
   for (int base = 0; base < P; base += 32) {
     const int j = base + lane;
     const uint8_t st = j < P ? w.status[j] : (uint8_t)ST_NONE;
@@ -335,59 +348,114 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
   }
   __syncwarp();
 
-  // ---- gstate [4,H,W]: planes 0..3 are exactly its channels --------------------------------------
-  if (p.gstate != nullptr) {
-    float* out = p.gstate + (size_t)row * 4 * HW;
-    if ((HW & 3) == 0) {
-      float4* out4 = reinterpret_cast<float4*>(out);
-      for (int q = lane; q < HW; q += 32) {  // 4 planes * HW / 4 float4s
-        const uint32_t e = (uint32_t)q << 2;
-        const uint32_t ch = __umulhi(e, p.mul_plane);
-        const uint32_t cl = e - ch * HW;
-        const uint32_t nib = (w.planes[ch * W32 + (cl >> 5)] >> (cl & 31u)) & 15u;
-        __stcs(out4 + q, lut[nib]);
-      }
-    } else {
-      for (int e = lane; e < 4 * HW; e += 32) {
-        const uint32_t ch = __umulhi((uint32_t)e, p.mul_plane);
-        const uint32_t cl = (uint32_t)e - ch * HW;
-        __stcs(out + e, ((w.planes[ch * W32 + (cl >> 5)] >> (cl & 31u)) & 1u) ? 1.0f : 0.0f);
+  if (kS > 0) {
+    // ---- plane-structured path: lane owns float4 number (lane + 32*s) of every plane ------------
+    const int n4p = HW >> 2;
+    const uint32_t sh = (uint32_t)(lane & 7) << 2;
+    uint32_t ng[kS > 0 ? kS : 1], nrb[kS > 0 ? kS : 1], nws[kS > 0 ? kS : 1], nat[kS > 0 ? kS : 1];
+#pragma unroll
+    for (int s_ = 0; s_ < kS; ++s_) {
+      const int wi = (lane >> 3) + 4 * s_;
+      const bool ok = lane + 32 * s_ < n4p;
+      ng[s_] = ok ? (w.planes[wi] >> sh) & 15u : 0u;
+      nrb[s_] = ok ? (w.planes[W32 + wi] >> sh) & 15u : 0u;
+      nws[s_] = ok ? (w.planes[2 * W32 + wi] >> sh) & 15u : 0u;
+      nat[s_] = ok ? (w.planes[3 * W32 + wi] >> sh) & 15u : 0u;
+    }
+    if (p.gstate != nullptr) {
+      float4* out4 = reinterpret_cast<float4*>(p.gstate + (size_t)row * 4 * HW);
+#pragma unroll
+      for (int s_ = 0; s_ < kS; ++s_) {
+        const int q = lane + 32 * s_;
+        if (q < n4p) {
+          __stcs(out4 + q, lut[ng[s_]]);
+          __stcs(out4 + n4p + q, lut[nrb[s_]]);
+          __stcs(out4 + 2 * n4p + q, lut[nws[s_]]);
+          __stcs(out4 + 3 * n4p + q, lut[nat[s_]]);
+        }
       }
     }
-  }
-
-  // ---- obs [R,6,H,W]: per robot three private planes (self, others, own target), double-buffered --
-  if (p.obs != nullptr) {
-    for (int i = 0; i < R; ++i) {
-      const int b = 4 + 3 * (i & 1);
-      const uint32_t rc = w.rcell[i], tg = w.rtgt[i];
-      for (int x = lane; x < W32; x += 32) {
-        const uint32_t self = ((rc >> 5) == (uint32_t)x) ? (1u << (rc & 31u)) : 0u;
-        w.planes[b * W32 + x] = self;
-        w.planes[(b + 1) * W32 + x] = w.planes[W32 + x] & ~self;
-        w.planes[(b + 2) * W32 + x] = ((tg >> 5) == (uint32_t)x) ? (1u << (tg & 31u)) : 0u;  // tg = 0xFFFF: no plane word matches
+    if (p.obs != nullptr) {
+      float4* base4 = reinterpret_cast<float4*>(p.obs + (size_t)row * R * 6 * HW);
+#pragma unroll 1
+      for (int i = 0; i < R; ++i) {
+        const uint32_t rc = w.rcell[i], tg = w.rtgt[i];  // tg = 0xFFFF (none) never matches: tg >> 2 > any q
+        float4* out4 = base4 + (size_t)i * 6 * n4p;
+#pragma unroll
+        for (int s_ = 0; s_ < kS; ++s_) {
+          const int q = lane + 32 * s_;
+          if (q < n4p) {
+            const uint32_t oh_r = ((rc >> 2) == (uint32_t)q) ? (1u << (rc & 3u)) : 0u;
+            const uint32_t oh_t = ((tg >> 2) == (uint32_t)q) ? (1u << (tg & 3u)) : 0u;
+            __stcs(out4 + q, lut[ng[s_]]);                        // 0: obstacles
+            __stcs(out4 + n4p + q, lut[oh_r]);                    // 1: this robot
+            __stcs(out4 + 2 * n4p + q, lut[nrb[s_] & ~oh_r]);     // 2: other robots
+            __stcs(out4 + 3 * n4p + q, lut[nws[s_]]);             // 3: waiting starts
+            __stcs(out4 + 4 * n4p + q, lut[nat[s_]]);             // 4: active targets
+            __stcs(out4 + 5 * n4p + q, lut[oh_t]);                // 5: own carried target
+          }
+        }
       }
-      __syncwarp();
-      // channel -> plane: 0 grid, 1 self, 2 others, 3 waiting starts, 4 active targets, 5 own target
-      const uint32_t pmap = 0u | ((uint32_t)b << 4) | ((uint32_t)(b + 1) << 8) | (2u << 12) | (3u << 16) | ((uint32_t)(b + 2) << 20);
-      float* out = p.obs + ((size_t)row * R + i) * 6 * HW;
+    }
+  } else {
+    // ---- generic path: flat loops, per robot three private planes (double-buffered) ---------------
+    if (p.gstate != nullptr) {
+      float* out = p.gstate + (size_t)row * 4 * HW;
       if ((HW & 3) == 0) {
         float4* out4 = reinterpret_cast<float4*>(out);
-        const int n4 = (6 * HW) >> 2;
-        for (int q = lane; q < n4; q += 32) {
+#pragma unroll 1
+        for (int q = lane; q < HW; q += 32) {  // 4 planes * HW / 4 float4s
           const uint32_t e = (uint32_t)q << 2;
           const uint32_t ch = __umulhi(e, p.mul_plane);
           const uint32_t cl = e - ch * HW;
-          const uint32_t pl = (pmap >> (ch << 2)) & 15u;
-          const uint32_t nib = (w.planes[pl * W32 + (cl >> 5)] >> (cl & 31u)) & 15u;
+          const uint32_t nib = (w.planes[ch * W32 + (cl >> 5)] >> (cl & 31u)) & 15u;
           __stcs(out4 + q, lut[nib]);
         }
       } else {
-        for (int e = lane; e < 6 * HW; e += 32) {
+#pragma unroll 1
+        for (int e = lane; e < 4 * HW; e += 32) {
           const uint32_t ch = __umulhi((uint32_t)e, p.mul_plane);
           const uint32_t cl = (uint32_t)e - ch * HW;
-          const uint32_t pl = (pmap >> (ch << 2)) & 15u;
-          __stcs(out + e, ((w.planes[pl * W32 + (cl >> 5)] >> (cl & 31u)) & 1u) ? 1.0f : 0.0f);
+          __stcs(out + e, ((w.planes[ch * W32 + (cl >> 5)] >> (cl & 31u)) & 1u) ? 1.0f : 0.0f);
+        }
+      }
+    }
+    if (p.obs != nullptr) {
+#pragma unroll 1
+      for (int i = 0; i < R; ++i) {
+        const int b = 4 + 3 * (i & 1);
+        const uint32_t rc = w.rcell[i], tg = w.rtgt[i];
+#pragma unroll 1
+        for (int x = lane; x < W32; x += 32) {
+          const uint32_t self = ((rc >> 5) == (uint32_t)x) ? (1u << (rc & 31u)) : 0u;
+          w.planes[b * W32 + x] = self;
+          w.planes[(b + 1) * W32 + x] = w.planes[W32 + x] & ~self;
+          w.planes[(b + 2) * W32 + x] = ((tg >> 5) == (uint32_t)x) ? (1u << (tg & 31u)) : 0u;  // tg = 0xFFFF: no word matches
+        }
+        __syncwarp();
+        // channel -> plane: 0 grid, 1 self, 2 others, 3 waiting starts, 4 active targets, 5 own target
+        const uint32_t pmap = 0u | ((uint32_t)b << 4) | ((uint32_t)(b + 1) << 8) | (2u << 12) | (3u << 16) | ((uint32_t)(b + 2) << 20);
+        float* out = p.obs + ((size_t)row * R + i) * 6 * HW;
+        if ((HW & 3) == 0) {
+          float4* out4 = reinterpret_cast<float4*>(out);
+          const int n4 = (6 * HW) >> 2;
+#pragma unroll 1
+          for (int q = lane; q < n4; q += 32) {
+            const uint32_t e = (uint32_t)q << 2;
+            const uint32_t ch = __umulhi(e, p.mul_plane);
+            const uint32_t cl = e - ch * HW;
+            const uint32_t pl = (pmap >> (ch << 2)) & 15u;
+            const uint32_t nib = (w.planes[pl * W32 + (cl >> 5)] >> (cl & 31u)) & 15u;
+            __stcs(out4 + q, lut[nib]);
+          }
+        } else {
+#pragma unroll 1
+          for (int e = lane; e < 6 * HW; e += 32) {
+            const uint32_t ch = __umulhi((uint32_t)e, p.mul_plane);
+            const uint32_t cl = (uint32_t)e - ch * HW;
+            const uint32_t pl = (pmap >> (ch << 2)) & 15u;
+            __stcs(out + e, ((w.planes[pl * W32 + (cl >> 5)] >> (cl & 31u)) & 1u) ? 1.0f : 0.0f);
+          }
         }
       }
     }
@@ -408,8 +476,22 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
     const int nsel = min(Ksel, nw);
     const int rpf = p.vec_rows_per_flush;
     // lanes as (robot, other) pairs for the stable sort of the other robots
-    const int G = 32 / R;                 // robots per pass
-    const int gi = lane / R, gj = lane - gi * R;
+    const int G = p.pair_g;  // robots per pass = 32 / R
+    const int gi = (int)__umulhi((uint32_t)lane, p.mul_r), gj = lane - gi * R;
+    // selection keys: (remaining deadline * nranks + rank of the float64 distance key) << wbits | list index.
+    // The robot-independent part of a lane's own entries is computed once.
+    uint32_t kb0 = 0, kb1 = 0, rce0 = 0, rce1 = 0;
+    if (kSmall) {
+      if (lane < nw) {
+        rce0 = w.wrc[lane];
+        kb0 = (((uint32_t)w.wdl[lane] * (uint32_t)p.nranks_max) << p.key_wbits) | (uint32_t)lane;
+      }
+      if (lane + 32 < nw) {
+        rce1 = w.wrc[lane + 32];
+        kb1 = (((uint32_t)w.wdl[lane + 32] * (uint32_t)p.nranks_max) << p.key_wbits) | (uint32_t)(lane + 32);
+      }
+    }
+#pragma unroll 1
     for (int i0 = 0; i0 < R; i0 += rpf) {
       const int nrows = min(rpf, R - i0);
       const size_t g0 = ((size_t)row * R + i0) * D;
@@ -424,14 +506,15 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
         rowp[1] = __ldg(qc + (c + Wm1));
         rowp[2] = cflag;
         if (carrying_it) {
-          rowp[3] = __ldg(qr + (tr_own - r + Hm1));
-          rowp[4] = __ldg(qc + (tc_own - c + Wm1));
+          rowp[3] = ot_r;  // (tr - my_r) / n_rows: same quotient as in the other-robot rows
+          rowp[4] = ot_c;
           rowp[5] = tnorm(p, own_rem);
         }
         rowp[D - 1] = tfrac;
       }
       // other robots, stable-sorted by the float64 key rank (:115-141)
       if (K_o > 0 && R > 1) {
+#pragma unroll 1
         for (int ib = i0; ib < i0 + nrows; ib += G) {
           const int i = ib + gi;
           const bool valid = gi < G && i < i0 + nrows && gj != i;
@@ -444,6 +527,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
             okey = ((uint32_t)__ldg(map.rank + (dr + Hm1) * NC + (dc + Wm1)) << 5) | (uint32_t)gj;
           }
           int pos = 0;
+#pragma unroll 1
           for (int k = 0; k < R; ++k) pos += (__shfl_sync(MDX_FULL, okey, gi * R + k) < okey) ? 1 : 0;
           const float cf_j = __shfl_sync(MDX_FULL, cflag, gj);
           const float otr_j = __shfl_sync(MDX_FULL, ot_r, gj), otc_j = __shfl_sync(MDX_FULL, ot_c, gj);
@@ -458,49 +542,71 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
         }
       }
       // waiting packages, stable-sorted by (remaining deadline, key rank) (:143-160): per robot a
-      // repeated warp arg-min over 32-bit keys (rem * nranks + rank) << wbits | list index records
-      // the winners; the rows are written afterwards, one lane per (robot, slot)
+      // repeated warp arg-min over the keys records the winners; the rows are written afterwards,
+      // one lane per (robot, slot)
       if (nsel > 0) {
+#pragma unroll 1
         for (int i = i0; i < i0 + nrows; ++i) {
           const uint32_t rci = w.rrc[i];
           const int ri = (int)(rci >> 8), ci = (int)(rci & 255u);
-          uint32_t lm = MDX_NONE32;
-          for (int k = lane; k < nw; k += 32) {
-            const uint32_t rc = w.wrc[k];
-            const uint32_t rk = __ldg(map.rank + ((int)(rc >> 8) - ri + Hm1) * NC + ((int)(rc & 255u) - ci + Wm1));
-            const uint32_t key = (((uint32_t)w.wdl[k] * (uint32_t)p.nranks_max + rk) << p.key_wbits) | (uint32_t)k;
-            w.wkey[k] = key;
-            lm = min(lm, key);
-          }
           uint16_t* selp = w.sel + (i - i0) * Ksel;
-          for (int q = 0; q < nsel; ++q) {
-            const uint32_t best = __reduce_min_sync(MDX_FULL, lm);
-            if (lm == best) {  // exactly one lane: keys are unique
-              const uint32_t k = best & wmask;
-              selp[q] = (uint16_t)k;
-              w.wkey[k] = MDX_NONE32;
-              lm = MDX_NONE32;
-              for (int kk = lane; kk < nw; kk += 32) lm = min(lm, w.wkey[kk]);
+          if (kSmall) {
+            uint32_t k0 = MDX_NONE32, k1 = MDX_NONE32;
+            if (lane < nw)
+              k0 = kb0 + ((uint32_t)__ldg(map.rank + ((int)(rce0 >> 8) - ri + Hm1) * NC + ((int)(rce0 & 255u) - ci + Wm1)) << p.key_wbits);
+            if (lane + 32 < nw)
+              k1 = kb1 + ((uint32_t)__ldg(map.rank + ((int)(rce1 >> 8) - ri + Hm1) * NC + ((int)(rce1 & 255u) - ci + Wm1)) << p.key_wbits);
+#pragma unroll 1
+            for (int q = 0; q < nsel; ++q) {
+              const uint32_t best = __reduce_min_sync(MDX_FULL, min(k0, k1));
+              if (lane == 0) selp[q] = (uint16_t)(best & wmask);
+              if (k0 == best) k0 = MDX_NONE32;  // keys are unique: exactly one entry is retired
+              if (k1 == best) k1 = MDX_NONE32;
+            }
+          } else {
+            uint32_t lm = MDX_NONE32;
+#pragma unroll 1
+            for (int k = lane; k < nw; k += 32) {
+              const uint32_t rc = w.wrc[k];
+              const uint32_t rk = __ldg(map.rank + ((int)(rc >> 8) - ri + Hm1) * NC + ((int)(rc & 255u) - ci + Wm1));
+              const uint32_t key = (((uint32_t)w.wdl[k] * (uint32_t)p.nranks_max + rk) << p.key_wbits) | (uint32_t)k;
+              w.wkey[k] = key;
+              lm = min(lm, key);
+            }
+#pragma unroll 1
+            for (int q = 0; q < nsel; ++q) {
+              const uint32_t best = __reduce_min_sync(MDX_FULL, lm);
+              if (lm == best) {  // exactly one lane: keys are unique
+                const uint32_t k = best & wmask;
+                selp[q] = (uint16_t)k;
+                w.wkey[k] = MDX_NONE32;
+                lm = MDX_NONE32;
+#pragma unroll 1
+                for (int kk = lane; kk < nw; kk += 32) lm = min(lm, w.wkey[kk]);
+              }
             }
           }
         }
         __syncwarp();
-        const int nslot = nrows * nsel;
+        const int nslot = nrows * Ksel;
+#pragma unroll 1
         for (int x = lane; x < nslot; x += 32) {
-          const int ii = x / nsel, q = x - ii * nsel;
-          const uint32_t rci = w.rrc[i0 + ii];
-          const int ri = (int)(rci >> 8), ci = (int)(rci & 255u);
-          const int k = w.sel[ii * Ksel + q];
-          const int j = w.wlist[k];
-          const uint32_t rc = w.wrc[k];
-          const uint32_t tc_ = w.target[j];
-          const int tr = (int)__umulhi(tc_, p.mul_wout), tcol = (int)tc_ - tr * Wo;
-          float* o = chunk + ii * D + 6 + K_o * 5 + q * 5;
-          o[0] = __ldg(qr + ((int)(rc >> 8) - ri + Hm1));
-          o[1] = __ldg(qc + ((int)(rc & 255u) - ci + Wm1));
-          o[2] = __ldg(qr + (tr - ri + Hm1));
-          o[3] = __ldg(qc + (tcol - ci + Wm1));
-          o[4] = tnorm(p, (int)w.wdl[k]);
+          const int ii = (int)__umulhi((uint32_t)x, p.mul_ksel), q = x - ii * Ksel;
+          if (q < nsel) {
+            const uint32_t rci = w.rrc[i0 + ii];
+            const int ri = (int)(rci >> 8), ci = (int)(rci & 255u);
+            const int k = w.sel[ii * Ksel + q];
+            const int j = w.wlist[k];
+            const uint32_t rc = w.wrc[k];
+            const uint32_t tc_ = w.target[j];
+            const int tr = (int)__umulhi(tc_, p.mul_wout), tcol = (int)tc_ - tr * Wo;
+            float* o = chunk + ii * D + 6 + K_o * 5 + q * 5;
+            o[0] = __ldg(qr + ((int)(rc >> 8) - ri + Hm1));
+            o[1] = __ldg(qc + ((int)(rc & 255u) - ci + Wm1));
+            o[2] = __ldg(qr + (tr - ri + Hm1));
+            o[3] = __ldg(qc + (tcol - ci + Wm1));
+            o[4] = tnorm(p, (int)w.wdl[k]);
+          }
         }
       }
       __syncwarp();
@@ -533,6 +639,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
         o[5] = tnorm(p, own_rem);
       }
     }
+#pragma unroll 1
     for (int k = lane; k < nrow; k += 32) {
       const int j = w.alist[k];
       const bool wait = w.status[j] == ST_WAITING;
@@ -568,7 +675,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
 
 // ------------------------------------------------------------------------------------------------
 // kMode bit 0: step (+ shaped reward, + optional auto-reset);  bit 1: featurise.
-template <int kMode>
+template <int kMode, int kS, bool kSmall>
 __global__ void __launch_bounds__(128, (kMode & 2) ? 7 : 8) mdx_env_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const float4* lut = reinterpret_cast<const float4*>(smem_raw);
@@ -596,6 +703,7 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? 7 : 8) mdx_env_kernel(const
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.status + (size_t)env * p.Pp16);
     uint4* dst = reinterpret_cast<uint4*>(w.status);
+#pragma unroll 1
     for (int i = lane; i < (p.Pp16 >> 4); i += 32) dst[i] = src[i];
   }
   uint32_t rob = active ? p.robots[(size_t)env * R + lane] : 0u;
@@ -736,7 +844,8 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? 7 : 8) mdx_env_kernel(const
     {
       uint4* dst = reinterpret_cast<uint4*>(p.status + (size_t)env * p.Pp16);
       const uint4* src = reinterpret_cast<const uint4*>(w.status);
-      for (int i = lane; i < (p.Pp16 >> 4); i += 32) dst[i] = src[i];
+  #pragma unroll 1
+    for (int i = lane; i < (p.Pp16 >> 4); i += 32) dst[i] = src[i];
     }
     if (lane == 0) {
       p.t[env] = t;
@@ -745,7 +854,7 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? 7 : 8) mdx_env_kernel(const
     }
   }
 
-  if (kMode & 2) featurize_env(p, w, lut, map, lane, widx, t, cell, carry);
+  if (kMode & 2) featurize_env<kS, kSmall>(p, w, lut, map, lane, widx, t, cell, carry);
 }
 
 // compute_shaped_rewards on injected "current" robots against the stored state as "previous".
@@ -763,6 +872,7 @@ __global__ void __launch_bounds__(128) mdx_shape_kernel(const __grid_constant__ 
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.status + (size_t)env * p.Pp16);
     uint4* dst = reinterpret_cast<uint4*>(w.status);
+#pragma unroll 1
     for (int i = lane; i < (p.Pp16 >> 4); i += 32) dst[i] = src[i];
   }
   __syncwarp();

@@ -374,3 +374,27 @@ def test_helper_dropins_match_golden():
             g, gv = mdb.helper.convert_global_state(st, tracker, meta["T"], meta["MR"], meta["MP"])
             assert np.array_equal(g, z["gstate"][step].astype(np.float32)) and np.array_equal(_bits(gv), _bits(z["gvec"][step]))
     assert mdb.helper.generate_vector_features(st, tracker, 99, 10).shape == (1007,)
+
+
+@pytest.mark.parametrize("name", ["map1_mix", "map5_c4", "map1_home"])
+def test_generic_featuriser_path_matches_golden(name, monkeypatch):
+    """The kernels pick a plane-sliced fast path for H*W <= 512; MDX_GENERIC=1 forces the generic flat
+    path (any H*W, e.g. maps larger than 22x22), which must produce the same bits."""
+    monkeypatch.setenv("MDX_GENERIC", "1")
+    meta, z = load_traj(name)
+    b = _batch_for(meta, z, n_envs=2, ring_episodes=4)
+    monkeypatch.delenv("MDX_GENERIC")
+    b.reset()
+    fi = 0
+    for step in range(min(meta["n_steps"], 260)):
+        if step % 64 == 0:
+            b.prefetch(3)
+        a = torch.from_numpy(np.repeat(z["actions"][step][None], 2, 0).copy())
+        r, sh, d, o, v, g, gv = b.step_featurize(a, auto_reset=True)
+        assert np.all(sh.cpu().numpy() == z["shaped_mappo"][step]), step
+        if step % meta["feat_every"] == 0:
+            assert np.array_equal(o.cpu().numpy()[1], z["obs"][fi].astype(np.float32)), step
+            assert np.array_equal(_bits(v.cpu().numpy()[1]), _bits(z["vec"][fi])), step
+            assert np.array_equal(g.cpu().numpy()[0], z["gstate"][fi].astype(np.float32)), step
+            assert np.array_equal(_bits(gv.cpu().numpy()[1]), _bits(z["gvec"][fi])), step
+            fi += 1
