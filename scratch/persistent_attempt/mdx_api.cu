@@ -117,6 +117,9 @@ struct mdx_env {
   int32_t* d_ids = nullptr;     // [2][n]
   int wpb_override = 0;
   size_t smem_configured[24] = {};
+  int resident_blocks[24] = {};
+  int sm_count = 148;
+  int persistent = 1;  // MDX_PERSISTENT=0: one CTA per 4 envs instead of a resident grid (experiments)
   int force_generic = 0;  // MDX_GENERIC=1: always take the generic featuriser path (tests)
 };
 
@@ -218,7 +221,14 @@ int launch_variant(mdx_env* e, const KParams& kp, cudaStream_t st) {
   }
   KParams q = kp;
   q.smem_per_warp = spw;
-  const unsigned grid = (unsigned)((kp.n + wpb - 1) / wpb);
+  // persistent launch: one wave of resident CTAs, every warp walks over envs with a grid stride
+  if (e->resident_blocks[slot] == 0) {
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mdx_env_kernel<kMode, kS, kSmall>, wpb * 32, smem));
+    e->resident_blocks[slot] = std::max(1, per_sm) * e->sm_count;
+  }
+  const unsigned need = (unsigned)((kp.n + wpb - 1) / wpb);
+  const unsigned grid = e->persistent ? std::min(need, (unsigned)e->resident_blocks[slot]) : need;
   mdx_env_kernel<kMode, kS, kSmall><<<grid, wpb * 32, smem, st>>>(q);
   CU(cudaGetLastError());
   return MDX_OK;
@@ -296,6 +306,7 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   e->threads = cfg->sampler_threads > 0 ? cfg->sampler_threads : (int)std::max(1u, std::thread::hardware_concurrency());
   if (const char* s = getenv("MDX_WPB")) e->wpb_override = atoi(s);
   if (const char* s = getenv("MDX_GENERIC")) e->force_generic = atoi(s);
+  if (const char* s = getenv("MDX_PERSISTENT")) e->persistent = atoi(s);
 
   // ---- maps
   int Ho = 0, Wo = 0;
@@ -412,8 +423,8 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
     off = round_up(off + bytes, 16);
     return at;
   };
-  b.off_sched = take(8 * b.Pp8);
-  b.off_status = take(b.Pp16);
+  b.ep_blk = 8 * b.Pp8 + b.Pp16;
+  b.off_sched = take(2 * b.ep_blk);
   b.off_wlist = take(3 * 2 * b.Pp8);  // wlist, wrc, wdl
   b.off_wkey = take(4 * b.Pp8);
   b.off_rinfo = take(2 * 5 * 32);
@@ -450,6 +461,10 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
     return fail(MDX_E_CUDA, "no CUDA device: libmdx has no CPU fallback");
   if (cfg->device < 0 || cfg->device >= ndev) return fail(MDX_E_INVALID, "device ordinal %d out of range", cfg->device);
   DeviceGuard guard(e->device);
+  {
+    int smc = 0;
+    if (cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, e->device) == cudaSuccess && smc > 0) e->sm_count = smc;
+  }
   const size_t n = (size_t)e->n;
   mdx_env* raw = e.get();
 #define CUX(call)                                                                      \

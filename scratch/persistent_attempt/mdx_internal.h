@@ -79,7 +79,7 @@ struct KParams {
   int32_t sel_rp;        // 32 / sel_k: robots whose package selection fits one pass of lane-held winners
   // smem carve-up (bytes from the warp's base)
   // step-only launches need [0, off_alist); the featuriser adds alist, sel, planes and the stage
-  int32_t off_sched, off_status, off_wlist, off_wkey, off_rinfo, off_alist, off_sel, off_masks, off_stage;
+  int32_t off_sched, ep_blk, off_wlist, off_wkey, off_rinfo, off_alist, off_sel, off_masks, off_stage;  // off_sched: two episode buffers of ep_blk bytes ([4][Pp8] u16 schedule | [Pp16] u8 status)
   int32_t smem_per_warp;
   int32_t sel_k;      // min(K_p, P): selection slots per robot
   int32_t stage_b;    // float offset of the gvec package segment inside the stage

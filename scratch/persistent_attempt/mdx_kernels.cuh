@@ -30,7 +30,7 @@ namespace mdx {
 #define MDX_FULL 0xffffffffu
 #define MDX_NONE32 0xffffffffu
 #ifndef MDX_FEAT_BLOCKS
-#define MDX_FEAT_BLOCKS 7  // resident CTAs per SM the featurising variants are compiled for (register cap 65536 / 128 / n)
+#define MDX_FEAT_BLOCKS 6  // resident CTAs per SM the featurising variants are compiled for (register cap 65536 / 128 / n)
 #endif
 constexpr int kLutBytes = 256;  // block-shared nibble -> float4 table at the start of dynamic smem
 
@@ -47,12 +47,6 @@ struct Warp {
 
 __device__ __forceinline__ Warp carve(const KParams& p, unsigned char* base) {
   Warp w;
-  uint16_t* s = reinterpret_cast<uint16_t*>(base + p.off_sched);
-  w.start = s;
-  w.target = s + p.Pp8;
-  w.t0 = s + 2 * p.Pp8;
-  w.dl = s + 3 * p.Pp8;
-  w.status = base + p.off_status;
   uint16_t* wl = reinterpret_cast<uint16_t*>(base + p.off_wlist);
   w.wlist = wl;
   w.wrc = wl + p.Pp8;
@@ -70,6 +64,32 @@ __device__ __forceinline__ Warp carve(const KParams& p, unsigned char* base) {
   w.stage = reinterpret_cast<float*>(base + p.off_stage);
   return w;
 }
+
+// Point the episode views at one of the two [schedule | status] buffers of the warp.
+__device__ __forceinline__ void bind_episode(const KParams& p, Warp& w, unsigned char* buf) {
+  uint16_t* s = reinterpret_cast<uint16_t*>(buf);
+  w.start = s;
+  w.target = s + p.Pp8;
+  w.t0 = s + 2 * p.Pp8;
+  w.dl = s + 3 * p.Pp8;
+  w.status = buf + 8 * p.Pp8;
+}
+
+// Asynchronous (cp.async, L2 -> shared, no register staging) copy of an env's current schedule block
+// and status row into an episode buffer; completion is awaited with cp_async_wait_all().
+__device__ __forceinline__ void prefetch_episode(const KParams& p, unsigned char* buf, int env, int slot, int lane) {
+  const unsigned char* g_sched = reinterpret_cast<const unsigned char*>(p.sched + ((size_t)slot * p.n_envs + env) * 4 * p.Pp8);
+  const unsigned char* g_status = p.status + (size_t)env * p.Pp16;
+  const int n_sched = p.Pp8 >> 1, n_all = n_sched + (p.Pp16 >> 4);  // 16-byte chunks
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(buf);
+#pragma unroll 1
+  for (int i = lane; i < n_all; i += 32) {
+    const unsigned char* src = i < n_sched ? g_sched + (size_t)i * 16 : g_status + (size_t)(i - n_sched) * 16;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sbase + (uint32_t)i * 16u), "l"(src) : "memory");
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // max(0, deadline - t) / T  and  t / T  (MAPPO/helper.py:107,155,163): table of correctly rounded
 // float64 quotients, IEEE double division beyond the table (t keeps running past T).
@@ -728,7 +748,34 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
 }
 
 // ------------------------------------------------------------------------------------------------
+// What a warp needs from global memory before it can start on an env; loaded one env ahead.
+struct EnvHeader {
+  int env, t, ep, action;
+  uint32_t rob;
+  double total;
+};
+
+template <int kMode>
+__device__ __forceinline__ EnvHeader load_header(const KParams& p, int widx, int lane) {
+  EnvHeader h;
+  h.env = p.env_ids ? __ldg(p.env_ids + widx) : widx;
+  h.t = p.t[h.env];
+  h.ep = p.ep[h.env];
+  h.rob = lane < p.R ? p.robots[(size_t)h.env * p.R + lane] : 0u;
+  h.action = 3;
+  h.total = 0.0;
+  if (kMode & 1) {
+    if (lane < p.R) h.action = (int)__ldg(p.actions + (size_t)widx * p.R + lane);
+    h.total = p.total_reward[h.env];
+  }
+  return h;
+}
+
 // kMode bit 0: step (+ shaped reward, + optional auto-reset);  bit 1: featurise.
+// Persistent: the grid is sized to the number of resident CTAs and every warp walks over envs
+// widx, widx + stride, ...  The next env's header is loaded into registers and its schedule/status block
+// is copied into the other shared-memory episode buffer with cp.async while the current env is being
+// processed, so no global-load latency is exposed after a warp's first env.
 template <int kMode, int kS, bool kSmall>
 __global__ void __launch_bounds__(128, (kMode & 2) ? MDX_FEAT_BLOCKS : 8) mdx_env_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -743,172 +790,185 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? MDX_FEAT_BLOCKS : 8) mdx_en
   }
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int widx = blockIdx.x * (blockDim.x >> 5) + wib;
+  const int wpb = blockDim.x >> 5;
+  const int stride = gridDim.x * wpb;
+  int widx = blockIdx.x * wpb + wib;
   if (widx >= p.n) return;
-  const Warp w = carve(p, smem_raw + kLutBytes + (size_t)wib * p.smem_per_warp);
-  const int env = p.env_ids ? __ldg(p.env_ids + widx) : widx;
+  unsigned char* wbase = smem_raw + kLutBytes + (size_t)wib * p.smem_per_warp;
+  Warp w = carve(p, wbase);
+  unsigned char* ebuf0 = wbase + p.off_sched;
   const int R = p.R, P = p.P, Wo = p.W_out;
   const bool active = lane < R;
-  const MapDev& map = p.maps[p.env_map ? __ldg(p.env_map + env) : 0];
 
-  int t = p.t[env];
-  int ep = p.ep[env];
-  load_episode(p, w, env, ep % p.E, lane);
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(p.status + (size_t)env * p.Pp16);
-    uint4* dst = reinterpret_cast<uint4*>(w.status);
+  EnvHeader cur = load_header<kMode>(p, widx, lane);
+  prefetch_episode(p, ebuf0, cur.env, cur.ep % p.E, lane);
+  EnvHeader nxt = cur;
 #pragma unroll 1
-    for (int i = lane; i < (p.Pp16 >> 4); i += 32) dst[i] = src[i];
-  }
-  uint32_t rob = active ? p.robots[(size_t)env * R + lane] : 0u;
-  int cell = active ? (int)(rob & 0xffffu) : (0x10000 + lane);
-  int carry = active ? (int)(rob >> 16) : 0;
-  __syncwarp();
-
-  if (kMode & 1) {
-    // ---------------- decode ----------------
-    int mv, op;
-    decode_action(active ? (int)__ldg(p.actions + (size_t)widx * R + lane) : 3, mv, op);
-    // ---------------- proposals (env.py:193-201) ----------------
-    const int r = active ? (int)__umulhi((uint32_t)cell, p.mul_wout) : 0;
-    const int c = active ? cell - r * Wo : 0;
-    const int nr = r + (mv == MV_D) - (mv == MV_U);
-    const int nc = c + (mv == MV_R) - (mv == MV_L);
-    int tgt = cell;
-    if (active && nr >= 0 && nr < map.H && nc >= 0 && nc < map.W) {
-      const int ncell = nr * Wo + nc;
-      if (((__ldg(map.grid_bits + (ncell >> 5)) >> (ncell & 31)) & 1u) == 0u) tgt = ncell;
-    }
-    // ---------------- resolution (env.py:203-250) as a monotone fixed point ----------------
-    // robot i moves  <=>  it is the lowest-index contender for its target cell AND that cell was
-    // empty at step start or its holder moves away.  Cycles/swaps never enter the fixed point.
-    int holder = -1;
-    for (int j = 0; j < R; ++j) {
-      const int cj = __shfl_sync(MDX_FULL, cell, j);
-      if (cj == tgt && j != lane) holder = j;
-    }
-    const bool wants = active && tgt != cell;
-    const unsigned grp = __match_any_sync(MDX_FULL, tgt);
-    const unsigned wants_mask = __ballot_sync(MDX_FULL, wants);
-    const bool winner = wants && (((grp & wants_mask) & ((1u << lane) - 1u)) == 0u);
-    unsigned mm = 0u;
-    while (true) {
-      const bool m = winner && (holder < 0 || ((mm >> holder) & 1u));
-      const unsigned nm = __ballot_sync(MDX_FULL, m);
-      if (nm == mm) break;
-      mm = nm;
-    }
-    const bool moved = (mm >> lane) & 1u;
-    const int cell1 = moved ? tgt : cell;
-    const int r1 = moved ? nr : r, c1 = moved ? nc : c;
-    const int n_moved = __popc(mm);  // every mover used one of L/R/U/D (env.py:255)
-
-    // ---------------- package ops in robot order (env.py:260-292) ----------------
-    // robots stand on distinct cells, so pickups never contend across robots: each takes the
-    // lowest-id waiting package on its own cell
-    const int nw_prev = build_waiting(p, w, lane, t);
-    const Scan sc = scan_waiting<kSmall>(w, lane, R, nw_prev, r, c, r1, c1);
-    const bool want_pick = active && op == 1 && carry == 0;
-    const int picked = (want_pick && sc.at_new != MDX_NONE32) ? (int)w.wlist[sc.at_new] : -1;
-    const int tgt0 = carry ? (int)w.target[carry - 1] : -1;
-    const int dl0 = carry ? (int)w.dl[carry - 1] : 0;
-    const bool delivered = active && op == 2 && carry != 0 && cell1 == tgt0;
-    const bool on_time = delivered && t <= dl0;
-    const int carry1 = delivered ? 0 : (picked >= 0 ? picked + 1 : carry);
-    // env reward in float64, reference order: move costs first, then deliveries by robot index
-    const unsigned dmask = __ballot_sync(MDX_FULL, delivered), omask = __ballot_sync(MDX_FULL, on_time);
-    double rew = 0.0;
-    for (int k = 0; k < n_moved; ++k) rew = __dadd_rn(rew, p.move_cost);
-    for (unsigned mleft = dmask; mleft; mleft &= mleft - 1u) {
-      const int b = __ffs(mleft) - 1;
-      rew = __dadd_rn(rew, ((omask >> b) & 1u) ? p.delivery_reward : p.delay_reward);
-    }
-    // shaped reward reads the PREVIOUS statuses, so evaluate it before they change
-    float shaped = 0.0f;
-    if (p.out_shaped != nullptr)
-      shaped = shaped_team_reward(p, w, lane, t + 1, r, c, carry, r1, c1, carry1, mv, op, nw_prev, sc, rew);
+  for (int it = 0;; ++it) {
+    const bool has_next = widx + stride < p.n;
+    if (has_next) nxt = load_header<kMode>(p, widx + stride, lane);  // consumed in the next iteration
+    unsigned char* ebuf = ebuf0 + (it & 1) * p.ep_blk;
+    unsigned char* ebuf_next = ebuf0 + ((it + 1) & 1) * p.ep_blk;
+    bind_episode(p, w, ebuf);
+    const int env = cur.env;
+    const MapDev& map = p.maps[p.env_map ? __ldg(p.env_map + env) : 0];
+    int t = cur.t;
+    int ep = cur.ep;
+    int cell = active ? (int)(cur.rob & 0xffffu) : (0x10000 + lane);
+    int carry = active ? (int)(cur.rob >> 16) : 0;
+    cp_async_wait_all();
     __syncwarp();
-    if (delivered) w.status[carry - 1] = ST_DELIVERED;
-    if (picked >= 0) w.status[picked] = ST_IN_TRANSIT;
-    __syncwarp();
-    // ---------------- time, spawn, termination (env.py:295-306, 127-137) ----------------
-    const int t1 = t + 1;
-    bool all_delivered = true;
-    for (int base = 0; base < P; base += 32) {
-      const int j = base + lane;
-      bool ok = true;
-      if (j < P) {
-        if ((int)w.t0[j] == t1) w.status[j] = ST_WAITING;
-        ok = w.status[j] == ST_DELIVERED;
+
+    if (kMode & 1) {
+      // ---------------- decode ----------------
+      int mv, op;
+      decode_action(cur.action, mv, op);
+      // ---------------- proposals (env.py:193-201) ----------------
+      const int r = active ? (int)__umulhi((uint32_t)cell, p.mul_wout) : 0;
+      const int c = active ? cell - r * Wo : 0;
+      const int nr = r + (mv == MV_D) - (mv == MV_U);
+      const int nc = c + (mv == MV_R) - (mv == MV_L);
+      int tgt = cell;
+      if (active && nr >= 0 && nr < map.H && nc >= 0 && nc < map.W) {
+        const int ncell = nr * Wo + nc;
+        if (((__ldg(map.grid_bits + (ncell >> 5)) >> (ncell & 31)) & 1u) == 0u) tgt = ncell;
       }
-      all_delivered = all_delivered && __all_sync(MDX_FULL, ok);
-    }
-    const bool done = (t1 == p.T) || all_delivered;  // not latched
-    double total = p.total_reward[env] + rew;
-    if (lane == 0) {
-      if (p.out_reward) p.out_reward[widx] = rew;
-      if (p.out_shaped) p.out_shaped[widx] = shaped;
-      if (p.out_done) p.out_done[widx] = done ? 1 : 0;
-    }
-    // cumulative per-env counters
-    {
-      const int n_pick = __popc(__ballot_sync(MDX_FULL, picked >= 0));
+      // ---------------- resolution (env.py:203-250) as a monotone fixed point ----------------
+      // robot i moves  <=>  it is the lowest-index contender for its target cell AND that cell was
+      // empty at step start or its holder moves away.  Cycles/swaps never enter the fixed point.
+      int holder = -1;
+#pragma unroll 1
+      for (int j = 0; j < R; ++j) {
+        const int cj = __shfl_sync(MDX_FULL, cell, j);
+        if (cj == tgt && j != lane) holder = j;
+      }
+      const bool wants = active && tgt != cell;
+      const unsigned grp = __match_any_sync(MDX_FULL, tgt);
+      const unsigned wants_mask = __ballot_sync(MDX_FULL, wants);
+      const bool winner = wants && (((grp & wants_mask) & ((1u << lane) - 1u)) == 0u);
+      unsigned mm = 0u;
+      while (true) {
+        const bool m = winner && (holder < 0 || ((mm >> holder) & 1u));
+        const unsigned nm = __ballot_sync(MDX_FULL, m);
+        if (nm == mm) break;
+        mm = nm;
+      }
+      const bool moved = (mm >> lane) & 1u;
+      const int cell1 = moved ? tgt : cell;
+      const int r1 = moved ? nr : r, c1 = moved ? nc : c;
+      const int n_moved = __popc(mm);  // every mover used one of L/R/U/D (env.py:255)
+
+      // ---------------- package ops in robot order (env.py:260-292) ----------------
+      // robots stand on distinct cells, so pickups never contend across robots: each takes the
+      // lowest-id waiting package on its own cell
+      const int nw_prev = build_waiting(p, w, lane, t);
+      const Scan sc = scan_waiting<kSmall>(w, lane, R, nw_prev, r, c, r1, c1);
+      const bool want_pick = active && op == 1 && carry == 0;
+      const int picked = (want_pick && sc.at_new != MDX_NONE32) ? (int)w.wlist[sc.at_new] : -1;
+      const int tgt0 = carry ? (int)w.target[carry - 1] : -1;
+      const int dl0 = carry ? (int)w.dl[carry - 1] : 0;
+      const bool delivered = active && op == 2 && carry != 0 && cell1 == tgt0;
+      const bool on_time = delivered && t <= dl0;
+      const int carry1 = delivered ? 0 : (picked >= 0 ? picked + 1 : carry);
+      // env reward in float64, reference order: move costs first, then deliveries by robot index
+      const unsigned dmask = __ballot_sync(MDX_FULL, delivered), omask = __ballot_sync(MDX_FULL, on_time);
+      double rew = 0.0;
+#pragma unroll 1
+      for (int k = 0; k < n_moved; ++k) rew = __dadd_rn(rew, p.move_cost);
+      for (unsigned mleft = dmask; mleft; mleft &= mleft - 1u) {
+        const int b = __ffs(mleft) - 1;
+        rew = __dadd_rn(rew, ((omask >> b) & 1u) ? p.delivery_reward : p.delay_reward);
+      }
+      // shaped reward reads the PREVIOUS statuses, so evaluate it before they change
+      float shaped = 0.0f;
+      if (p.out_shaped != nullptr)
+        shaped = shaped_team_reward(p, w, lane, t + 1, r, c, carry, r1, c1, carry1, mv, op, nw_prev, sc, rew);
+      __syncwarp();
+      if (delivered) w.status[carry - 1] = ST_DELIVERED;
+      if (picked >= 0) w.status[picked] = ST_IN_TRANSIT;
+      __syncwarp();
+      // ---------------- time, spawn, termination (env.py:295-306, 127-137) ----------------
+      const int t1 = t + 1;
+      bool all_delivered = true;
+#pragma unroll 1
+      for (int base = 0; base < P; base += 32) {
+        const int j = base + lane;
+        bool ok = true;
+        if (j < P) {
+          if ((int)w.t0[j] == t1) w.status[j] = ST_WAITING;
+          ok = w.status[j] == ST_DELIVERED;
+        }
+        all_delivered = all_delivered && __all_sync(MDX_FULL, ok);
+      }
+      const bool done = (t1 == p.T) || all_delivered;  // not latched
+      double total = cur.total + rew;
       if (lane == 0) {
-        uint4* cn = reinterpret_cast<uint4*>(p.counters + (size_t)env * 8);
-        uint4 a = cn[0], b = cn[1];
-        a.y += (uint32_t)n_moved;                 // C_MOVES
-        a.z += (uint32_t)__popc(omask);           // C_ONTIME
-        a.w += (uint32_t)__popc(dmask & ~omask);  // C_LATE
-        b.x += (uint32_t)n_pick;                  // C_PICKUPS
-        b.y += 1u;                                // C_STEPS
-        if (done) {
-          a.x += 1u;            // C_EPISODES
-          b.z += (uint32_t)t1;  // C_EPLEN
+        if (p.out_reward) p.out_reward[widx] = rew;
+        if (p.out_shaped) p.out_shaped[widx] = shaped;
+        if (p.out_done) p.out_done[widx] = done ? 1 : 0;
+      }
+      // cumulative per-env counters: one fire-and-forget reduction per counter (lane = counter index)
+      {
+        const int n_pick = __popc(__ballot_sync(MDX_FULL, picked >= 0));
+        uint32_t delta = 0;
+        if (lane == C_EPISODES) delta = done ? 1u : 0u;
+        else if (lane == C_MOVES) delta = (uint32_t)n_moved;
+        else if (lane == C_ONTIME) delta = (uint32_t)__popc(omask);
+        else if (lane == C_LATE) delta = (uint32_t)__popc(dmask & ~omask);
+        else if (lane == C_PICKUPS) delta = (uint32_t)n_pick;
+        else if (lane == C_STEPS) delta = 1u;
+        else if (lane == C_EPLEN) delta = done ? (uint32_t)t1 : 0u;
+        if (lane < 7 && delta != 0u) atomicAdd(p.counters + (size_t)env * 8 + lane, delta);
+      }
+      cell = active ? cell1 : cell;
+      carry = carry1;
+      t = t1;
+      __syncwarp();
+      // ---------------- on-device auto-reset (MAPPO/trainer.py:229-234) ----------------
+      if (done && (p.flags & 1u)) {
+        if (ep + 1 < __ldg(p.ep_avail + env)) {
+          ep += 1;
+          const int slot = ep % p.E;
+          load_episode(p, w, env, slot, lane);
+          __syncwarp();
+          for (int j = lane; j < p.Pp16; j += 32)
+            w.status[j] = (j < P && w.t0[j] == 0) ? (uint8_t)ST_WAITING : (uint8_t)ST_NONE;
+          if (active) {
+            cell = __ldg(p.sched_robots + ((size_t)slot * p.n_envs + env) * 32 + lane);
+            carry = 0;
+          }
+          t = 0;
+          total = 0.0;
+          __syncwarp();
+        } else if (lane == 0) {
+          p.counters[(size_t)env * 8 + C_STARVED] = 1u;
         }
-        cn[0] = a;
-        cn[1] = b;
+      }
+      // ---------------- write the state back ----------------
+      if (active) p.robots[(size_t)env * R + lane] = (uint32_t)cell | ((uint32_t)carry << 16);
+      {
+        uint4* dst = reinterpret_cast<uint4*>(p.status + (size_t)env * p.Pp16);
+        const uint4* src = reinterpret_cast<const uint4*>(w.status);
+#pragma unroll 1
+        for (int i = lane; i < (p.Pp16 >> 4); i += 32) dst[i] = src[i];
+      }
+      if (lane == 0) {
+        p.t[env] = t;
+        p.ep[env] = ep;
+        p.total_reward[env] = total;
       }
     }
-    cell = active ? cell1 : cell;
-    carry = carry1;
-    t = t1;
-    __syncwarp();
-    // ---------------- on-device auto-reset (MAPPO/trainer.py:229-234) ----------------
-    if (done && (p.flags & 1u)) {
-      if (ep + 1 < __ldg(p.ep_avail + env)) {
-        ep += 1;
-        const int slot = ep % p.E;
-        load_episode(p, w, env, slot, lane);
-        __syncwarp();
-        for (int j = lane; j < p.Pp16; j += 32)
-          w.status[j] = (j < P && w.t0[j] == 0) ? (uint8_t)ST_WAITING : (uint8_t)ST_NONE;
-        if (active) {
-          cell = __ldg(p.sched_robots + ((size_t)slot * p.n_envs + env) * 32 + lane);
-          carry = 0;
-        }
-        t = 0;
-        total = 0.0;
-        __syncwarp();
-      } else if (lane == 0) {
-        p.counters[(size_t)env * 8 + C_STARVED] = 1u;
-      }
-    }
-    // ---------------- write the state back ----------------
-    if (active) p.robots[(size_t)env * R + lane] = (uint32_t)cell | ((uint32_t)carry << 16);
-    {
-      uint4* dst = reinterpret_cast<uint4*>(p.status + (size_t)env * p.Pp16);
-      const uint4* src = reinterpret_cast<const uint4*>(w.status);
-  #pragma unroll 1
-    for (int i = lane; i < (p.Pp16 >> 4); i += 32) dst[i] = src[i];
-    }
-    if (lane == 0) {
-      p.t[env] = t;
-      p.ep[env] = ep;
-      p.total_reward[env] = total;
-    }
-  }
 
-  if (kMode & 2) featurize_env<kS, kSmall>(p, w, lut, map, lane, widx, t, cell, carry);
+    // the next env's header has certainly arrived by now: start copying its episode block
+    if (has_next) prefetch_episode(p, ebuf_next, nxt.env, nxt.ep % p.E, lane);
+
+    if (kMode & 2) featurize_env<kS, kSmall>(p, w, lut, map, lane, widx, t, cell, carry);
+
+    if (!has_next) break;
+    cur = nxt;
+    widx += stride;
+    __syncwarp();
+  }
 }
 
 // compute_shaped_rewards on injected "current" robots against the stored state as "previous".
@@ -918,7 +978,9 @@ __global__ void __launch_bounds__(128) mdx_shape_kernel(const __grid_constant__ 
   const int wib = threadIdx.x >> 5;
   const int env = blockIdx.x * (blockDim.x >> 5) + wib;
   if (env >= p.n) return;
-  const Warp w = carve(p, smem_raw + kLutBytes + (size_t)wib * p.smem_per_warp);
+  unsigned char* wbase = smem_raw + kLutBytes + (size_t)wib * p.smem_per_warp;
+  Warp w = carve(p, wbase);
+  bind_episode(p, w, wbase + p.off_sched);
   const int R = p.R;
   const bool active = lane < R;
   const int t = p.t[env];
