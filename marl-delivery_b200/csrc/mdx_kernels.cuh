@@ -1,17 +1,20 @@
 // Hand-written sm_100a kernels of the marl-delivery hot path.
 //
-// Mapping: ONE WARP PER ENVIRONMENT, robots are lanes (R <= 32).  The reference's sequential,
-// robot-index-ordered move/collision resolution (env.py:203-250) is evaluated with
-// __match_any_sync / __ballot_sync as a monotone fixed point; package scans, the shaped reward
-// (MAPPO/helper.py:257-369) and the three featurisers (MAPPO/helper.py:6-255) run on the same warp
-// out of a shared-memory copy of the environment, and the feature tensors are written straight into
-// the caller's (torch-owned) HBM tensors with 128-bit coalesced streaming stores.
+// Mapping: ONE LANE GROUP PER ENVIRONMENT, robots are the group's lanes.  A group is a whole warp
+// (LPE = 32 lanes per env, R <= 32), a half warp (LPE = 16, R <= 16) or a quarter warp (LPE = 8,
+// R <= 8): with 5 robots most of the transition logic is warp-uniform control work, so packing 2-4
+// environments into one warp amortises those instructions while the 128-bit stores still leave the
+// warp 512 bytes at a time (LPE = 8: four 128-byte lines, one per env).  All warp collectives are
+// issued on the group's member mask.
 //
-// The kernel is bound by HBM writes (19.9 KB of mostly-zero float32 per env-step for map1/5 robots)
-// and, below that, by instruction issue, so the code is organised to spend few warp-instructions per
-// output byte: 0/1 planes live as bit masks in shared memory and are expanded four cells at a time
-// through a 16-entry nibble -> float4 table; sparse rows (gvec) are flushed as "data prefix + zero
-// tail" segments; per-robot searches over packages run package-parallel with warp reductions.
+// The reference's sequential, robot-index-ordered move/collision resolution (env.py:203-250) is
+// evaluated with __match_any_sync / __ballot_sync as a monotone fixed point; package scans, the shaped
+// reward (MAPPO/helper.py:257-369) and the three featurisers (MAPPO/helper.py:6-255) run on the same
+// group out of a shared-memory copy of the environment, and the feature tensors are written straight
+// into the caller's (torch-owned) HBM tensors with 128-bit coalesced streaming stores.  0/1 planes live
+// as bit masks and are expanded four cells at a time through a 16-entry nibble -> float4 table; sparse
+// rows (gvec) are flushed as "data prefix + zero tail" segments; per-robot searches over packages run
+// package-parallel with group reductions.
 //
 // Exactness: integers everywhere except (a) the env reward, accumulated in float64 in the reference's
 // order (env.py:181,256,288-291), (b) the shaped reward, float32 adds in the reference's order of terms
@@ -27,26 +30,47 @@
 
 namespace mdx {
 
-#define MDX_FULL 0xffffffffu
 #define MDX_NONE32 0xffffffffu
 #ifndef MDX_FEAT_BLOCKS
 #define MDX_FEAT_BLOCKS 7  // resident CTAs per SM the featurising variants are compiled for (register cap 65536 / 128 / n)
 #endif
 constexpr int kLutBytes = 256;  // block-shared nibble -> float4 table at the start of dynamic smem
 
-struct Warp {
+// A lane group: LPE consecutive lanes of a warp that own one environment.
+template <int LPE>
+struct Grp {
+  int sl;          // lane index inside the group (= robot index for sl < R)
+  int shift;       // first lane of the group inside the warp
+  unsigned mask;   // member mask of the group
+  __device__ __forceinline__ explicit Grp(int lane) {
+    sl = lane & (LPE - 1);
+    shift = lane & ~(LPE - 1);
+    mask = LPE == 32 ? 0xffffffffu : (((1u << (LPE & 31)) - 1u) << shift);
+  }
+  static __device__ __forceinline__ unsigned low() { return LPE == 32 ? 0xffffffffu : ((1u << (LPE & 31)) - 1u); }
+  __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+  __device__ __forceinline__ unsigned ballot(bool pr) const { return (__ballot_sync(mask, pr) >> shift) & low(); }  // group-relative bits
+  __device__ __forceinline__ bool all(bool pr) const { return __all_sync(mask, pr); }
+  __device__ __forceinline__ bool any(bool pr) const { return __any_sync(mask, pr); }
+  __device__ __forceinline__ unsigned match(int v) const { return (__match_any_sync(mask, v) >> shift) & low(); }
+  __device__ __forceinline__ uint32_t rmin(uint32_t v) const { return __reduce_min_sync(mask, v); }
+  template <typename T>
+  __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(mask, v, src, LPE); }  // src is group-relative
+};
+
+struct Env {
   uint16_t *start, *target, *t0, *dl;  // [Pp8] current episode schedule
   uint8_t* status;                     // [Pp16]
   uint16_t *wlist, *wrc, *wdl;         // compact waiting list: package index, start (r << 8 | c), remaining deadline
   uint16_t *alist, *sel;               // active list (gvec); selected waiting-list indices per robot (vec)
-  uint32_t* wkey;                      // per-robot selection keys of the waiting list
+  uint32_t* wkey;                      // per-robot selection keys of the waiting list (generic path)
   uint32_t* planes;                    // [10][W32] grid, robots, waiting starts, active targets, 2 x (self, others, own target)
   uint16_t *rcell, *rcarry, *rtgt, *rdl, *rrc;  // [32] per robot
   float* stage;                        // 16-byte aligned staging for vec / gvec rows
 };
 
-__device__ __forceinline__ Warp carve(const KParams& p, unsigned char* base) {
-  Warp w;
+__device__ __forceinline__ Env carve(const KParams& p, unsigned char* base) {
+  Env w;
   uint16_t* s = reinterpret_cast<uint16_t*>(base + p.off_sched);
   w.start = s;
   w.target = s + p.Pp8;
@@ -79,33 +103,36 @@ __device__ __forceinline__ float tnorm(const KParams& p, int k) {
   return p.T > 0 ? tnorm_slow(k, p.T) : 0.0f;
 }
 
-__device__ __forceinline__ void load_episode(const KParams& p, const Warp& w, int env, int slot, int lane) {
+template <int LPE>
+__device__ __forceinline__ void load_episode(const KParams& p, const Env& w, int env, int slot, int sl) {
   const uint4* src = reinterpret_cast<const uint4*>(p.sched + ((size_t)slot * p.n_envs + env) * 4 * p.Pp8);
   uint4* dst = reinterpret_cast<uint4*>(w.start);
   const int n16 = p.Pp8 >> 1;  // 4 rows * Pp8 u16 * 2 B / 16 B
 #pragma unroll 1
-  for (int i = lane; i < n16; i += 32) dst[i] = __ldg(src + i);
+  for (int i = sl; i < n16; i += LPE) dst[i] = __ldg(src + i);
 }
 
-// numpy float32 add.reduce over R lane values (pairwise_sum: plain loop for n < 8, eight running
-// partials for 8 <= n <= 128); every lane returns the same value.
-__device__ __forceinline__ float warp_np_sum(float v, int R) {
+// numpy float32 add.reduce over the R robot lanes (pairwise_sum: plain loop for n < 8, eight running
+// partials for 8 <= n <= 128); every lane of the group returns the same value.
+template <int LPE>
+__device__ __forceinline__ float group_np_sum(const Grp<LPE>& g, float v, int R) {
   if (R < 8) {
     float s = 0.0f;
-    for (int i = 0; i < R; ++i) s = __fadd_rn(s, __shfl_sync(MDX_FULL, v, i));
+#pragma unroll 1
+    for (int i = 0; i < R; ++i) s = __fadd_rn(s, g.shfl(v, i));
     return s;
   }
   float r[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) r[j] = __shfl_sync(MDX_FULL, v, j);
+  for (int j = 0; j < 8; ++j) r[j] = g.shfl(v, j);
   int i = 8;
   for (; i < R - (R % 8); i += 8) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], __shfl_sync(MDX_FULL, v, i + j));
+    for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], g.shfl(v, i + j));
   }
   float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
                         __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-  for (; i < R; ++i) res = __fadd_rn(res, __shfl_sync(MDX_FULL, v, i));
+  for (; i < R; ++i) res = __fadd_rn(res, g.shfl(v, i));
   return res;
 }
 
@@ -113,41 +140,45 @@ __device__ __forceinline__ float warp_np_sum(float v, int R) {
 // zeros.  `stage` is 16-byte aligned, the row starts at stage[off] with off == (global float index
 // & 3) so shared and global addresses are congruent modulo 16 bytes and the body moves as aligned
 // float4; the stage must be zero for at least 4 floats past n_data.
-__device__ __forceinline__ void flush_seg(float* gdst, const float* stage, int off, int n_data, int n_total, int lane) {
+template <int LPE>
+__device__ __forceinline__ void flush_seg(float* gdst, const float* stage, int off, int n_data, int n_total, int sl) {
   const float* s = stage + off;
   int head = (4 - off) & 3;
   if (head > n_total) head = n_total;
-  if (lane < head) __stcs(gdst + lane, lane < n_data ? s[lane] : 0.0f);
+  if (sl < head) __stcs(gdst + sl, sl < n_data ? s[sl] : 0.0f);
   const int body = (n_total - head) >> 2;
   const float4* s4 = reinterpret_cast<const float4*>(s + head);
   float4* g4 = reinterpret_cast<float4*>(gdst + head);
   int live = n_data > head ? (n_data - head + 3) >> 2 : 0;  // float4s that carry data
   if (live > body) live = body;
 #pragma unroll 1
-  for (int i = lane; i < live; i += 32) __stcs(g4 + i, s4[i]);
+  for (int i = sl; i < live; i += LPE) __stcs(g4 + i, s4[i]);
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-  for (int i = live + lane; i < body; i += 32) __stcs(g4 + i, z4);
+  for (int i = live + sl; i < body; i += LPE) __stcs(g4 + i, z4);
   const int done = head + (body << 2);
-  if (lane < n_total - done) __stcs(gdst + done + lane, done + lane < n_data ? s[done + lane] : 0.0f);
+  if (sl < n_total - done) __stcs(gdst + done + sl, done + sl < n_data ? s[done + sl] : 0.0f);
 }
 
-__device__ __forceinline__ void zero_stage(float* stage, int n_floats, int lane) {
+template <int LPE>
+__device__ __forceinline__ void zero_stage(float* stage, int n_floats, int sl) {
   float4* s4 = reinterpret_cast<float4*>(stage);
   const int n4 = (n_floats + 3) >> 2;
 #pragma unroll 1
-  for (int i = lane; i < n4; i += 32) s4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = sl; i < n4; i += LPE) s4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // Compact list of packages that are 'waiting' with start_time <= t, in id order: package index and
 // packed start position.  Returns the count.
-__device__ __forceinline__ int build_waiting(const KParams& p, const Warp& w, int lane, int t) {
+template <int LPE>
+__device__ __forceinline__ int build_waiting(const KParams& p, const Env& w, const Grp<LPE>& g, int t) {
   int nw = 0;
-  const unsigned lt = (1u << lane) - 1u;
-  for (int base = 0; base < p.P; base += 32) {
-    const int j = base + lane;
+  const unsigned lt = (1u << g.sl) - 1u;
+#pragma unroll 1
+  for (int base = 0; base < p.P; base += LPE) {
+    const int j = base + g.sl;
     const bool wait = j < p.P && w.status[j] == ST_WAITING && (int)w.t0[j] <= t;
-    const unsigned m = __ballot_sync(MDX_FULL, wait);
+    const unsigned m = g.ballot(wait);
     if (wait) {
       const int k = nw + __popc(m & lt);
       const uint32_t sc = w.start[j];
@@ -157,7 +188,7 @@ __device__ __forceinline__ int build_waiting(const KParams& p, const Warp& w, in
     }
     nw += __popc(m);
   }
-  __syncwarp();
+  g.sync();
   return nw;
 }
 
@@ -169,47 +200,46 @@ struct Scan {
 
 // For every robot: nearest waiting package from its old cell (MAPPO/helper.py:346-349), "waiting
 // package within 3" (:360-365) and the lowest-id waiting package on its new cell (env.py:267-274,
-// MAPPO/helper.py:312-317).  Package-parallel: lanes own list entries (two in registers when
-// P <= 64), one warp reduction per robot.
-template <bool kSmall>
-__device__ __forceinline__ Scan scan_waiting(const Warp& w, int lane, int R, int nw, int r0, int c0, int r1, int c1) {
+// MAPPO/helper.py:312-317).  Package-parallel: lanes own list entries (64 / LPE of them in registers
+// when P <= 64), one group reduction per robot.
+template <int LPE, bool kSmall>
+__device__ __forceinline__ Scan scan_waiting(const Env& w, const Grp<LPE>& g, int R, int nw, int r0, int c0, int r1, int c1) {
+  constexpr int EPL = 64 / LPE;  // entries per lane when P <= 64
   Scan mine{MDX_NONE32, MDX_NONE32, false};
   if (nw == 0) return mine;
   const uint32_t rc1 = ((uint32_t)r1 << 8) | (uint32_t)c1;
-  uint32_t e0 = 0, e1 = 0;
-  const bool h0 = lane < nw, h1 = lane + 32 < nw;
+  uint32_t e[EPL];
   if (kSmall) {
-    if (h0) e0 = w.wrc[lane];
-    if (h1) e1 = w.wrc[lane + 32];
+#pragma unroll
+    for (int s = 0; s < EPL; ++s) e[s] = (g.sl + LPE * s < nw) ? (uint32_t)w.wrc[g.sl + LPE * s] : MDX_NONE32;
   }
 #pragma unroll 1
   for (int i = 0; i < R; ++i) {
-    const int ri = __shfl_sync(MDX_FULL, r0, i), ci = __shfl_sync(MDX_FULL, c0, i);
-    const uint32_t rci = __shfl_sync(MDX_FULL, rc1, i);
+    const int ri = g.shfl(r0, i), ci = g.shfl(c0, i);
+    const uint32_t rci = g.shfl(rc1, i);
     uint32_t best = MDX_NONE32, at_new = MDX_NONE32;
     if (kSmall) {
-      if (h0) {
-        const int d = abs((int)(e0 >> 8) - ri) + abs((int)(e0 & 255u) - ci);
-        best = ((uint32_t)d << 16) | (uint32_t)lane;
-        if (e0 == rci) at_new = (uint32_t)lane;
-      }
-      if (h1) {
-        const int d = abs((int)(e1 >> 8) - ri) + abs((int)(e1 & 255u) - ci);
-        best = min(best, ((uint32_t)d << 16) | (uint32_t)(lane + 32));
-        if (e1 == rci) at_new = min(at_new, (uint32_t)(lane + 32));
+#pragma unroll
+      for (int s = 0; s < EPL; ++s) {
+        if (e[s] != MDX_NONE32) {
+          const uint32_t k = (uint32_t)(g.sl + LPE * s);
+          const int d = abs((int)(e[s] >> 8) - ri) + abs((int)(e[s] & 255u) - ci);
+          best = min(best, ((uint32_t)d << 16) | k);
+          if (e[s] == rci) at_new = min(at_new, k);
+        }
       }
     } else {
 #pragma unroll 1
-      for (int k = lane; k < nw; k += 32) {
+      for (int k = g.sl; k < nw; k += LPE) {
         const uint32_t rc = w.wrc[k];
         const int d = abs((int)(rc >> 8) - ri) + abs((int)(rc & 255u) - ci);
         best = min(best, ((uint32_t)d << 16) | (uint32_t)k);
         if (rc == rci) at_new = min(at_new, (uint32_t)k);
       }
     }
-    best = __reduce_min_sync(MDX_FULL, best);
-    at_new = __reduce_min_sync(MDX_FULL, at_new);
-    if (lane == i) {
+    best = g.rmin(best);
+    at_new = g.rmin(at_new);
+    if (g.sl == i) {
       mine.best = best;
       mine.at_new = at_new;
       mine.near = (best >> 16) <= 3u;  // the minimum distance decides "some waiting start within 3"
@@ -220,11 +250,12 @@ __device__ __forceinline__ Scan scan_waiting(const Warp& w, int lane, int R, int
 
 // Shaped team reward of one transition (MAPPO/helper.py:257-369).  Per lane (robot): old / new
 // position and carried id, decoded action, the scan above; w.status still holds the PREVIOUS statuses.
-__device__ __forceinline__ float shaped_team_reward(const KParams& p, const Warp& w, int lane, int t_cur, int r0, int c0,
-                                                    int k0, int r1, int c1, int k1, int mv, int op, int nw,
+template <int LPE>
+__device__ __forceinline__ float shaped_team_reward(const KParams& p, const Env& w, const Grp<LPE>& g, int t_cur, int r0,
+                                                    int c0, int k0, int r1, int c1, int k1, int mv, int op, int nw,
                                                     const Scan& sc, double env_reward) {
   float acc = 0.0f;
-  if (lane < p.R) {
+  if (g.sl < p.R) {
     const uint8_t st0 = k0 ? w.status[k0 - 1] : (uint8_t)ST_NONE;
     const bool tracked = k0 != 0 && (st0 == ST_WAITING || st0 == ST_IN_TRANSIT);
     int gr = -1, gc = 0, dl0 = 0;
@@ -276,7 +307,7 @@ __device__ __forceinline__ float shaped_team_reward(const KParams& p, const Warp
     // 4. idle next to work (:359-367)
     if (!moved && mv == MV_S && k0 == 0 && sc.near) acc = __fadd_rn(acc, p.shaping[7]);
   }
-  const float s = warp_np_sum(acc, p.R);
+  const float s = group_np_sum<LPE>(g, acc, p.R);
   // python float + np.float32 -> float32 under numpy >= 2
   return __fadd_rn(__double2float_rn(env_reward), s);
 }
@@ -296,19 +327,22 @@ __device__ __forceinline__ void decode_action(int a, int& mv, int& op) {
 
 // ------------------------------------------------------------------------------------------------
 // Featurisation of the env held in shared memory (statuses, schedule) and registers (cell / carry of
-// robot `lane`), MAPPO/helper.py:6-255.  `row` selects the output row.
-//   kS     > 0: a plane is kS slices of 32 float4 (H*W <= 128*kS, H*W % 4 == 0); the four shared planes'
-//               nibbles are hoisted into registers and every robot costs 6 table loads + 6 stores per slice.
+// robot `sl`), MAPPO/helper.py:6-255.  `row` selects the output row.
+//   kS     > 0: a plane is at most kS slices of LPE float4 (H*W % 4 == 0, H*W <= 4*LPE*kS); the four
+//               shared planes' nibbles are hoisted into registers and every robot costs 6 table loads +
+//               6 stores per slice.
 //          = 0: generic flat loops over per-robot bit planes (any H*W).
-//   kSmall:     P <= 64, so a lane owns at most two waiting-list entries and keeps their selection keys
-//               in registers.
-template <int kS, bool kSmall>
-__device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, const float4* lut, const MapDev& map,
-                                              int lane, int row, int t, int cell, int carry) {
+//   kSmall:     P <= 64, so a lane owns at most 64/LPE waiting-list entries and keeps their selection
+//               keys in registers.
+template <int LPE, int kS, bool kSmall>
+__device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, const Grp<LPE>& g, const float4* lut,
+                                              const MapDev& map, int row, int t, int cell, int carry) {
+  constexpr int EPL = 64 / LPE;
+  const int sl = g.sl;
   const int R = p.R, P = p.P, W32 = p.W32, HW = p.HW, Wo = p.W_out;
   const int Hm1 = p.H_out - 1, Wm1 = p.W_out - 1, NC = 2 * p.W_out - 1;
-  const unsigned lt = (1u << lane) - 1u;
-  const bool active = lane < R;
+  const unsigned lt = (1u << sl) - 1u;
+  const bool active = sl < R;
   const int r = active ? (int)__umulhi((uint32_t)cell, p.mul_wout) : 0;
   const int c = active ? cell - r * Wo : 0;
   const float* qr = map.qr;
@@ -325,25 +359,25 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
       tr_own = (int)__umulhi((uint32_t)own_tgt, p.mul_wout);
       tc_own = own_tgt - tr_own * Wo;
     }
-    w.rcell[lane] = (uint16_t)cell;
-    w.rcarry[lane] = (uint16_t)carry;
-    w.rtgt[lane] = (uint16_t)own_tgt;
-    w.rdl[lane] = (uint16_t)own_rem;
-    w.rrc[lane] = (uint16_t)((r << 8) | c);
+    w.rcell[sl] = (uint16_t)cell;
+    w.rcarry[sl] = (uint16_t)carry;
+    w.rtgt[sl] = (uint16_t)own_tgt;
+    w.rdl[sl] = (uint16_t)own_rem;
+    w.rrc[sl] = (uint16_t)((r << 8) | c);
   }
 #pragma unroll 1
-  for (int i = lane; i < W32; i += 32) {
+  for (int i = sl; i < W32; i += LPE) {
     w.planes[i] = __ldg(map.grid_bits + i);
     w.planes[W32 + i] = 0u;
     w.planes[2 * W32 + i] = 0u;
     w.planes[3 * W32 + i] = 0u;
   }
-  __syncwarp();
+  g.sync();
   if (active) atomicOr(&w.planes[W32 + (cell >> 5)], 1u << (cell & 31));
   int nw = 0, na = 0;
 #pragma unroll 1
-  for (int base = 0; base < P; base += 32) {
-    const int j = base + lane;
+  for (int base = 0; base < P; base += LPE) {
+    const int j = base + sl;
     const uint8_t st = j < P ? w.status[j] : (uint8_t)ST_NONE;
     const bool wait = j < P && st == ST_WAITING && (int)w.t0[j] <= t;
     const bool act = wait || (j < P && st == ST_IN_TRANSIT);
@@ -356,7 +390,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
       const int tc = w.target[j];
       atomicOr(&w.planes[3 * W32 + (tc >> 5)], 1u << (tc & 31));
     }
-    const unsigned wm = __ballot_sync(MDX_FULL, wait), am = __ballot_sync(MDX_FULL, act);
+    const unsigned wm = g.ballot(wait), am = g.ballot(act);
     if (wait) {
       const int k = nw + __popc(wm & lt);
       const uint32_t sr = __umulhi(sc, p.mul_wout);
@@ -371,17 +405,19 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
     nw += __popc(wm);
     na += __popc(am);
   }
-  __syncwarp();
+  g.sync();
 
   if (kS > 0) {
-    // ---- plane-structured path: lane owns float4 number (lane + 32*s) of every plane ------------
+    // ---- plane-structured path: lane owns float4 number (sl + LPE*s) of every plane -------------
+    constexpr int NS = kS > 0 ? kS : 1;
     const int n4p = HW >> 2;
-    const uint32_t sh = (uint32_t)(lane & 7) << 2;
-    uint32_t ng[kS > 0 ? kS : 1], nrb[kS > 0 ? kS : 1], nws[kS > 0 ? kS : 1], nat[kS > 0 ? kS : 1];
+    uint32_t ng[NS], nrb[NS], nws[NS], nat[NS];
 #pragma unroll
-    for (int s_ = 0; s_ < kS; ++s_) {
-      const int wi = (lane >> 3) + 4 * s_;
-      const bool ok = lane + 32 * s_ < n4p;
+    for (int s_ = 0; s_ < NS; ++s_) {
+      const int q = sl + LPE * s_;
+      const int wi = q >> 3;
+      const uint32_t sh = (uint32_t)(q & 7) << 2;
+      const bool ok = q < n4p;
       ng[s_] = ok ? (w.planes[wi] >> sh) & 15u : 0u;
       nrb[s_] = ok ? (w.planes[W32 + wi] >> sh) & 15u : 0u;
       nws[s_] = ok ? (w.planes[2 * W32 + wi] >> sh) & 15u : 0u;
@@ -390,8 +426,8 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
     if (p.gstate != nullptr) {
       float4* out4 = reinterpret_cast<float4*>(p.gstate + (size_t)row * 4 * HW);
 #pragma unroll
-      for (int s_ = 0; s_ < kS; ++s_) {
-        const int q = lane + 32 * s_;
+      for (int s_ = 0; s_ < NS; ++s_) {
+        const int q = sl + LPE * s_;
         if (q < n4p) {
           __stcs(out4 + q, lut[ng[s_]]);
           __stcs(out4 + n4p + q, lut[nrb[s_]]);
@@ -407,8 +443,8 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
         const uint32_t rc = w.rcell[i], tg = w.rtgt[i];  // tg = 0xFFFF (none) never matches: tg >> 2 > any q
         float4* out4 = base4 + (size_t)i * 6 * n4p;
 #pragma unroll
-        for (int s_ = 0; s_ < kS; ++s_) {
-          const int q = lane + 32 * s_;
+        for (int s_ = 0; s_ < NS; ++s_) {
+          const int q = sl + LPE * s_;
           if (q < n4p) {
             const uint32_t oh_r = ((rc >> 2) == (uint32_t)q) ? (1u << (rc & 3u)) : 0u;
             const uint32_t oh_t = ((tg >> 2) == (uint32_t)q) ? (1u << (tg & 3u)) : 0u;
@@ -429,7 +465,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
       if ((HW & 3) == 0) {
         float4* out4 = reinterpret_cast<float4*>(out);
 #pragma unroll 1
-        for (int q = lane; q < HW; q += 32) {  // 4 planes * HW / 4 float4s
+        for (int q = sl; q < HW; q += LPE) {  // 4 planes * HW / 4 float4s
           const uint32_t e = (uint32_t)q << 2;
           const uint32_t ch = __umulhi(e, p.mul_plane);
           const uint32_t cl = e - ch * HW;
@@ -438,7 +474,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
         }
       } else {
 #pragma unroll 1
-        for (int e = lane; e < 4 * HW; e += 32) {
+        for (int e = sl; e < 4 * HW; e += LPE) {
           const uint32_t ch = __umulhi((uint32_t)e, p.mul_plane);
           const uint32_t cl = (uint32_t)e - ch * HW;
           __stcs(out + e, ((w.planes[ch * W32 + (cl >> 5)] >> (cl & 31u)) & 1u) ? 1.0f : 0.0f);
@@ -451,13 +487,13 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
         const int b = 4 + 3 * (i & 1);
         const uint32_t rc = w.rcell[i], tg = w.rtgt[i];
 #pragma unroll 1
-        for (int x = lane; x < W32; x += 32) {
+        for (int x = sl; x < W32; x += LPE) {
           const uint32_t self = ((rc >> 5) == (uint32_t)x) ? (1u << (rc & 31u)) : 0u;
           w.planes[b * W32 + x] = self;
           w.planes[(b + 1) * W32 + x] = w.planes[W32 + x] & ~self;
           w.planes[(b + 2) * W32 + x] = ((tg >> 5) == (uint32_t)x) ? (1u << (tg & 31u)) : 0u;  // tg = 0xFFFF: no word matches
         }
-        __syncwarp();
+        g.sync();
         // channel -> plane: 0 grid, 1 self, 2 others, 3 waiting starts, 4 active targets, 5 own target
         const uint32_t pmap = 0u | ((uint32_t)b << 4) | ((uint32_t)(b + 1) << 8) | (2u << 12) | (3u << 16) | ((uint32_t)(b + 2) << 20);
         float* out = p.obs + ((size_t)row * R + i) * 6 * HW;
@@ -465,7 +501,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
           float4* out4 = reinterpret_cast<float4*>(out);
           const int n4 = (6 * HW) >> 2;
 #pragma unroll 1
-          for (int q = lane; q < n4; q += 32) {
+          for (int q = sl; q < n4; q += LPE) {
             const uint32_t e = (uint32_t)q << 2;
             const uint32_t ch = __umulhi(e, p.mul_plane);
             const uint32_t cl = e - ch * HW;
@@ -475,7 +511,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
           }
         } else {
 #pragma unroll 1
-          for (int e = lane; e < 6 * HW; e += 32) {
+          for (int e = sl; e < 6 * HW; e += LPE) {
             const uint32_t ch = __umulhi((uint32_t)e, p.mul_plane);
             const uint32_t cl = (uint32_t)e - ch * HW;
             const uint32_t pl = (pmap >> (ch << 2)) & 15u;
@@ -501,39 +537,23 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
     const int nsel = min(Ksel, nw);
     const int rpf = p.vec_rows_per_flush;
     // lanes as (robot, other) pairs for the stable sort of the other robots
-    const int G = p.pair_g;  // robots per pass = 32 / R
-    const int gi = (int)__umulhi((uint32_t)lane, p.mul_r), gj = lane - gi * R;
-    // selection keys: (remaining deadline * nranks + rank of the float64 distance key) << wbits | list index.
-    // The robot-independent parts of a lane's own entries are computed once: key base and the entry's
-    // offset into the rank table (the robot contributes a uniform offset).
-    uint32_t kb0 = 0, kb1 = 0;
-    int be0 = 0, be1 = 0;
-    if (kSmall) {
-      if (lane < nw) {
-        const uint32_t rc = w.wrc[lane];
-        be0 = (int)(rc >> 8) * NC + (int)(rc & 255u);
-        kb0 = (((uint32_t)w.wdl[lane] * (uint32_t)p.nranks_max) << p.key_wbits) | (uint32_t)lane;
-      }
-      if (lane + 32 < nw) {
-        const uint32_t rc = w.wrc[lane + 32];
-        be1 = (int)(rc >> 8) * NC + (int)(rc & 255u);
-        kb1 = (((uint32_t)w.wdl[lane + 32] * (uint32_t)p.nranks_max) << p.key_wbits) | (uint32_t)(lane + 32);
-      }
-    }
-    const bool lane_sel = kSmall && Ksel <= 32;  // winners are kept in lanes instead of shared memory
-    const int RP = lane_sel ? p.sel_rp : 1;      // robots per pass = 32 / Ksel
-    const int sel_ii = (int)__umulhi((uint32_t)lane, p.mul_ksel), sel_q = lane - sel_ii * Ksel;
+    const int gi = (int)__umulhi((uint32_t)sl, p.mul_r), gj = sl - gi * R;
+    const int G = (int)__umulhi((uint32_t)LPE, p.mul_r);  // robots per pass = LPE / R
+    // winners of the package selection are kept in lanes when a robot's slots fit the group
+    const bool lane_sel = kSmall && Ksel <= LPE;
+    const int RP = lane_sel ? (int)__umulhi((uint32_t)LPE, p.mul_ksel) : 1;  // robots per pass = LPE / Ksel
+    const int sel_ii = (int)__umulhi((uint32_t)sl, p.mul_ksel), sel_q = sl - sel_ii * Ksel;
 #pragma unroll 1
     for (int i0 = 0; i0 < R; i0 += rpf) {
       const int nrows = min(rpf, R - i0);
       const size_t g0 = ((size_t)row * R + i0) * D;
       const int off = (int)(g0 & 3);
-      zero_stage(w.stage, nrows * D + 4, lane);
-      __syncwarp();
+      zero_stage<LPE>(w.stage, nrows * D + 4, sl);
+      g.sync();
       float* chunk = w.stage + off;
       // own block (:93-112) and global time (:163)
-      if (lane >= i0 && lane < i0 + nrows) {
-        float* rowp = chunk + (lane - i0) * D;
+      if (sl >= i0 && sl < i0 + nrows) {
+        float* rowp = chunk + (sl - i0) * D;
         rowp[0] = __ldg(qr + (r + Hm1));
         rowp[1] = __ldg(qc + (c + Wm1));
         rowp[2] = cflag;
@@ -560,9 +580,9 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
           }
           int pos = 0;
 #pragma unroll 1
-          for (int k = 0; k < R; ++k) pos += (__shfl_sync(MDX_FULL, okey, gi * R + k) < okey) ? 1 : 0;
-          const float cf_j = __shfl_sync(MDX_FULL, cflag, gj);
-          const float otr_j = __shfl_sync(MDX_FULL, ot_r, gj), otc_j = __shfl_sync(MDX_FULL, ot_c, gj);
+          for (int k = 0; k < R; ++k) pos += (g.shfl(okey, gi * R + k) < okey) ? 1 : 0;
+          const float cf_j = g.shfl(cflag, gj);
+          const float otr_j = g.shfl(ot_r, gj), otc_j = g.shfl(ot_c, gj);
           if (valid && pos < K_o) {
             float* o = chunk + (i - i0) * D + 6 + pos * 5;
             o[0] = __ldg(qr + (dr + Hm1));
@@ -574,8 +594,10 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
         }
       }
       // waiting packages, stable-sorted by (remaining deadline, key rank) (:143-160): per robot,
-      // min(K_p, n_waiting) rounds of a warp arg-min over the unique keys; the winner of round q for the
-      // ii-th robot of a pass is remembered by lane ii*Ksel+q, which then writes that row.
+      // min(K_p, n_waiting) rounds of a group arg-min over the unique keys
+      //   (remaining deadline * nranks + rank of the float64 distance key) << wbits | list index;
+      // the winner of round q for the ii-th robot of a pass is remembered by lane ii*Ksel+q, which then
+      // writes that row.
       if (nsel > 0 && lane_sel) {
 #pragma unroll 1
         for (int ib = i0; ib < i0 + nrows; ib += RP) {
@@ -585,16 +607,28 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
           for (int ii = 0; ii < npass; ++ii) {
             const uint32_t rci = w.rrc[ib + ii];
             const int bi = (Hm1 - (int)(rci >> 8)) * NC + (Wm1 - (int)(rci & 255u));
-            uint32_t k0 = MDX_NONE32, k1 = MDX_NONE32;
-            if (lane < nw) k0 = kb0 + ((uint32_t)__ldg(map.rank + (be0 + bi)) << p.key_wbits);
-            if (lane + 32 < nw) k1 = kb1 + ((uint32_t)__ldg(map.rank + (be1 + bi)) << p.key_wbits);
+            uint32_t key[EPL];
+#pragma unroll
+            for (int s = 0; s < EPL; ++s) {
+              const int k = sl + LPE * s;
+              key[s] = MDX_NONE32;
+              if (k < nw) {
+                const uint32_t rc = w.wrc[k];
+                const uint32_t rk = __ldg(map.rank + ((int)(rc >> 8) * NC + (int)(rc & 255u) + bi));
+                key[s] = (((uint32_t)w.wdl[k] * (uint32_t)p.nranks_max + rk) << p.key_wbits) | (uint32_t)k;
+              }
+            }
             const int x0 = ii * Ksel;
 #pragma unroll 1
             for (int q = 0; q < nsel; ++q) {
-              const uint32_t best = __reduce_min_sync(MDX_FULL, min(k0, k1));
-              if (lane == x0 + q) mysel = best & wmask;
-              if (k0 == best) k0 = MDX_NONE32;  // keys are unique: exactly one entry is retired
-              if (k1 == best) k1 = MDX_NONE32;
+              uint32_t lm = key[0];
+#pragma unroll
+              for (int s = 1; s < EPL; ++s) lm = min(lm, key[s]);
+              const uint32_t best = g.rmin(lm);
+              if (sl == x0 + q) mysel = best & wmask;
+#pragma unroll
+              for (int s = 0; s < EPL; ++s)
+                if (key[s] == best) key[s] = MDX_NONE32;  // keys are unique: exactly one entry is retired
             }
           }
           if (sel_ii < npass && sel_q < nsel) {
@@ -621,7 +655,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
           uint16_t* selp = w.sel + (i - i0) * Ksel;
           uint32_t lm = MDX_NONE32;
 #pragma unroll 1
-          for (int k = lane; k < nw; k += 32) {
+          for (int k = sl; k < nw; k += LPE) {
             const uint32_t rc = w.wrc[k];
             const uint32_t rk = __ldg(map.rank + ((int)(rc >> 8) - ri + Hm1) * NC + ((int)(rc & 255u) - ci + Wm1));
             const uint32_t key = (((uint32_t)w.wdl[k] * (uint32_t)p.nranks_max + rk) << p.key_wbits) | (uint32_t)k;
@@ -630,21 +664,21 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
           }
 #pragma unroll 1
           for (int q = 0; q < nsel; ++q) {
-            const uint32_t best = __reduce_min_sync(MDX_FULL, lm);
+            const uint32_t best = g.rmin(lm);
             if (lm == best) {  // exactly one lane: keys are unique
               const uint32_t k = best & wmask;
               selp[q] = (uint16_t)k;
               w.wkey[k] = MDX_NONE32;
               lm = MDX_NONE32;
 #pragma unroll 1
-              for (int kk = lane; kk < nw; kk += 32) lm = min(lm, w.wkey[kk]);
+              for (int kk = sl; kk < nw; kk += LPE) lm = min(lm, w.wkey[kk]);
             }
           }
         }
-        __syncwarp();
+        g.sync();
         const int nslot = nrows * Ksel;
 #pragma unroll 1
-        for (int x = lane; x < nslot; x += 32) {
+        for (int x = sl; x < nslot; x += LPE) {
           const int ii = (int)__umulhi((uint32_t)x, p.mul_ksel), q = x - ii * Ksel;
           if (q < nsel) {
             const uint32_t rci = w.rrc[i0 + ii];
@@ -663,9 +697,9 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
           }
         }
       }
-      __syncwarp();
-      flush_seg(p.vec + g0, w.stage, off, nrows * D, nrows * D, lane);
-      __syncwarp();
+      g.sync();
+      flush_seg<LPE>(p.vec + g0, w.stage, off, nrows * D, nrows * D, sl);
+      g.sync();
     }
   }
 
@@ -679,11 +713,11 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
     const int nA = 6 * min(R, MR), nrow = min(na, MP), nB = 7 * nrow;
     float* stA = w.stage;
     float* stB = w.stage + p.stage_b;
-    zero_stage(stA, nA + 8, lane);
-    zero_stage(stB, nB + 8, lane);
-    __syncwarp();
-    if (active && lane < MR) {
-      float* o = stA + offA + lane * 6;
+    zero_stage<LPE>(stA, nA + 8, sl);
+    zero_stage<LPE>(stB, nB + 8, sl);
+    g.sync();
+    if (active && sl < MR) {
+      float* o = stA + offA + sl * 6;
       o[0] = __ldg(qr + (r + Hm1));
       o[1] = __ldg(qc + (c + Wm1));
       o[2] = carry != 0 ? 1.0f : 0.0f;
@@ -694,7 +728,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
       }
     }
 #pragma unroll 1
-    for (int k = lane; k < nrow; k += 32) {
+    for (int k = sl; k < nrow; k += LPE) {
       const int j = w.alist[k];
       const bool wait = w.status[j] == ST_WAITING;
       const uint32_t sc = w.start[j], tc_ = w.target[j];
@@ -719,18 +753,51 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Warp& w, c
       }
       o[6] = cn;
     }
-    __syncwarp();
-    flush_seg(p.gvec + gA, stA, offA, nA, 6 * MR, lane);
-    flush_seg(p.gvec + gB, stB, offB, nB, 7 * MP, lane);
-    if (lane == 0) __stcs(p.gvec + gA + Dg - 1, tnorm(p, t));
-    __syncwarp();
+    g.sync();
+    flush_seg<LPE>(p.gvec + gA, stA, offA, nA, 6 * MR, sl);
+    flush_seg<LPE>(p.gvec + gB, stB, offB, nB, 7 * MP, sl);
+    if (sl == 0) __stcs(p.gvec + gA + Dg - 1, tnorm(p, t));
+    g.sync();
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // kMode bit 0: step (+ shaped reward, + optional auto-reset);  bit 1: featurise.
-template <int kMode, int kS, bool kSmall>
-__global__ void __launch_bounds__(128, (kMode & 2) ? MDX_FEAT_BLOCKS : 8) mdx_env_kernel(const __grid_constant__ KParams p) {
+// LPE lanes per environment: a 128-thread CTA holds 128 / LPE environments.
+// kFix: shape specialisation.  0 = every shape parameter is read from KParams at run time; 1 = the
+// headline MAPPO shape (C3: map1 10x10, 5 robots, <= 56 packages, K_o = 4, K_p = 5, MR = MP = 100) is baked
+// in as compile-time constants, so loops over robots / planes / rows unroll and the index arithmetic folds.
+template <int kFix>
+__device__ __forceinline__ void specialise(KParams& p) {
+  if (kFix == 1) {
+    p.R = 5;
+    p.Pp8 = 56;
+    p.Pp16 = 64;
+    p.H_out = 10;
+    p.W_out = 10;
+    p.HW = 100;
+    p.W32 = 4;
+    p.K_o = 4;
+    p.K_p = 5;
+    p.sel_k = 5;
+    p.MR = 100;
+    p.MP = 100;
+    p.D = 52;
+    p.Dg = 1301;
+    p.vec_rows_per_flush = 5;
+    p.mul_wout = 429496730u;   // ceil(2^32 / 10)
+    p.mul_r = 858993460u;      // ceil(2^32 / 5)
+    p.mul_ksel = 858993460u;
+    p.mul_plane = 42949673u;   // ceil(2^32 / 100)
+    p.pair_g = 6;
+    p.stage_b = 44;            // round_up(6 * 5 + 12, 4)
+  }
+}
+
+template <int kMode, int LPE, int kS, bool kSmall, int kFix>
+__global__ void __launch_bounds__(128, (kMode & 2) ? MDX_FEAT_BLOCKS : 8) mdx_env_kernel(const __grid_constant__ KParams pg) {
+  KParams p = pg;
+  specialise<kFix>(p);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const float4* lut = reinterpret_cast<const float4*>(smem_raw);
   if (kMode & 2) {
@@ -741,34 +808,35 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? MDX_FEAT_BLOCKS : 8) mdx_en
     }
     __syncthreads();
   }
-  const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  const int widx = blockIdx.x * (blockDim.x >> 5) + wib;
-  if (widx >= p.n) return;
-  const Warp w = carve(p, smem_raw + kLutBytes + (size_t)wib * p.smem_per_warp);
+  const int gib = threadIdx.x / LPE;  // group index inside the CTA
+  const int widx = blockIdx.x * (blockDim.x / LPE) + gib;
+  if (widx >= p.n) return;  // whole groups leave; every collective below names only the group's lanes
+  const Grp<LPE> g(threadIdx.x & 31);
+  const int sl = g.sl;
+  const Env w = carve(p, smem_raw + kLutBytes + (size_t)gib * p.smem_per_warp);
   const int env = p.env_ids ? __ldg(p.env_ids + widx) : widx;
   const int R = p.R, P = p.P, Wo = p.W_out;
-  const bool active = lane < R;
+  const bool active = sl < R;
   const MapDev& map = p.maps[p.env_map ? __ldg(p.env_map + env) : 0];
 
   int t = p.t[env];
   int ep = p.ep[env];
-  load_episode(p, w, env, ep % p.E, lane);
+  load_episode<LPE>(p, w, env, ep % p.E, sl);
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.status + (size_t)env * p.Pp16);
     uint4* dst = reinterpret_cast<uint4*>(w.status);
 #pragma unroll 1
-    for (int i = lane; i < (p.Pp16 >> 4); i += 32) dst[i] = src[i];
+    for (int i = sl; i < (p.Pp16 >> 4); i += LPE) dst[i] = src[i];
   }
-  uint32_t rob = active ? p.robots[(size_t)env * R + lane] : 0u;
-  int cell = active ? (int)(rob & 0xffffu) : (0x10000 + lane);
+  uint32_t rob = active ? p.robots[(size_t)env * R + sl] : 0u;
+  int cell = active ? (int)(rob & 0xffffu) : (0x10000 + sl);
   int carry = active ? (int)(rob >> 16) : 0;
-  __syncwarp();
+  g.sync();
 
   if (kMode & 1) {
     // ---------------- decode ----------------
     int mv, op;
-    decode_action(active ? (int)__ldg(p.actions + (size_t)widx * R + lane) : 3, mv, op);
+    decode_action(active ? (int)__ldg(p.actions + (size_t)widx * R + sl) : 3, mv, op);
     // ---------------- proposals (env.py:193-201) ----------------
     const int r = active ? (int)__umulhi((uint32_t)cell, p.mul_wout) : 0;
     const int c = active ? cell - r * Wo : 0;
@@ -783,22 +851,23 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? MDX_FEAT_BLOCKS : 8) mdx_en
     // robot i moves  <=>  it is the lowest-index contender for its target cell AND that cell was
     // empty at step start or its holder moves away.  Cycles/swaps never enter the fixed point.
     int holder = -1;
+#pragma unroll 1
     for (int j = 0; j < R; ++j) {
-      const int cj = __shfl_sync(MDX_FULL, cell, j);
-      if (cj == tgt && j != lane) holder = j;
+      const int cj = g.shfl(cell, j);
+      if (cj == tgt && j != sl) holder = j;
     }
     const bool wants = active && tgt != cell;
-    const unsigned grp = __match_any_sync(MDX_FULL, tgt);
-    const unsigned wants_mask = __ballot_sync(MDX_FULL, wants);
-    const bool winner = wants && (((grp & wants_mask) & ((1u << lane) - 1u)) == 0u);
+    const unsigned grp = g.match(tgt);
+    const unsigned wants_mask = g.ballot(wants);
+    const bool winner = wants && (((grp & wants_mask) & ((1u << sl) - 1u)) == 0u);
     unsigned mm = 0u;
     while (true) {
       const bool m = winner && (holder < 0 || ((mm >> holder) & 1u));
-      const unsigned nm = __ballot_sync(MDX_FULL, m);
+      const unsigned nm = g.ballot(m);
       if (nm == mm) break;
       mm = nm;
     }
-    const bool moved = (mm >> lane) & 1u;
+    const bool moved = (mm >> sl) & 1u;
     const int cell1 = moved ? tgt : cell;
     const int r1 = moved ? nr : r, c1 = moved ? nc : c;
     const int n_moved = __popc(mm);  // every mover used one of L/R/U/D (env.py:255)
@@ -806,8 +875,8 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? MDX_FEAT_BLOCKS : 8) mdx_en
     // ---------------- package ops in robot order (env.py:260-292) ----------------
     // robots stand on distinct cells, so pickups never contend across robots: each takes the
     // lowest-id waiting package on its own cell
-    const int nw_prev = build_waiting(p, w, lane, t);
-    const Scan sc = scan_waiting<kSmall>(w, lane, R, nw_prev, r, c, r1, c1);
+    const int nw_prev = build_waiting<LPE>(p, w, g, t);
+    const Scan sc = scan_waiting<LPE, kSmall>(w, g, R, nw_prev, r, c, r1, c1);
     const bool want_pick = active && op == 1 && carry == 0;
     const int picked = (want_pick && sc.at_new != MDX_NONE32) ? (int)w.wlist[sc.at_new] : -1;
     const int tgt0 = carry ? (int)w.target[carry - 1] : -1;
@@ -816,8 +885,9 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? MDX_FEAT_BLOCKS : 8) mdx_en
     const bool on_time = delivered && t <= dl0;
     const int carry1 = delivered ? 0 : (picked >= 0 ? picked + 1 : carry);
     // env reward in float64, reference order: move costs first, then deliveries by robot index
-    const unsigned dmask = __ballot_sync(MDX_FULL, delivered), omask = __ballot_sync(MDX_FULL, on_time);
+    const unsigned dmask = g.ballot(delivered), omask = g.ballot(on_time);
     double rew = 0.0;
+#pragma unroll 1
     for (int k = 0; k < n_moved; ++k) rew = __dadd_rn(rew, p.move_cost);
     for (unsigned mleft = dmask; mleft; mleft &= mleft - 1u) {
       const int b = __ffs(mleft) - 1;
@@ -826,34 +896,35 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? MDX_FEAT_BLOCKS : 8) mdx_en
     // shaped reward reads the PREVIOUS statuses, so evaluate it before they change
     float shaped = 0.0f;
     if (p.out_shaped != nullptr)
-      shaped = shaped_team_reward(p, w, lane, t + 1, r, c, carry, r1, c1, carry1, mv, op, nw_prev, sc, rew);
-    __syncwarp();
+      shaped = shaped_team_reward<LPE>(p, w, g, t + 1, r, c, carry, r1, c1, carry1, mv, op, nw_prev, sc, rew);
+    g.sync();
     if (delivered) w.status[carry - 1] = ST_DELIVERED;
     if (picked >= 0) w.status[picked] = ST_IN_TRANSIT;
-    __syncwarp();
+    g.sync();
     // ---------------- time, spawn, termination (env.py:295-306, 127-137) ----------------
     const int t1 = t + 1;
     bool all_delivered = true;
-    for (int base = 0; base < P; base += 32) {
-      const int j = base + lane;
+#pragma unroll 1
+    for (int base = 0; base < P; base += LPE) {
+      const int j = base + sl;
       bool ok = true;
       if (j < P) {
         if ((int)w.t0[j] == t1) w.status[j] = ST_WAITING;
         ok = w.status[j] == ST_DELIVERED;
       }
-      all_delivered = all_delivered && __all_sync(MDX_FULL, ok);
+      all_delivered = g.all(ok) && all_delivered;
     }
     const bool done = (t1 == p.T) || all_delivered;  // not latched
     double total = p.total_reward[env] + rew;
-    if (lane == 0) {
+    if (sl == 0) {
       if (p.out_reward) p.out_reward[widx] = rew;
       if (p.out_shaped) p.out_shaped[widx] = shaped;
       if (p.out_done) p.out_done[widx] = done ? 1 : 0;
     }
     // cumulative per-env counters
     {
-      const int n_pick = __popc(__ballot_sync(MDX_FULL, picked >= 0));
-      if (lane == 0) {
+      const int n_pick = __popc(g.ballot(picked >= 0));
+      if (sl == 0) {
         uint4* cn = reinterpret_cast<uint4*>(p.counters + (size_t)env * 8);
         uint4 a = cn[0], b = cn[1];
         a.y += (uint32_t)n_moved;                 // C_MOVES
@@ -872,74 +943,75 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? MDX_FEAT_BLOCKS : 8) mdx_en
     cell = active ? cell1 : cell;
     carry = carry1;
     t = t1;
-    __syncwarp();
+    g.sync();
     // ---------------- on-device auto-reset (MAPPO/trainer.py:229-234) ----------------
     if (done && (p.flags & 1u)) {
       if (ep + 1 < __ldg(p.ep_avail + env)) {
         ep += 1;
         const int slot = ep % p.E;
-        load_episode(p, w, env, slot, lane);
-        __syncwarp();
-        for (int j = lane; j < p.Pp16; j += 32)
+        load_episode<LPE>(p, w, env, slot, sl);
+        g.sync();
+        for (int j = sl; j < p.Pp16; j += LPE)
           w.status[j] = (j < P && w.t0[j] == 0) ? (uint8_t)ST_WAITING : (uint8_t)ST_NONE;
         if (active) {
-          cell = __ldg(p.sched_robots + ((size_t)slot * p.n_envs + env) * 32 + lane);
+          cell = __ldg(p.sched_robots + ((size_t)slot * p.n_envs + env) * 32 + sl);
           carry = 0;
         }
         t = 0;
         total = 0.0;
-        __syncwarp();
-      } else if (lane == 0) {
+        g.sync();
+      } else if (sl == 0) {
         p.counters[(size_t)env * 8 + C_STARVED] = 1u;
       }
     }
     // ---------------- write the state back ----------------
-    if (active) p.robots[(size_t)env * R + lane] = (uint32_t)cell | ((uint32_t)carry << 16);
+    if (active) p.robots[(size_t)env * R + sl] = (uint32_t)cell | ((uint32_t)carry << 16);
     {
       uint4* dst = reinterpret_cast<uint4*>(p.status + (size_t)env * p.Pp16);
       const uint4* src = reinterpret_cast<const uint4*>(w.status);
-  #pragma unroll 1
-    for (int i = lane; i < (p.Pp16 >> 4); i += 32) dst[i] = src[i];
+#pragma unroll 1
+      for (int i = sl; i < (p.Pp16 >> 4); i += LPE) dst[i] = src[i];
     }
-    if (lane == 0) {
+    if (sl == 0) {
       p.t[env] = t;
       p.ep[env] = ep;
       p.total_reward[env] = total;
     }
   }
 
-  if (kMode & 2) featurize_env<kS, kSmall>(p, w, lut, map, lane, widx, t, cell, carry);
+  if (kMode & 2) featurize_env<LPE, kS, kSmall>(p, w, g, lut, map, widx, t, cell, carry);
 }
 
 // compute_shaped_rewards on injected "current" robots against the stored state as "previous".
 __global__ void __launch_bounds__(128) mdx_shape_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int env = blockIdx.x * (blockDim.x >> 5) + wib;
   if (env >= p.n) return;
-  const Warp w = carve(p, smem_raw + kLutBytes + (size_t)wib * p.smem_per_warp);
+  const Grp<32> g(threadIdx.x & 31);
+  const int lane = g.sl;
+  const Env w = carve(p, smem_raw + kLutBytes + (size_t)wib * p.smem_per_warp);
   const int R = p.R;
   const bool active = lane < R;
   const int t = p.t[env];
-  load_episode(p, w, env, p.ep[env] % p.E, lane);
+  load_episode<32>(p, w, env, p.ep[env] % p.E, lane);
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.status + (size_t)env * p.Pp16);
     uint4* dst = reinterpret_cast<uint4*>(w.status);
 #pragma unroll 1
     for (int i = lane; i < (p.Pp16 >> 4); i += 32) dst[i] = src[i];
   }
-  __syncwarp();
+  g.sync();
   const uint32_t rob0 = active ? p.robots[(size_t)env * R + lane] : 0u;
   const uint32_t rob1 = active ? p.cur_robots[(size_t)env * R + lane] : 0u;
   int mv, op;
   decode_action(active ? (int)p.actions[(size_t)env * R + lane] : 3, mv, op);
   const int r0 = (int)__umulhi(rob0 & 0xffffu, p.mul_wout), c0 = (int)(rob0 & 0xffffu) - r0 * p.W_out;
   const int r1 = (int)__umulhi(rob1 & 0xffffu, p.mul_wout), c1 = (int)(rob1 & 0xffffu) - r1 * p.W_out;
-  const int nw = build_waiting(p, w, lane, t);
-  const Scan sc = scan_waiting<false>(w, lane, R, nw, r0, c0, r1, c1);
-  const float s = shaped_team_reward(p, w, lane, p.cur_t[env], r0, c0, (int)(rob0 >> 16), r1, c1, (int)(rob1 >> 16), mv, op,
-                                     nw, sc, p.global_reward[env]);
+  const int nw = build_waiting<32>(p, w, g, t);
+  const Scan sc = scan_waiting<32, false>(w, g, R, nw, r0, c0, r1, c1);
+  const float s = shaped_team_reward<32>(p, w, g, p.cur_t[env], r0, c0, (int)(rob0 >> 16), r1, c1, (int)(rob1 >> 16), mv, op,
+                                         nw, sc, p.global_reward[env]);
   if (lane == 0) p.out_shaped[env] = s;
 }
 

@@ -398,3 +398,33 @@ def test_generic_featuriser_path_matches_golden(name, monkeypatch):
             assert np.array_equal(g.cpu().numpy()[0], z["gstate"][fi].astype(np.float32)), step
             assert np.array_equal(_bits(gv.cpu().numpy()[1]), _bits(z["gvec"][fi])), step
             fi += 1
+
+
+@pytest.mark.parametrize("lpe", [8, 16, 32])
+@pytest.mark.parametrize("name", ["map1_mix", "map7_odd", "map7_home"])
+def test_lanes_per_env_variants_match_golden(name, lpe, monkeypatch):
+    """The kernels pack 4 / 2 / 1 environments per warp (8 / 16 / 32 lanes per env) depending on the
+    robot count; MDX_LPE forces a larger group so that every variant is checked on the same trajectory.
+    An odd env count leaves a lane group without an env (it must simply leave)."""
+    monkeypatch.setenv("MDX_LPE", str(lpe))
+    meta, z = load_traj(name)
+    N = 7
+    b = _batch_for(meta, z, n_envs=N, ring_episodes=4)
+    monkeypatch.delenv("MDX_LPE")
+    b.reset()
+    fi = 0
+    for step in range(min(meta["n_steps"], 200)):
+        if step % 64 == 0:
+            b.prefetch(3)
+        a = torch.from_numpy(np.repeat(z["actions"][step][None], N, 0).copy())
+        r, sh, d, o, v, g, gv = b.step_featurize(a, auto_reset=True)
+        assert np.all(r.cpu().numpy() == z["reward"][step]) and np.all(d.cpu().numpy() == z["done"][step]), step
+        assert np.all(sh.cpu().numpy() == z["shaped_mappo"][step]), step
+        if step % meta["feat_every"] == 0:
+            o, v, g, gv = o.cpu().numpy(), v.cpu().numpy(), g.cpu().numpy(), gv.cpu().numpy()
+            for i in (0, 3, 6):
+                assert np.array_equal(o[i], z["obs"][fi].astype(np.float32)), (step, i)
+                assert np.array_equal(_bits(v[i]), _bits(z["vec"][fi])), (step, i)
+                assert np.array_equal(g[i], z["gstate"][fi].astype(np.float32)), (step, i)
+                assert np.array_equal(_bits(gv[i]), _bits(z["gvec"][fi])), (step, i)
+            fi += 1
