@@ -513,6 +513,7 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
     CUX(cudaMemcpy(raw->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     raw->d_maps = reinterpret_cast<MapDev*>(dbase + off_maps);
     b.maps = raw->d_maps;
+    b.map0 = md[0];
     b.tq = reinterpret_cast<const float*>(dbase + off_tq);
     b.cq = reinterpret_cast<const float*>(dbase + off_cq);
   }

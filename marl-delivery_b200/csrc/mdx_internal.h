@@ -99,6 +99,7 @@ struct KParams {
   uint32_t* counters;      // [n_envs][8]
   const int32_t* env_map;  // [n_envs]
   const MapDev* maps;
+  MapDev map0;             // copy of maps[0] (used directly when every env shares one map)
   const float* tq;         // tq[k] = (float)((double)k / T)
   const float* cq;         // cq[i] = (float)((double)i / (MR - 1)), i < 32 (MAPPO/helper.py:247)
   // call arguments

@@ -817,18 +817,32 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? MDX_FEAT_BLOCKS : 8) mdx_en
   const int env = p.env_ids ? __ldg(p.env_ids + widx) : widx;
   const int R = p.R, P = p.P, Wo = p.W_out;
   const bool active = sl < R;
-  const MapDev& map = p.maps[p.env_map ? __ldg(p.env_map + env) : 0];
+  // single-map instances read the map descriptor from the kernel parameters (no pointer chase)
+  MapDev map = p.map0;
+  if (p.env_map) map = p.maps[__ldg(p.env_map + env)];
 
+  // Issue every global load of the env's state up front so that their latencies overlap; only the
+  // schedule block depends on a loaded value (the episode cursor selects the ring slot).
   int t = p.t[env];
   int ep = p.ep[env];
+  const uint4* st_src = reinterpret_cast<const uint4*>(p.status + (size_t)env * p.Pp16);
+  const int n_st16 = p.Pp16 >> 4;
+  uint4 st0 = make_uint4(0u, 0u, 0u, 0u);
+  if (sl < n_st16) st0 = st_src[sl];
+  uint32_t rob = active ? p.robots[(size_t)env * R + sl] : 0u;
+  int action = 3;
+  double total0 = 0.0;
+  if (kMode & 1) {
+    if (active) action = (int)__ldg(p.actions + (size_t)widx * R + sl);
+    total0 = p.total_reward[env];
+  }
   load_episode<LPE>(p, w, env, ep % p.E, sl);
   {
-    const uint4* src = reinterpret_cast<const uint4*>(p.status + (size_t)env * p.Pp16);
     uint4* dst = reinterpret_cast<uint4*>(w.status);
+    if (sl < n_st16) dst[sl] = st0;
 #pragma unroll 1
-    for (int i = sl; i < (p.Pp16 >> 4); i += LPE) dst[i] = src[i];
+    for (int i = sl + LPE; i < n_st16; i += LPE) dst[i] = st_src[i];
   }
-  uint32_t rob = active ? p.robots[(size_t)env * R + sl] : 0u;
   int cell = active ? (int)(rob & 0xffffu) : (0x10000 + sl);
   int carry = active ? (int)(rob >> 16) : 0;
   g.sync();
@@ -836,7 +850,7 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? MDX_FEAT_BLOCKS : 8) mdx_en
   if (kMode & 1) {
     // ---------------- decode ----------------
     int mv, op;
-    decode_action(active ? (int)__ldg(p.actions + (size_t)widx * R + sl) : 3, mv, op);
+    decode_action(action, mv, op);
     // ---------------- proposals (env.py:193-201) ----------------
     const int r = active ? (int)__umulhi((uint32_t)cell, p.mul_wout) : 0;
     const int c = active ? cell - r * Wo : 0;
@@ -915,30 +929,24 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? MDX_FEAT_BLOCKS : 8) mdx_en
       all_delivered = g.all(ok) && all_delivered;
     }
     const bool done = (t1 == p.T) || all_delivered;  // not latched
-    double total = p.total_reward[env] + rew;
+    double total = total0 + rew;
     if (sl == 0) {
       if (p.out_reward) p.out_reward[widx] = rew;
       if (p.out_shaped) p.out_shaped[widx] = shaped;
       if (p.out_done) p.out_done[widx] = done ? 1 : 0;
     }
-    // cumulative per-env counters
+    // cumulative per-env counters: fire-and-forget reductions, lane = counter index (no load, no wait)
     {
       const int n_pick = __popc(g.ballot(picked >= 0));
-      if (sl == 0) {
-        uint4* cn = reinterpret_cast<uint4*>(p.counters + (size_t)env * 8);
-        uint4 a = cn[0], b = cn[1];
-        a.y += (uint32_t)n_moved;                 // C_MOVES
-        a.z += (uint32_t)__popc(omask);           // C_ONTIME
-        a.w += (uint32_t)__popc(dmask & ~omask);  // C_LATE
-        b.x += (uint32_t)n_pick;                  // C_PICKUPS
-        b.y += 1u;                                // C_STEPS
-        if (done) {
-          a.x += 1u;            // C_EPISODES
-          b.z += (uint32_t)t1;  // C_EPLEN
-        }
-        cn[0] = a;
-        cn[1] = b;
-      }
+      uint32_t delta = 0u;
+      if (sl == C_EPISODES) delta = done ? 1u : 0u;
+      else if (sl == C_MOVES) delta = (uint32_t)n_moved;
+      else if (sl == C_ONTIME) delta = (uint32_t)__popc(omask);
+      else if (sl == C_LATE) delta = (uint32_t)__popc(dmask & ~omask);
+      else if (sl == C_PICKUPS) delta = (uint32_t)n_pick;
+      else if (sl == C_STEPS) delta = 1u;
+      else if (sl == C_EPLEN) delta = done ? (uint32_t)t1 : 0u;
+      if (sl < 7 && delta != 0u) atomicAdd(p.counters + (size_t)env * 8 + sl, delta);
     }
     cell = active ? cell1 : cell;
     carry = carry1;
