@@ -38,26 +38,56 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-R, P, T, K_O, K_P, MR, MP = 5, 50, 500, 4, 5, 100, 100
 BASE_SEED = 42
-WORKLOAD = "C3: map1 10x10, 5 robots, 50 packages, T=500, fused step+shaped reward+auto-reset+obs/vec/gstate/gvec (D=52, Dg=1301)"
+# BASELINE.json configs.  c3 is the headline (the metric is quoted on it); the others are here so that
+# every config can be measured with the same harness (`--workload`), their numbers live in profiles/.
+WORKLOADS = {
+    "c3": dict(desc="C3: map1 10x10, 5 robots, 50 packages, T=500, fused step+shaped reward+auto-reset+obs/vec/gstate/gvec (D=52, Dg=1301)",
+               maps=["map1.txt"], R=5, P=50, T=500, K_o=4, K_p=5, MR=100, MP=100, envs=65536, feat=True),
+    "c3k100": dict(desc="C3 with generate_vector_features defaults K=100/100 (D=1007)",
+                   maps=["map1.txt"], R=5, P=50, T=500, K_o=100, K_p=100, MR=100, MP=100, envs=32768, feat=True),
+    "c2": dict(desc="C2: map1 10x10, 5 robots, 50 packages, T=500, 4096 envs, step + env reward + shaped reward only (no featurisation)",
+               maps=["map1.txt"], R=5, P=50, T=500, K_o=4, K_p=5, MR=100, MP=100, envs=4096, feat=False),
+    "c4": dict(desc="C4: map1..map5 mixed by env index (planes padded to 20x20), 10 robots, 100 packages, T=500, K_o=9, K_p=5",
+               maps=["map1.txt", "map2.txt", "map3.txt", "map4.txt", "map5.txt"], R=10, P=100, T=500, K_o=9, K_p=5, MR=100,
+               MP=100, envs=16384, feat=True),
+    "c5": dict(desc="C5: map5 20x20, 32 robots (full warp), 500 packages, T=1000, K_o=31, K_p=5",
+               maps=["map5.txt"], R=32, P=500, T=1000, K_o=31, K_p=5, MR=100, MP=100, envs=32768, feat=True),
+}
+WL = dict(WORKLOADS["c3"])
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
 def _cpu_worker(args):
-    seed, n_envs, n_steps = args
+    seed, n_envs, n_steps, wl = args
     import numpy as np
+
+    import importlib.util
 
     from oracle import oracle_env as orc
 
-    grid = orc.parse_map_text("\n".join(" ".join("1" if (r in (0, 9) or c in (0, 9)) else "0" for c in range(10)) for r in range(10)))
-    ve = orc.OracleVecEnv(n_envs, grid, seed=seed, max_time_steps=T, n_robots=R, n_packages=P)
+    # map data only (stand-alone module, numpy only); the oracle does all the computing on this arm
+    spec = importlib.util.spec_from_file_location("_mdx_maps", os.path.join(ROOT, "marl-delivery_b200", "maps.py"))
+    maps = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(maps)
+
+    grid = maps.stock_map(wl["maps"][0])
+    R = wl["R"]
+    ve = orc.OracleVecEnv(n_envs, grid, seed=seed, max_time_steps=wl["T"], n_robots=R, n_packages=wl["P"])
     ve.reset()
     rs = np.random.RandomState(seed)
     acts = rs.randint(0, 15, size=(n_steps, n_envs, R))
     t0 = time.perf_counter()
     for s in range(n_steps):
-        orc.mappo_rollout_step(ve, acts[s], K_O, K_P, MR, MP)
+        if wl["feat"]:
+            orc.mappo_rollout_step(ve, acts[s], wl["K_o"], wl["K_p"], wl["MR"], wl["MP"])
+        else:  # C2: step + shaped reward, auto-reset, no featurisation
+            for n, e in enumerate(ve.envs):
+                before = e.snapshot()
+                r, d = e.step(acts[s, n])
+                orc.shaped_reward(e, r, before, e.snapshot(), acts[s, n])
+                if d:
+                    e.reset()
     return time.perf_counter() - t0
 
 
@@ -66,7 +96,7 @@ def cpu_arm(n_envs_per_core, n_steps, cores=None):
     same workload (the reference's VectorizedEnv is a sequential loop; shards are how it would use
     more cores)."""
     cores = cores or os.cpu_count() or 1
-    jobs = [(BASE_SEED + 1000 * k, n_envs_per_core, n_steps) for k in range(cores)]
+    jobs = [(BASE_SEED + 1000 * k, n_envs_per_core, n_steps, WL) for k in range(cores)]
     if cores == 1:
         times = [_cpu_worker(jobs[0])]
     else:
@@ -149,12 +179,15 @@ def gpu_arm(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    N = args.envs_per_gpu
+    wl = WL
+    R, P, T, feat_on = wl["R"], wl["P"], wl["T"], wl["feat"]
+    N = args.envs_per_gpu or wl["envs"]
     K, W = args.steps, args.warmup
 
-    ve = mdb.VectorizedEnv(mdb.Environment, N, map_file="map1.txt", n_robots=R, n_packages=P, max_time_steps=T,
-                           seed=BASE_SEED, k_others=K_O, k_packages=K_P, max_robots_in_state=MR,
-                           max_packages_in_state=MP, ring_episodes=8, first_env_index=rank * N)
+    ve = mdb.VectorizedEnv(mdb.Environment, N, map_file=wl["maps"] if len(wl["maps"]) > 1 else wl["maps"][0], n_robots=R,
+                           n_packages=P, max_time_steps=T, seed=BASE_SEED, k_others=wl["K_o"], k_packages=wl["K_p"],
+                           max_robots_in_state=wl["MR"], max_packages_in_state=wl["MP"], ring_episodes=8,
+                           first_env_index=rank * N)
     b = ve.batch
     b.reset()  # VectorizedEnv.reset() minus the list of 65k state dicts it would build
 
@@ -167,10 +200,15 @@ def gpu_arm(args):
     gen.manual_seed(1234 + rank)
     n_act = min(K + W, 64)  # distinct pre-generated action batches, cycled
     actions = torch.randint(0, 15, (n_act, N, R), dtype=torch.uint8, device=dev, generator=gen)
-    feat = b.alloc_features(N)
+    feat = b.alloc_features(N) if feat_on else None
     out = (torch.empty(N, dtype=torch.float64, device=dev), torch.empty(N, dtype=torch.float32, device=dev),
            torch.empty(N, dtype=torch.uint8, device=dev))
-    stats = torch.zeros(8, dtype=torch.int64, device=dev)
+
+    def one_step(a):
+        if feat_on:
+            b.step_featurize(a, auto_reset=True, out=out, feat_out=feat)
+        else:
+            b.step(a, auto_reset=True, out=out)
 
     def barrier():
         if world > 1:
@@ -182,14 +220,14 @@ def gpu_arm(args):
     if covered < K + W:
         raise SystemExit(f"--steps too large for the episode ring ({covered} steps covered)")
     for s in range(W):
-        b.step_featurize(actions[s % n_act], auto_reset=True, out=out, feat_out=feat)
+        one_step(actions[s % n_act])
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     ev_end = torch.cuda.Event(enable_timing=True)
     ev[0].record()
     for s in range(K):
-        b.step_featurize(actions[(W + s) % n_act], auto_reset=True, out=out, feat_out=feat)
+        one_step(actions[(W + s) % n_act])
         ev[s + 1].record()
     stats = b.episode_stats()
     if world > 1:
@@ -205,6 +243,29 @@ def gpu_arm(args):
     ms_total_max = float(t_ms.item())
     stats_h = stats.cpu().tolist()
 
+    # ---- CUDA-graph replay (launch-bound workloads: C2) -----------------------------------------
+    graph_ms = None
+    if args.graph:
+        prefetch_for(64 * 6 + 8)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for s in range(3):
+                one_step(actions[s % n_act])
+        torch.cuda.current_stream().wait_stream(side)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for s in range(64):
+                one_step(actions[s % n_act])
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(5):
+            gr.replay()
+        g1.record()
+        barrier()
+        graph_ms = g0.elapsed_time(g1) / (5 * 64)
+
     # ---- end-to-end arm: host buffers through the public API ------------------------------------
     Ke = min(K, 200)
     prefetch_for(Ke + 3)
@@ -212,15 +273,23 @@ def gpu_arm(args):
     d_act = torch.empty((N, R), dtype=torch.uint8, device=dev)
     h_shaped = torch.empty(N, dtype=torch.float32).pin_memory()
     h_done = torch.empty(N, dtype=torch.uint8).pin_memory()
+
+    def api_step(a):
+        if feat_on:
+            _, shaped, done, *_ = ve.rollout_step(a, out=out, feat_out=feat)
+        else:
+            _, shaped, done = ve.batch.step(a, auto_reset=True, out=out)
+        return shaped, done
+
     for s in range(3):
         d_act.copy_(h_act[s % len(h_act)], non_blocking=True)
-        ve.rollout_step(d_act, out=out, feat_out=feat)
+        api_step(d_act)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(Ke):
         d_act.copy_(h_act[s % len(h_act)], non_blocking=True)
-        _, shaped, done, *_ = ve.rollout_step(d_act, out=out, feat_out=feat)
+        shaped, done = api_step(d_act)
         h_shaped.copy_(shaped, non_blocking=True)
         h_done.copy_(done, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads reward/done before choosing actions
@@ -238,21 +307,26 @@ def gpu_arm(args):
         return
 
     peak, peak_src = _peaks()
-    Bytes = b.bytes_per_env_step
+    # algorithmic bytes per env-step, SURVEY.md section 8(d): feature tensors + reward/done/actions, or
+    # the state model for the step-only workload
+    Bytes = b.bytes_per_env_step if feat_on else R * 9 + P * 10 + 37
     mean_launch_ms = statistics.mean(per_launch)
     achieved = Bytes * N / (mean_launch_ms * 1e-3) / 1e9
     value = world * N * K / (ms_total_max * 1e-3)
+    kern = "mdx_env_kernel<3,...> (fused step+featurise)" if feat_on else "mdx_env_kernel<1,...> (step+rewards)"
     line = {
-        "metric": "env-steps/sec (map1, 5 robots, 50 pkgs, T=500) with obs+state+vector featurisation",
+        "metric": "env-steps/sec (map1, 5 robots, 50 pkgs, T=500) with obs+state+vector featurisation" if args.workload == "c3"
+                  else f"env-steps/sec ({args.workload})",
         "value": value, "unit": "env-steps/s", "robot_steps_per_s": value * R,
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total_max / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16/u8 state, f32 features, f64 reward",
         "data": "synthetic (uniform random actions 0..14, host-sampled reference-exact spawn schedules)",
-        "config": {"workload": WORKLOAD, "envs_per_gpu": N, "envs_total": N * world, "parallelism": f"env-shards x{world}",
-                   "l2": f"outputs are {Bytes * N / 1e6:.0f} MB per step per GPU, larger than the 126 MB L2 (no flush needed)",
-                   "auto_reset": "on-device from a pre-sampled episode ring; all envs reset inside the timed region every 500 steps"},
+        "config": {"workload": wl["desc"], "envs_per_gpu": N, "envs_total": N * world, "parallelism": f"env-shards x{world}",
+                   "l2": (f"outputs are {Bytes * N / 1e6:.0f} MB per step per GPU, larger than the 126 MB L2 (no flush needed)" if feat_on
+                          else "state (a few MB) is L2-resident by design: this workload is launch/latency-bound, not HBM-bound"),
+                   "auto_reset": f"on-device from a pre-sampled episode ring; all envs reset inside the timed region every {T} steps"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "mdx_env_kernel<3> (fused step+featurise)",
+                     "traffic": None, "peak_source": peak_src, "kernel": kern,
                      "bytes_per_env_step": Bytes, "mean_launch_ms": mean_launch_ms,
                      "median_launch_ms": statistics.median(per_launch)},
         "e2e": {"value": world * N * Ke / (e2e_ms * 1e-3), "unit": "env-steps/s", "steps": Ke,
@@ -262,8 +336,11 @@ def gpu_arm(args):
         "clocks": clocks,
         "episode_stats": dict(zip(mdb.STAT_NAMES, stats_h)), "starved_envs": starved,
     }
+    if graph_ms is not None:
+        line["cuda_graph"] = {"ms_per_step": graph_ms, "value": world * N / (graph_ms * 1e-3), "unit": "env-steps/s",
+                              "note": "64 steps captured in one CUDA graph, replayed 5 times"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic_per_launch.json")
-    if os.path.exists(traffic_file):
+    if os.path.exists(traffic_file) and args.workload == "c3":
         try:
             tr = json.load(open(traffic_file))
             if tr.get("envs") == N:
@@ -275,7 +352,7 @@ def gpu_arm(args):
         v, cores, wall = cpu_arm(args.cpu_envs, args.cpu_steps)
         line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                 "sample": f"{cores} processes x {args.cpu_envs} envs x {args.cpu_steps} steps of the same "
-                                          f"workload (oracle/oracle_env.py mappo_rollout_step), {wall:.1f} s wall"}
+                                          f"workload (oracle/oracle_env.py), {wall:.1f} s wall"}
     print(json.dumps(line))
 
 
@@ -291,11 +368,12 @@ def reference_arm(args):
     v, cores, wall = cpu_arm(per_step_envs, steps)
     line = {
         "impl": "reference",
-        "metric": "env-steps/sec (map1, 5 robots, 50 pkgs, T=500) with obs+state+vector featurisation",
-        "value": v, "unit": "env-steps/s", "robot_steps_per_s": v * R, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "metric": "env-steps/sec (map1, 5 robots, 50 pkgs, T=500) with obs+state+vector featurisation" if args.workload == "c3"
+                  else f"env-steps/sec ({args.workload})",
+        "value": v, "unit": "env-steps/s", "robot_steps_per_s": v * WL["R"], "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
         "steps": steps, "warmup": min(W, 3), "ms_per_step": wall / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "python int / float64 / float32 (numpy)", "data": "synthetic (uniform random actions 0..14)",
-        "config": {"workload": WORKLOAD, "envs_per_step": per_step_envs * cores,
+        "config": {"workload": WL["desc"], "envs_per_step": per_step_envs * cores,
                    "note": "CPU arm: the reference is pure Python and does not travel to the GPU box; its restatement "
                            "(oracle/oracle_env.py, pinned to the reference's golden vectors) is timed instead"},
         "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
@@ -312,13 +390,17 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=65536)
+    ap.add_argument("--envs-per-gpu", type=int, default=0, help="0 = the workload's own size (65536 for c3)")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--graph", action="store_true", help="also time a CUDA-graph replay of 64 steps")
     ap.add_argument("--cpu-envs", type=int, default=5, help="envs per core in the CPU arm (the reference trains with 5)")
     ap.add_argument("--cpu-steps", type=int, default=600, help="steps per core in the CPU arm")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    WL.clear()
+    WL.update(WORKLOADS[args.workload])
     if args.impl == "reference":
         reference_arm(args)
     else:
