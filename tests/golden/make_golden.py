@@ -379,6 +379,59 @@ def gen_readme_random():
                 readme_actions_sha=np.array(hashlib.sha256(all_actions.tobytes()).hexdigest()))
 
 
+def gen_greedy():
+    """README.md:117-121 Greedy row (seed 10, map1, 5 robots, 100 packages, T=1000, 100 episodes; a new
+    GreedyAgents per episode like evaluation.py:9-66) plus two wall-heavy trajectories, with the agent's
+    actions recorded per step.  greedyagent.py prints on every call; stdout is discarded."""
+    out = {}
+    rewards, delivered = [], []
+    acts0 = None
+    for ep in range(100):
+        e = ref_env.Environment(os.path.join(REF, "map1.txt"), 1000, 5, 100, seed=10 + ep)
+        st = e.reset()
+        ag = ref_greedy.GreedyAgents()
+        ag.init_agents(st)
+        done = False
+        rec = []
+        while not done:
+            with contextlib.redirect_stdout(io.StringIO()):
+                acts = ag.get_actions(st)
+            rec.append([encode(m, o) for (m, o) in acts])
+            st, r, done, info = e.step(acts)
+        rewards.append(info["total_reward"])
+        delivered.append(sum(p.status == "delivered" for p in e.packages))
+        if ep < 3:
+            out[f"readme_greedy_actions_ep{ep}"] = np.array(rec, np.uint8)
+    print("README greedy: %.2f +- %.2f, delivered %.2f +- %.2f" % (
+        np.mean(rewards), np.std(rewards), np.mean(delivered), np.std(delivered)))
+    out["readme_greedy_rewards"] = np.array(rewards, np.float64)
+    out["readme_greedy_delivered"] = np.array(delivered, np.int32)
+    cases = [("map5.txt", 4, 30, 300, 3), ("map2.txt", 10, 60, 200, 8), ("map.txt", 3, 8, 80, 21), ("map4.txt", 7, 40, 150, 5)]
+    meta = []
+    for k, (m, R, P, T, seed) in enumerate(cases):
+        e = ref_env.Environment(os.path.join(REF, m), T, R, P, seed=seed)
+        st = e.reset()
+        ag = ref_greedy.GreedyAgents()
+        ag.init_agents(st)
+        rec, rew = [], []
+        done = False
+        while not done:
+            with contextlib.redirect_stdout(io.StringIO()):
+                acts = ag.get_actions(st)
+            rec.append([encode(mm, o) for (mm, o) in acts])
+            st, r, done, info = e.step(acts)
+            rew.append(r)
+        out[f"greedy_actions_{k}"] = np.array(rec, np.uint8)
+        out[f"greedy_rewards_{k}"] = np.array(rew, np.float64)
+        out[f"greedy_grid_{k}"] = grid_of(m)
+        meta.append(dict(map=m, R=R, P=P, T=T, seed=seed, steps=len(rec), total=float(e.total_reward),
+                         delivered=int(sum(p.status == "delivered" for p in e.packages))))
+        print("greedy case", meta[-1])
+    out["greedy_meta"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(HERE, "kats_greedy.npz"), **out)
+    print("kats_greedy.npz", os.path.getsize(os.path.join(HERE, "kats_greedy.npz")) // 1024, "KiB")
+
+
 def main():
     os.makedirs(HERE, exist_ok=True)
     gen_reset_blocks()
@@ -404,4 +457,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "greedy":
+        gen_greedy()
+    else:
+        main()
+        gen_greedy()
