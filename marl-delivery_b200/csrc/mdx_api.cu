@@ -13,13 +13,12 @@
 #include <vector>
 
 #include "../../include/mdx.h"
-#include "mdx_internal.h"
-#include "mdx_kernels.cuh"
+#include "mdx_host.h"
+#include "mdx_small_kernels.cuh"
 
 using namespace mdx;
 
-namespace {
-
+namespace mdx {
 thread_local std::string g_err;
 
 int fail(int code, const char* fmt, ...) {
@@ -31,102 +30,13 @@ int fail(int code, const char* fmt, ...) {
   g_err = buf;
   return code;
 }
-
-#define CU(call)                                                                            \
-  do {                                                                                      \
-    cudaError_t e_ = (call);                                                                \
-    if (e_ != cudaSuccess) return fail(MDX_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
-  } while (0)
-
-struct DeviceGuard {
-  int prev = -1;
-  explicit DeviceGuard(int dev) {
-    cudaGetDevice(&prev);
-    if (prev != dev) cudaSetDevice(dev);
-    else prev = -1;
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
-
-struct MapHost {
-  int rows = 0, cols = 0;
-  std::vector<uint8_t> cells;
-  std::vector<int> free_cells;
-};
-
-inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
-inline uint32_t magic(uint32_t d) { return (uint32_t)((0x100000000ull + d - 1) / d); }
-
-template <typename F>
-void parallel_for(int n, int n_threads, F&& fn) {
-  if (n <= 0) return;
-  n_threads = std::max(1, std::min(n_threads, n / 64 + 1));
-  if (n_threads == 1) {
-    fn(0, 0, n);
-    return;
-  }
-  std::vector<std::thread> th;
-  const int chunk = (n + n_threads - 1) / n_threads;
-  for (int k = 0; k < n_threads; ++k) {
-    const int lo = k * chunk, hi = std::min(n, lo + chunk);
-    if (lo >= hi) break;
-    th.emplace_back([&fn, k, lo, hi] { fn(k, lo, hi); });
-  }
-  for (auto& t : th) t.join();
-}
-
-}  // namespace
+}  // namespace mdx
 
 struct mdx_sampler {
   EpisodeSampler s;
 };
 
-struct mdx_env {
-  mdx_config cfg{};
-  int device = 0;
-  int n = 0, R = 0, P = 0, T = 0, E = 0;
-  int H_out = 0, W_out = 0;
-  int rec_u16 = 0;  // staging record size in u16: 4*Pp8 + 32
-  int threads = 1;
-  std::vector<MapHost> maps;
-  std::vector<int32_t> env_map;
-  std::vector<Mt19937> rng;        // one legacy RandomState stream per env
-  std::vector<int32_t> sampled;    // reset blocks drawn so far per env (== device ep_avail)
-  std::vector<int32_t> ep_host;    // last known device episode cursor
-  KParams base{};                  // everything but the per-call arguments
-  // device memory
-  void* d_blob = nullptr;          // maps + LUTs
-  MapDev* d_maps = nullptr;
-  int32_t* d_t = nullptr;
-  int32_t* d_ep = nullptr;
-  int32_t* d_ep_avail = nullptr;
-  double* d_total = nullptr;
-  uint32_t* d_robots = nullptr;
-  uint8_t* d_status = nullptr;
-  uint16_t* d_sched = nullptr;
-  uint16_t* d_sched_robots = nullptr;
-  uint32_t* d_counters = nullptr;
-  int32_t* d_env_map = nullptr;
-  // upload staging (sized for one block per env; larger uploads go in waves)
-  uint16_t* h_stage = nullptr;  // pinned
-  int32_t* h_ids = nullptr;     // pinned: [2][n] ids, slots
-  int32_t* h_i32 = nullptr;     // pinned scratch [n]
-  uint16_t* d_stage = nullptr;
-  int32_t* d_ids = nullptr;     // [2][n]
-  int wpb_override = 0;
-  size_t smem_configured[96] = {};
-  int no_fixed = 0;       // MDX_NOFIX=1: never use the shape-specialised instantiation
-  int lpe_override = 0;   // MDX_LPE=8|16|32: minimum lanes per environment (experiments / tests)
-  int force_generic = 0;  // MDX_GENERIC=1: always take the generic featuriser path (tests)
-};
-
 namespace {
-
-int smem_for_mode(const mdx_env* e, int mode) {
-  return (mode & 2) ? e->base.smem_per_warp : e->base.off_alist;
-}
 
 int pick_wpb(const mdx_env* e, int smem_per_warp) {
   if (e->wpb_override > 0) return std::min(4, e->wpb_override);  // kernels are compiled for <= 128 threads
@@ -205,68 +115,6 @@ int refresh_ep(mdx_env* e, cudaStream_t st) {
   CU(cudaStreamSynchronize(st));
   std::memcpy(e->ep_host.data(), e->h_i32, sizeof(int32_t) * (size_t)e->n);
   return MDX_OK;
-}
-
-template <int kMode, int LPE, int kS, bool kSmall, int kFix>
-int launch_variant(mdx_env* e, const KParams& kp, cudaStream_t st) {
-  const int spe = smem_for_mode(e, kMode);  // shared memory per environment
-  const int epb = 128 / LPE;                // environments per 128-thread CTA
-  const size_t smem = (size_t)kLutBytes + (size_t)epb * spe;
-  const int slot = kFix ? 95 - kMode
-                        : ((kMode * 3 + (LPE == 8 ? 0 : LPE == 16 ? 1 : 2)) * 4 + (kS == 0 ? 0 : kS == 1 ? 1 : kS == 2 ? 2 : 3)) * 2 + (kSmall ? 1 : 0);
-  if (smem > 227 * 1024) return fail(MDX_E_INVALID, "per-CTA working set (%zu bytes) exceeds shared memory", smem);
-  if (smem > e->smem_configured[slot]) {
-    CU(cudaFuncSetAttribute(mdx_env_kernel<kMode, LPE, kS, kSmall, kFix>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)std::max<size_t>(smem, 48 * 1024)));
-    e->smem_configured[slot] = smem;
-  }
-  KParams q = kp;
-  q.smem_per_warp = spe;
-  const unsigned grid = (unsigned)((kp.n + epb - 1) / epb);
-  mdx_env_kernel<kMode, LPE, kS, kSmall, kFix><<<grid, 128, smem, st>>>(q);
-  CU(cudaGetLastError());
-  return MDX_OK;
-}
-
-template <int kMode, int LPE>
-int launch_lpe(mdx_env* e, const KParams& kp, cudaStream_t st, int ks) {
-  const bool small = e->P <= 64;
-  if (kMode == 1) return small ? launch_variant<1, LPE, 0, true, 0>(e, kp, st) : launch_variant<1, LPE, 0, false, 0>(e, kp, st);
-  switch (ks) {
-    case 1: return small ? launch_variant<kMode, LPE, 1, true, 0>(e, kp, st) : launch_variant<kMode, LPE, 1, false, 0>(e, kp, st);
-    case 2: return small ? launch_variant<kMode, LPE, 2, true, 0>(e, kp, st) : launch_variant<kMode, LPE, 2, false, 0>(e, kp, st);
-    case 4: return small ? launch_variant<kMode, LPE, 4, true, 0>(e, kp, st) : launch_variant<kMode, LPE, 4, false, 0>(e, kp, st);
-    default: return small ? launch_variant<kMode, LPE, 0, true, 0>(e, kp, st) : launch_variant<kMode, LPE, 0, false, 0>(e, kp, st);
-  }
-}
-
-// Lanes per environment: the smallest group (8, 16, 32 lanes) that holds all robots and, for the
-// featurising modes, still has a plane-sliced fast path (a plane = H*W/4 float4 in <= 4 slices of LPE).
-template <int kMode>
-int launch_env_kernel(mdx_env* e, const KParams& kp, cudaStream_t st) {
-  const int HW = e->base.HW, n4p = HW >> 2;
-  auto slices = [&](int lpe) {
-    if (e->force_generic || (HW & 3) != 0) return 0;
-    const int s = (n4p + lpe - 1) / lpe;
-    return s <= 1 ? 1 : s <= 2 ? 2 : s <= 4 ? 4 : 0;
-  };
-  // Measured on B200 (C3, 5 robots): 32 lanes per env 221-229 M env-steps/s, 16 lanes 194 M, 8 lanes 143 M --
-  // packing several envs into a warp lowers the warp count and lengthens each warp's dependent chain, which
-  // costs more than the amortised uniform instructions save.  Whole warps are therefore the default;
-  // MDX_LPE=8|16 selects the packed variants (kept and tested).
-  int lpe = 32;
-  if (e->lpe_override) lpe = std::max(e->R <= 8 ? 8 : e->R <= 16 ? 16 : 32, e->lpe_override);
-  if (kMode != 1 && !e->force_generic && (HW & 3) == 0)
-    while (lpe < 32 && slices(lpe) == 0) lpe *= 2;
-  const int ks = kMode == 1 ? 0 : slices(lpe);
-  // the headline MAPPO shape has a fully specialised instantiation
-  const KParams& b = e->base;
-  if (kMode != 1 && lpe == 32 && ks == 1 && !e->no_fixed && b.R == 5 && b.Pp8 == 56 && b.Pp16 == 64 && b.H_out == 10 && b.W_out == 10 &&
-      b.K_o == 4 && b.K_p == 5 && b.sel_k == 5 && b.MR == 100 && b.MP == 100 && b.vec_rows_per_flush == 5 && b.stage_b == 44)
-    return launch_variant<kMode, 32, 1, true, 1>(e, kp, st);
-  if (lpe == 8) return launch_lpe<kMode, 8>(e, kp, st, ks);
-  if (lpe == 16) return launch_lpe<kMode, 16>(e, kp, st, ks);
-  return launch_lpe<kMode, 32>(e, kp, st, ks);
 }
 
 int check_ptr16(const void* p, const char* name) {
@@ -698,9 +546,9 @@ static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int
   kp.gstate = d_gstate;
   kp.gvec = d_gvec;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (mode == 1) return launch_env_kernel<1>(e, kp, st);
-  if (mode == 2) return launch_env_kernel<2>(e, kp, st);
-  return launch_env_kernel<3>(e, kp, st);
+  if (mode == 1) return launch_env_kernel_1(e, kp, st);
+  if (mode == 2) return launch_env_kernel_2(e, kp, st);
+  return launch_env_kernel_3(e, kp, st);
 }
 
 int32_t mdx_step(mdx_env* e, const uint8_t* d_actions, const int32_t* d_env_ids, int32_t n, double* d_reward, float* d_shaped,

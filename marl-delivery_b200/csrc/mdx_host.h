@@ -1,0 +1,116 @@
+// Host-side state of one mdx_env and the helpers shared by the translation units of libmdx.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/mdx.h"
+#include "mdx_internal.h"
+
+namespace mdx {
+
+// records the calling thread's error message (mdx_last_error) and returns `code`
+int fail(int code, const char* fmt, ...);
+
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) return ::mdx::fail(MDX_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+struct MapHost {
+  int rows = 0, cols = 0;
+  std::vector<uint8_t> cells;
+  std::vector<int> free_cells;
+};
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+inline uint32_t magic(uint32_t d) { return (uint32_t)((0x100000000ull + d - 1) / d); }
+
+template <typename F>
+void parallel_for(int n, int n_threads, F&& fn) {
+  if (n <= 0) return;
+  n_threads = std::max(1, std::min(n_threads, n / 64 + 1));
+  if (n_threads == 1) {
+    fn(0, 0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  const int chunk = (n + n_threads - 1) / n_threads;
+  for (int k = 0; k < n_threads; ++k) {
+    const int lo = k * chunk, hi = std::min(n, lo + chunk);
+    if (lo >= hi) break;
+    th.emplace_back([&fn, k, lo, hi] { fn(k, lo, hi); });
+  }
+  for (auto& t : th) t.join();
+}
+
+
+}  // namespace mdx
+
+struct mdx_env {
+  using MapHost = mdx::MapHost;
+  using Mt19937 = mdx::Mt19937;
+  using KParams = mdx::KParams;
+  using MapDev = mdx::MapDev;
+  mdx_config cfg{};
+  int device = 0;
+  int n = 0, R = 0, P = 0, T = 0, E = 0;
+  int H_out = 0, W_out = 0;
+  int rec_u16 = 0;  // staging record size in u16: 4*Pp8 + 32
+  int threads = 1;
+  std::vector<MapHost> maps;
+  std::vector<int32_t> env_map;
+  std::vector<Mt19937> rng;        // one legacy RandomState stream per env
+  std::vector<int32_t> sampled;    // reset blocks drawn so far per env (== device ep_avail)
+  std::vector<int32_t> ep_host;    // last known device episode cursor
+  KParams base{};                  // everything but the per-call arguments
+  // device memory
+  void* d_blob = nullptr;          // maps + LUTs
+  MapDev* d_maps = nullptr;
+  int32_t* d_t = nullptr;
+  int32_t* d_ep = nullptr;
+  int32_t* d_ep_avail = nullptr;
+  double* d_total = nullptr;
+  uint32_t* d_robots = nullptr;
+  uint8_t* d_status = nullptr;
+  uint16_t* d_sched = nullptr;
+  uint16_t* d_sched_robots = nullptr;
+  uint32_t* d_counters = nullptr;
+  int32_t* d_env_map = nullptr;
+  // upload staging (sized for one block per env; larger uploads go in waves)
+  uint16_t* h_stage = nullptr;  // pinned
+  int32_t* h_ids = nullptr;     // pinned: [2][n] ids, slots
+  int32_t* h_i32 = nullptr;     // pinned scratch [n]
+  uint16_t* d_stage = nullptr;
+  int32_t* d_ids = nullptr;     // [2][n]
+  int wpb_override = 0;
+  size_t smem_configured[96] = {};
+  int no_fixed = 0;       // MDX_NOFIX=1: never use the shape-specialised instantiation
+  int lpe_override = 0;   // MDX_LPE=8|16|32: minimum lanes per environment (experiments / tests)
+  int force_generic = 0;  // MDX_GENERIC=1: always take the generic featuriser path (tests)
+};
+
+
+namespace mdx {
+// one translation unit per kernel mode (mdx_launch{1,2,3}.cu): 1 step, 2 featurise, 3 fused
+int launch_env_kernel_1(mdx_env* e, const KParams& kp, cudaStream_t st);
+int launch_env_kernel_2(mdx_env* e, const KParams& kp, cudaStream_t st);
+int launch_env_kernel_3(mdx_env* e, const KParams& kp, cudaStream_t st);
+}  // namespace mdx

@@ -1,0 +1,81 @@
+// Variant selection and launch of mdx_env_kernel for ONE kernel mode (MDX_MODE), so that the three modes
+// compile in parallel translation units.
+#include "mdx_host.h"
+#include "mdx_kernels.cuh"
+
+namespace mdx {
+namespace {
+
+int smem_for_mode(const mdx_env* e, int mode) {
+  return (mode & 2) ? e->base.smem_per_warp : e->base.off_alist;
+}
+
+template <int kMode, int LPE, int kS, bool kSmall, int kFix>
+int launch_variant(mdx_env* e, const KParams& kp, cudaStream_t st) {
+  const int spe = smem_for_mode(e, kMode);  // shared memory per environment
+  const int epb = 128 / LPE;                // environments per 128-thread CTA
+  const size_t smem = (size_t)kLutBytes + (size_t)epb * spe;
+  const int slot = kFix ? 95 - kMode
+                        : ((kMode * 3 + (LPE == 8 ? 0 : LPE == 16 ? 1 : 2)) * 4 + (kS == 0 ? 0 : kS == 1 ? 1 : kS == 2 ? 2 : 3)) * 2 + (kSmall ? 1 : 0);
+  if (smem > 227 * 1024) return fail(MDX_E_INVALID, "per-CTA working set (%zu bytes) exceeds shared memory", smem);
+  if (smem > e->smem_configured[slot]) {
+    CU(cudaFuncSetAttribute(mdx_env_kernel<kMode, LPE, kS, kSmall, kFix>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)std::max<size_t>(smem, 48 * 1024)));
+    e->smem_configured[slot] = smem;
+  }
+  KParams q = kp;
+  q.smem_per_warp = spe;
+  const unsigned grid = (unsigned)((kp.n + epb - 1) / epb);
+  mdx_env_kernel<kMode, LPE, kS, kSmall, kFix><<<grid, 128, smem, st>>>(q);
+  CU(cudaGetLastError());
+  return MDX_OK;
+}
+
+template <int kMode, int LPE>
+int launch_lpe(mdx_env* e, const KParams& kp, cudaStream_t st, int ks) {
+  const bool small = e->P <= 64;
+  if (kMode == 1) return small ? launch_variant<1, LPE, 0, true, 0>(e, kp, st) : launch_variant<1, LPE, 0, false, 0>(e, kp, st);
+  switch (ks) {
+    case 1: return small ? launch_variant<kMode, LPE, 1, true, 0>(e, kp, st) : launch_variant<kMode, LPE, 1, false, 0>(e, kp, st);
+    case 2: return small ? launch_variant<kMode, LPE, 2, true, 0>(e, kp, st) : launch_variant<kMode, LPE, 2, false, 0>(e, kp, st);
+    case 4: return small ? launch_variant<kMode, LPE, 4, true, 0>(e, kp, st) : launch_variant<kMode, LPE, 4, false, 0>(e, kp, st);
+    default: return small ? launch_variant<kMode, LPE, 0, true, 0>(e, kp, st) : launch_variant<kMode, LPE, 0, false, 0>(e, kp, st);
+  }
+}
+
+// Lanes per environment: the smallest group (8, 16, 32 lanes) that holds all robots and, for the
+// featurising modes, still has a plane-sliced fast path (a plane = H*W/4 float4 in <= 4 slices of LPE).
+template <int kMode>
+int launch_env_kernel(mdx_env* e, const KParams& kp, cudaStream_t st) {
+  const int HW = e->base.HW, n4p = HW >> 2;
+  auto slices = [&](int lpe) {
+    if (e->force_generic || (HW & 3) != 0) return 0;
+    const int s = (n4p + lpe - 1) / lpe;
+    return s <= 1 ? 1 : s <= 2 ? 2 : s <= 4 ? 4 : 0;
+  };
+  // Measured on B200 (C3, 5 robots): 32 lanes per env 221-229 M env-steps/s, 16 lanes 194 M, 8 lanes 143 M --
+  // packing several envs into a warp lowers the warp count and lengthens each warp's dependent chain, which
+  // costs more than the amortised uniform instructions save.  Whole warps are therefore the default;
+  // MDX_LPE=8|16 selects the packed variants (kept and tested).
+  int lpe = 32;
+  if (e->lpe_override) lpe = std::max(e->R <= 8 ? 8 : e->R <= 16 ? 16 : 32, e->lpe_override);
+  if (kMode != 1 && !e->force_generic && (HW & 3) == 0)
+    while (lpe < 32 && slices(lpe) == 0) lpe *= 2;
+  const int ks = kMode == 1 ? 0 : slices(lpe);
+  // the headline MAPPO shape has a fully specialised instantiation
+  const KParams& b = e->base;
+  if (kMode != 1 && lpe == 32 && ks == 1 && !e->no_fixed && b.R == 5 && b.Pp8 == 56 && b.Pp16 == 64 && b.H_out == 10 && b.W_out == 10 &&
+      b.K_o == 4 && b.K_p == 5 && b.sel_k == 5 && b.MR == 100 && b.MP == 100 && b.vec_rows_per_flush == 5 && b.stage_b == 44)
+    return launch_variant<kMode, 32, 1, true, 1>(e, kp, st);
+  if (lpe == 8) return launch_lpe<kMode, 8>(e, kp, st, ks);
+  if (lpe == 16) return launch_lpe<kMode, 16>(e, kp, st, ks);
+  return launch_lpe<kMode, 32>(e, kp, st, ks);
+}
+
+}  // namespace
+
+#define MDX_CAT2(a, b) a##b
+#define MDX_CAT(a, b) MDX_CAT2(a, b)
+int MDX_CAT(launch_env_kernel_, MDX_MODE)(mdx_env* e, const KParams& kp, cudaStream_t st) { return launch_env_kernel<MDX_MODE>(e, kp, st); }
+
+}  // namespace mdx
