@@ -44,10 +44,17 @@ enum {
 /* flags for mdx_step / mdx_step_featurize */
 #define MDX_F_AUTO_RESET 1u /* done envs advance to their next pre-sampled episode inside the kernel   \
                                (MAPPO/trainer.py:229-234: reset, then featurise the reset state) */
+#define MDX_F_ACTIONS_I64 2u /* d_actions is int64 [n, n_robots]: the policy's raw samples a in [0, 15), decoded   \
+                                in the kernel like MAPPO/trainer.py:195-204 (move a % 5 in sorted LabelEncoder order, \
+                                package op a / 5, clamped to '0' when >= 3); negative values mean "stay, no op" */
 
 /* mdx_config.flags */
 #define MDX_CFG_BLANK 1 /* skip the constructor's reset draw: envs start empty (t = 0, robots on cell 0, no    \
                            packages) and are filled with mdx_set_state -- used by the per-call helper drop-ins */
+#define MDX_CFG_BFS_SHAPING 2 /* OPT-IN, not reference behaviour: the distance terms of the shaped reward (nearest     \
+                                 waiting package, closer / away, "work within 3") use shortest-path lengths from the   \
+                                 per-map all-pairs BFS table instead of MAPPO/helper.py:284-285's Manhattan distance   \
+                                 (BASELINE.json north star vs SURVEY.md Q9).  Identical on maps without inner walls. */
 
 /* Shaping constants of compute_shaped_rewards, in this order (MAPPO/helper.py:271-279,
  * QMIX/helper.py:270-278). */
@@ -171,6 +178,36 @@ int32_t mdx_set_state(mdx_env* env, int32_t env_id, const mdx_state_view* in, vo
  * env_steps, sum_episode_len, starved_envs} summed over this instance's envs (cumulative since
  * creation).  The caller all-reduces it across ranks. */
 int32_t mdx_episode_stats(mdx_env* env, int64_t* d_out8, void* stream);
+
+/* ---- callers either side of the path -------------------------------------- */
+
+/* GreedyAgents.get_actions for every listed env (greedyagent.py:42-174, incl. run_bfs :6-41 and
+ * update_move_to_target :64-100): one action code per robot into d_actions [n, n_robots] u8, ready for
+ * mdx_step.  The agent's bookkeeping (per-robot target, the `packages_free` flags over its own package
+ * list -- which holds every t = 0 package twice and is indexed by package_id - 1, exactly like the
+ * reference) lives on the device per env; it is re-initialised whenever the env is at t = 0, i.e. a new
+ * GreedyAgents() + init_agents(state) per episode as in evaluation.py:9-66.  Call it once per env step.
+ * run_bfs is a lookup in the per-map all-pairs BFS table (uint16, built on first use). */
+int32_t mdx_greedy_actions(mdx_env* env, const int32_t* d_env_ids, int32_t n, uint8_t* d_actions, void* stream);
+
+/* The all-pairs BFS table of map `map_id` (greedyagent.py:6-29 run from every free cell): h_out
+ * [rows_out*cols_out][rows_out*cols_out] uint16 in output-plane cell ids, 0xFFFF = unreachable. */
+int32_t mdx_bfs_table(mdx_env* env, int32_t map_id, uint16_t* h_out);
+
+/* GAE + returns of MAPPO/trainer.py:288-301 for a [T, N] rollout, float32 with the reference's order of
+ * operations: delta = r + gamma*v_next*nonterminal - v; adv = last = delta + (gamma*lambda)*nonterminal*last;
+ * ret = adv + v.  d_rewards/d_values [T, N] f32, d_dones [T, N] u8, d_last_value [N] f32 ->
+ * d_advantages, d_returns [T, N] f32.  Needs no mdx_env. */
+int32_t mdx_gae(const float* d_rewards, const float* d_values, const uint8_t* d_dones, const float* d_last_value,
+                int32_t T, int32_t N, double gamma, double gae_lambda, float* d_advantages, float* d_returns,
+                void* stream);
+
+/* Env-state checkpointing (the reference checkpoints only network weights, MAPPO/helper.py:371-389): the
+ * complete state of the instance -- device arrays, episode ring, counters, greedy bookkeeping and every
+ * env's MT19937 stream position -- as one host blob.  A loaded instance continues bit-identically. */
+int64_t mdx_checkpoint_bytes(const mdx_env* env);
+int32_t mdx_checkpoint_save(mdx_env* env, void* h_buf, int64_t bytes, void* stream);
+int32_t mdx_checkpoint_load(mdx_env* env, const void* h_buf, int64_t bytes, void* stream);
 
 /* ---- host-only pieces (no GPU needed) ------------------------------------------------------- */
 

@@ -10,7 +10,9 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libmdx.so")
 
 MDX_OK, MDX_E_INVALID, MDX_E_CUDA, MDX_E_STARVED, MDX_E_NOMEM = 0, -1, -2, -3, -4
 MDX_F_AUTO_RESET = 1
+MDX_F_ACTIONS_I64 = 2
 MDX_CFG_BLANK = 1
+MDX_CFG_BFS_SHAPING = 2
 MDX_MAX_ROBOTS = 32
 
 
@@ -78,6 +80,12 @@ SYMBOLS = {
     "mdx_get_state": (C.c_int32, [_VP, C.c_int32, C.POINTER(StateView), _VP]),
     "mdx_set_state": (C.c_int32, [_VP, C.c_int32, C.POINTER(StateView), _VP]),
     "mdx_episode_stats": (C.c_int32, [_VP, _VP, _VP]),
+    "mdx_greedy_actions": (C.c_int32, [_VP, _VP, C.c_int32, _VP, _VP]),
+    "mdx_bfs_table": (C.c_int32, [_VP, C.c_int32, C.POINTER(C.c_uint16)]),
+    "mdx_gae": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int32, C.c_int32, C.c_double, C.c_double, _VP, _VP, _VP]),
+    "mdx_checkpoint_bytes": (C.c_int64, [_VP]),
+    "mdx_checkpoint_save": (C.c_int32, [_VP, _VP, C.c_int64, _VP]),
+    "mdx_checkpoint_load": (C.c_int32, [_VP, _VP, C.c_int64, _VP]),
     "mdx_sampler_create": (C.c_int32, [C.c_uint32, C.POINTER(C.c_uint8), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_int32, C.POINTER(_VP)]),
     "mdx_sampler_next": (C.c_int32, [_VP, _I32P, _I32P]),

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import MDX_F_AUTO_RESET
+from ._lib import MDX_F_ACTIONS_I64, MDX_F_AUTO_RESET
 
 # compute_shaped_rewards constants (MAPPO/helper.py:271-279, QMIX/helper.py:270-278)
 MAPPO_SHAPING = (5.0, 200.0, 20.0, 0.02, 0.0, 0.0, -0.05, -0.05, -0.01)
@@ -49,7 +49,7 @@ class DeliveryBatch:
                  delay_reward: float = 1.0, seeds=None, base_seed: int = 2025, env_map=None,
                  k_others: int = 100, k_packages: int = 100, max_robots_in_state: int = 100,
                  max_packages_in_state: int = 100, shaping=MAPPO_SHAPING, device=None, ring_episodes: int = 4,
-                 sampler_threads: int = 0, blank: bool = False):
+                 sampler_threads: int = 0, blank: bool = False, bfs_shaping: bool = False):
         L = _lib.lib()
         if not torch.cuda.is_available():
             raise _lib.MdxError("no CUDA device: marl-delivery_b200 runs on the GPU only (no CPU fallback)")
@@ -94,7 +94,7 @@ class DeliveryBatch:
         cfg.device = int(self.device.index)
         cfg.ring_episodes = int(ring_episodes)
         cfg.sampler_threads = int(sampler_threads)
-        cfg.flags = _lib.MDX_CFG_BLANK if blank else 0
+        cfg.flags = (_lib.MDX_CFG_BLANK if blank else 0) | (_lib.MDX_CFG_BFS_SHAPING if bfs_shaping else 0)
         handle = C.c_void_p()
         _lib.check(L.mdx_create(C.byref(cfg), C.byref(handle)))
         self._h = handle
@@ -163,19 +163,24 @@ class DeliveryBatch:
 
     # ------------------------------------------------------------------ step
     def _check_actions(self, actions, n):
+        """-> (device tensor, flag bits).  uint8 action codes are used as they are; an int64 tensor is taken
+        to be the policy's raw samples (mb_actions of MAPPO/trainer.py:193) and decoded inside the kernel."""
         if not isinstance(actions, torch.Tensor):
             actions = torch.as_tensor(np.asarray(actions, dtype=np.uint8))
-        if actions.dtype != torch.uint8:
+        flags = 0
+        if actions.dtype == torch.int64:
+            flags = MDX_F_ACTIONS_I64
+        elif actions.dtype != torch.uint8:
             actions = actions.to(torch.uint8)
         actions = actions.to(self.device).contiguous()
         if tuple(actions.shape) != (n, self.n_robots):
             raise ValueError("The number of actions must match the number of robots.")  # env.py:182-183
-        return actions
+        return actions, flags
 
     def step(self, actions, ids=None, auto_reset: bool = False, want_shaped: bool = True, out=None):
         """-> (reward f64 [n], shaped f32 [n] or None, done u8 [n]); rows follow `ids`."""
         d_ids, _, n = self._ids(ids)
-        actions = self._check_actions(actions, n)
+        actions, aflags = self._check_actions(actions, n)
         if out is None:
             reward = self._buf("reward", (n,), torch.float64)
             shaped = self._buf("shaped", (n,), torch.float32) if want_shaped else None
@@ -183,7 +188,7 @@ class DeliveryBatch:
         else:
             reward, shaped, done = out
         _lib.check(self._L.mdx_step(self._h, _ptr(actions), _ptr(d_ids), n, _ptr(reward), _ptr(shaped), _ptr(done),
-                                    MDX_F_AUTO_RESET if auto_reset else 0, self._stream()))
+                                    (MDX_F_AUTO_RESET if auto_reset else 0) | aflags, self._stream()))
         self._version += 1
         return reward, shaped, done
 
@@ -213,7 +218,7 @@ class DeliveryBatch:
     def step_featurize(self, actions, ids=None, auto_reset: bool = True, out=None, feat_out=None):
         """One launch per MAPPO rollout iteration (MAPPO/trainer.py:172-286 minus the networks)."""
         d_ids, _, n = self._ids(ids)
-        actions = self._check_actions(actions, n)
+        actions, aflags = self._check_actions(actions, n)
         if out is None:
             reward = self._buf("reward", (n,), torch.float64)
             shaped = self._buf("shaped", (n,), torch.float32)
@@ -223,7 +228,7 @@ class DeliveryBatch:
         obs, vec, gstate, gvec = self._feat_out(n, feat_out)
         _lib.check(self._L.mdx_step_featurize(self._h, _ptr(actions), _ptr(d_ids), n, _ptr(reward), _ptr(shaped),
                                               _ptr(done), _ptr(obs), _ptr(vec), _ptr(gstate), _ptr(gvec),
-                                              MDX_F_AUTO_RESET if auto_reset else 0, self._stream()))
+                                              (MDX_F_AUTO_RESET if auto_reset else 0) | aflags, self._stream()))
         self._version += 1
         return reward, shaped, done, obs, vec, gstate, gvec
 
@@ -233,12 +238,45 @@ class DeliveryBatch:
         cur_robots = cur_robots.to(self.device, torch.int64).contiguous()
         packed = (cur_robots[..., 0] | (cur_robots[..., 1] << 16)).to(torch.int32).contiguous()  # cell | carry << 16
         cur_t = cur_t.to(self.device, torch.int32).contiguous()
-        actions = self._check_actions(actions, n)
+        actions, aflags = self._check_actions(actions, n)
+        if aflags:
+            raise ValueError("shaped_reward takes uint8 action codes")
         gr = global_reward.to(self.device, torch.float64).contiguous()
         out = torch.empty(n, dtype=torch.float32, device=self.device)
         _lib.check(self._L.mdx_shaped_reward(self._h, _ptr(packed), _ptr(cur_t), _ptr(actions), _ptr(gr), _ptr(out),
                                              self._stream()))
         return out
+
+    # ------------------------------------------------------------------ callers either side of the path
+    def greedy_actions(self, ids=None, out=None) -> torch.Tensor:
+        """GreedyAgents.get_actions (greedyagent.py:119-174) for the listed envs -> uint8 [n, R] action codes on
+        the GPU, ready for step().  Call once per env step; the agent re-initialises itself at t = 0."""
+        d_ids, _, n = self._ids(ids)
+        if out is None:
+            out = torch.empty((n, self.n_robots), dtype=torch.uint8, device=self.device)
+        _lib.check(self._L.mdx_greedy_actions(self._h, _ptr(d_ids), n, _ptr(out), self._stream()))
+        return out
+
+    def bfs_table(self, map_id: int = 0) -> np.ndarray:
+        """All-pairs shortest-path lengths of one map, uint16 [H*W, H*W] in output-plane cell ids (0xFFFF =
+        unreachable): run_bfs (greedyagent.py:6-29) from every free cell."""
+        hw = self.rows_out * self.cols_out
+        out = np.empty((hw, hw), np.uint16)
+        _lib.check(self._L.mdx_bfs_table(self._h, int(map_id), out.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return out
+
+    def state_dict(self) -> torch.Tensor:
+        """Complete env state (device arrays, episode ring, counters, greedy bookkeeping, every env's RNG stream)
+        as one uint8 host tensor; `load_state_dict` makes an instance of the same shape continue bit-identically."""
+        nbytes = int(self._L.mdx_checkpoint_bytes(self._h))
+        buf = torch.empty(nbytes, dtype=torch.uint8)
+        _lib.check(self._L.mdx_checkpoint_save(self._h, C.c_void_p(buf.data_ptr()), nbytes, self._stream()))
+        return buf
+
+    def load_state_dict(self, blob: torch.Tensor):
+        blob = blob.detach().to("cpu", torch.uint8).contiguous()
+        _lib.check(self._L.mdx_checkpoint_load(self._h, C.c_void_p(blob.data_ptr()), int(blob.numel()), self._stream()))
+        self._version += 1
 
     # ------------------------------------------------------------------ introspection
     def get_state(self, i: int) -> dict:
@@ -277,3 +315,25 @@ class DeliveryBatch:
         out = torch.empty(8, dtype=torch.int64, device=self.device)
         _lib.check(self._L.mdx_episode_stats(self._h, _ptr(out), self._stream()))
         return out
+
+
+def compute_gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, last_value: torch.Tensor,
+                gamma: float = 0.99, gae_lambda: float = 0.95):
+    """GAE + returns of MAPPO/trainer.py:288-301 on a device-resident [T, N] rollout (float32, the reference's order
+    of operations) -> (advantages, returns).  One CUDA launch instead of the reference's T small torch ops."""
+    if rewards.device.type != "cuda":
+        raise _lib.MdxError("compute_gae runs on the GPU only (no CPU fallback)")
+    T, N = rewards.shape
+    rewards = rewards.to(torch.float32).contiguous()
+    values = values.to(device=rewards.device, dtype=torch.float32).contiguous()
+    dones = dones.to(device=rewards.device, dtype=torch.uint8).contiguous()
+    last_value = last_value.to(device=rewards.device, dtype=torch.float32).reshape(N).contiguous()
+    if tuple(values.shape) != (T, N) or tuple(dones.shape) != (T, N):
+        raise ValueError("rewards, values and dones must share the shape [T, N]")
+    adv = torch.empty_like(rewards)
+    ret = torch.empty_like(rewards)
+    with torch.cuda.device(rewards.device):
+        st = C.c_void_p(torch.cuda.current_stream(rewards.device).cuda_stream)
+        _lib.check(_lib.lib().mdx_gae(_ptr(rewards), _ptr(values), _ptr(dones), _ptr(last_value), int(T), int(N), float(gamma),
+                                      float(gae_lambda), _ptr(adv), _ptr(ret), st))
+    return adv, ret

@@ -146,6 +146,9 @@ int32_t mdx_destroy(mdx_env* e) {
   cudaFree(e->d_env_map);
   cudaFree(e->d_stage);
   cudaFree(e->d_ids);
+  cudaFree(e->d_bfs);
+  cudaFree(e->d_greedy);
+  cudaFree(e->d_gfree);
   cudaFreeHost(e->h_stage);
   cudaFreeHost(e->h_ids);
   cudaFreeHost(e->h_i32);
@@ -357,6 +360,7 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
       md[m].qr = reinterpret_cast<const float*>(dbase + offs[(size_t)m].qr);
       md[m].qc = reinterpret_cast<const float*>(dbase + offs[(size_t)m].qc);
       md[m].rank = reinterpret_cast<const uint16_t*>(dbase + offs[(size_t)m].rank);
+      md[m].bfs = nullptr;
     }
     CUX(cudaMemcpy(raw->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     raw->d_maps = reinterpret_cast<MapDev*>(dbase + off_maps);
@@ -411,6 +415,14 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
 
   CUX2(cudaMemset(raw->d_robots, 0, sizeof(uint32_t) * n * e->R));
   CUX2(cudaMemset(raw->d_status, 0, n * b.Pp16));
+  if (cfg->flags & MDX_CFG_BFS_SHAPING) {
+    b.shaping_bfs = 1;
+    int rcb = ensure_bfs(raw);
+    if (rcb != MDX_OK) {
+      mdx_destroy(e.release());
+      return rcb;
+    }
+  }
   if (cfg->flags & MDX_CFG_BLANK) {
     // blank envs for state injection; their first mdx_reset draws block 0.  ep = -1 is never read
     // by a kernel before that reset because slot arithmetic uses the sched of slot 0 (all zero).

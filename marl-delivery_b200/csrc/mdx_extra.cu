@@ -1,0 +1,409 @@
+// Callers either side of the hot path: the batched greedy policy on per-map
+// all-pairs BFS tables (f2), GAE over a device-resident rollout (f4) and env-state checkpointing (f4).
+// See include/mdx.h for the contract of every entry point.
+#include <cstring>
+#include <deque>
+#include <vector>
+
+#include "mdx_host.h"
+
+using namespace mdx;
+
+namespace mdx {
+
+// ------------------------------------------------------------------------------------------------
+// All-pairs BFS (greedyagent.py:6-29 run from every free cell), output-plane cell ids.
+// ------------------------------------------------------------------------------------------------
+static void bfs_all_pairs(const MapHost& m, int Ho, int Wo, uint16_t* out) {
+  const int HW = Ho * Wo;
+  std::fill(out, out + (size_t)HW * HW, (uint16_t)0xFFFF);
+  std::vector<int> queue((size_t)m.rows * m.cols);
+  for (int gr = 0; gr < m.rows; ++gr)
+    for (int gc = 0; gc < m.cols; ++gc) {
+      if (m.cells[(size_t)gr * m.cols + gc] != 0) continue;
+      uint16_t* d = out + (size_t)(gr * Wo + gc) * HW;
+      int head = 0, tail = 0;
+      d[gr * Wo + gc] = 0;
+      queue[(size_t)tail++] = gr * m.cols + gc;
+      while (head < tail) {
+        const int cur = queue[(size_t)head++];
+        const int r = cur / m.cols, c = cur % m.cols;
+        const uint16_t dc = d[r * Wo + c];
+        const int nr[4] = {r - 1, r + 1, r, r}, nc[4] = {c, c, c - 1, c + 1};
+        for (int k = 0; k < 4; ++k) {
+          if (nr[k] < 0 || nr[k] >= m.rows || nc[k] < 0 || nc[k] >= m.cols) continue;
+          if (m.cells[(size_t)nr[k] * m.cols + nc[k]] != 0) continue;
+          uint16_t& dn = d[nr[k] * Wo + nc[k]];
+          if (dn != 0xFFFF) continue;
+          dn = (uint16_t)(dc + 1);
+          queue[(size_t)tail++] = nr[k] * m.cols + nc[k];
+        }
+      }
+    }
+}
+
+int ensure_bfs(mdx_env* e) {
+  if (e->d_bfs) return MDX_OK;
+  const int HW = e->base.HW;
+  if (HW > 4096) return fail(MDX_E_INVALID, "all-pairs BFS tables are limited to maps of at most 4096 cells (have %d)", HW);
+  DeviceGuard g(e->device);
+  const size_t per = (size_t)HW * HW;
+  const int nm = (int)e->maps.size();
+  std::vector<uint16_t> host(per * (size_t)nm);
+  for (int m = 0; m < nm; ++m) bfs_all_pairs(e->maps[(size_t)m], e->H_out, e->W_out, host.data() + per * (size_t)m);
+  CU(cudaMalloc(&e->d_bfs, sizeof(uint16_t) * host.size()));
+  CU(cudaMemcpy(e->d_bfs, host.data(), sizeof(uint16_t) * host.size(), cudaMemcpyHostToDevice));
+  std::vector<MapDev> md((size_t)nm);
+  CU(cudaMemcpy(md.data(), e->d_maps, sizeof(MapDev) * (size_t)nm, cudaMemcpyDeviceToHost));
+  for (int m = 0; m < nm; ++m) md[(size_t)m].bfs = e->d_bfs + per * (size_t)m;
+  CU(cudaMemcpy(e->d_maps, md.data(), sizeof(MapDev) * (size_t)nm, cudaMemcpyHostToDevice));
+  e->base.map0 = md[0];
+  return MDX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GreedyAgents.get_actions, one warp per environment, robots are lanes (greedyagent.py:42-174).
+//
+// The agent's package list is reconstructed in closed form from the env's schedule: init_agents stores the
+// packages visible at t = 0 and the first get_actions call appends the same packages again (is_init is only
+// set inside get_actions, :52-62,121-129), later calls append the packages spawning at that step.  With n0
+// packages at t = 0 the list entry j therefore holds package id (j < n0 ? j + 1 : j - n0 + 1), and the list
+// has n0 + #{start_time <= t} entries at time t.  The reference indexes that list by `package_id - 1`
+// everywhere (:143,147,165-168) -- for ids beyond the t = 0 packages that is a different entry -- and so
+// does this kernel.
+// ------------------------------------------------------------------------------------------------
+struct GreedyArgs {
+  uint32_t* gstate;   // [n_envs][32]
+  uint32_t* gfree;    // [n_envs][fw]
+  int32_t fw;
+  uint8_t* out;       // [n][R]
+};
+
+__global__ void __launch_bounds__(128) mdx_greedy_kernel(const __grid_constant__ KParams p, const GreedyArgs a) {
+  extern __shared__ uint32_t sm_free[];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int widx = blockIdx.x * (blockDim.x >> 5) + wib;
+  if (widx >= p.n) return;
+  const int env = p.env_ids ? __ldg(p.env_ids + widx) : widx;
+  uint32_t* fr = sm_free + (size_t)wib * a.fw;
+  MapDev map = p.map0;
+  if (p.env_map) map = p.maps[__ldg(p.env_map + env)];
+  const int R = p.R, P = p.P, Wo = p.W_out, HW = p.HW;
+  const int t = p.t[env];
+  const int slot = p.ep[env] % p.E;
+  const uint16_t* S = p.sched + ((size_t)slot * p.n_envs + env) * 4 * p.Pp8;  // start cells
+  const uint16_t* G = S + p.Pp8;                                                // target cells
+  const uint16_t* T0 = S + 2 * p.Pp8;                                           // start times
+  int n0 = 0, cnt = 0;
+  for (int base = 0; base < P; base += 32) {
+    const int j = base + lane;
+    const int t0 = j < P ? (int)__ldg(T0 + j) : 0x7fffffff;
+    n0 += __popc(__ballot_sync(FULL, t0 == 0));
+    cnt += __popc(__ballot_sync(FULL, t0 <= t));
+  }
+  const int L = n0 + cnt;  // entries of the agent's package list after this call's update_inner_state
+  const bool active = lane < R;
+  const uint32_t rob = active ? p.robots[(size_t)env * R + lane] : 0u;
+  const int cell = (int)(rob & 0xffffu), carry = (int)(rob >> 16);
+  uint32_t gs = 0u;
+  if (t == 0) {  // GreedyAgents() + init_agents(state): every robot 'free', every package free
+    for (int i = lane; i < a.fw; i += 32) fr[i] = 0xffffffffu;
+  } else {
+    for (int i = lane; i < a.fw; i += 32) fr[i] = a.gfree[(size_t)env * a.fw + i];
+    if (active) gs = a.gstate[(size_t)env * 32 + lane];
+  }
+  int tgt = (int)(gs & 0xffffu);
+  const int prev_carry = (int)(gs >> 16);
+  // update_inner_state (:102-117): only a robot that WAS carrying refreshes its target from the env
+  if (prev_carry != 0) tgt = carry;
+  __syncwarp();
+  const int r = (int)__umulhi((uint32_t)cell, p.mul_wout), c = cell - r * Wo;
+  bool fresh = false;
+  // robots in index order: a 'free' robot takes the Manhattan-nearest entry whose flag is still set
+  // (first minimum in list order, :149-160) and clears the flag AT INDEX id - 1 (:163)
+  for (int i = 0; i < R; ++i) {
+    if (__shfl_sync(FULL, tgt, i) != 0) continue;
+    const int ri = __shfl_sync(FULL, r, i), ci = __shfl_sync(FULL, c, i);
+    uint32_t best = 0xffffffffu;
+    for (int j = lane; j < L; j += 32) {
+      if ((fr[j >> 5] >> (j & 31)) & 1u) {
+        const int id = j < n0 ? j + 1 : j - n0 + 1;
+        const uint32_t sc = __ldg(S + id - 1);
+        const int sr = (int)__umulhi(sc, p.mul_wout);
+        const int d = abs(sr - ri) + abs((int)sc - sr * Wo - ci);
+        best = min(best, ((uint32_t)d << 16) | (uint32_t)j);
+      }
+    }
+    best = __reduce_min_sync(FULL, best);
+    if (best != 0xffffffffu) {
+      const int j = (int)(best & 0xffffu);
+      const int id = j < n0 ? j + 1 : j - n0 + 1;
+      if (lane == 0) fr[(id - 1) >> 5] &= ~(1u << ((id - 1) & 31));
+      if (lane == i) {
+        tgt = id;
+        fresh = true;
+      }
+      __syncwarp();
+    }
+  }
+  // update_move_to_target (:64-100) for every robot that has a target
+  int code = MV_S;  // ('S', '0')
+  if (active && tgt != 0) {
+    const int idx = tgt - 1;                                 // list index used by the reference
+    const int id = idx < n0 ? idx + 1 : idx - n0 + 1;        // package that entry really holds
+    const bool to_target = !fresh && carry != 0;
+    const int goal = (int)__ldg((to_target ? G : S) + id - 1);
+    const int gr = (int)__umulhi((uint32_t)goal, p.mul_wout), gc = goal - gr * Wo;
+    int dist = abs(gr - r) + abs(gc - c);
+    int mv = MV_S, act = 0;
+    if (dist >= 1) {
+      // run_bfs (:6-41): first of U, D, L, R whose BFS distance to the goal is one less than ours
+      const uint16_t* d = map.bfs + (size_t)goal * HW;
+      const int ds = (int)__ldg(d + cell);
+      if (ds == 0xFFFF) {
+        dist = 100000;
+      } else {
+        dist = ds;
+        if (r > 0 && (int)__ldg(d + cell - Wo) == ds - 1) {
+          mv = MV_U;
+          dist = ds - 1;
+        } else if (r + 1 < map.H && (int)__ldg(d + cell + Wo) == ds - 1) {
+          mv = MV_D;
+          dist = ds - 1;
+        } else if (c > 0 && (int)__ldg(d + cell - 1) == ds - 1) {
+          mv = MV_L;
+          dist = ds - 1;
+        } else if (c + 1 < map.W && (int)__ldg(d + cell + 1) == ds - 1) {
+          mv = MV_R;
+          dist = ds - 1;
+        }
+      }
+      if (dist == 0) act = to_target ? 2 : 1;
+    } else {
+      act = to_target ? 2 : 1;
+    }
+    code = mv + 5 * act;
+  }
+  if (active) {
+    a.out[(size_t)widx * R + lane] = (uint8_t)code;
+    a.gstate[(size_t)env * 32 + lane] = (uint32_t)tgt | ((uint32_t)carry << 16);
+  }
+  for (int i = lane; i < a.fw; i += 32) a.gfree[(size_t)env * a.fw + i] = fr[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// GAE (MAPPO/trainer.py:288-301): one thread per env walks its column of the [T, N] rollout backwards;
+// every load/store is coalesced across envs.  float32, no FMA contraction (-fmad=false), the reference's
+// order of operations.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mdx_gae_kernel(const float* __restrict__ rew, const float* __restrict__ val,
+                                                      const uint8_t* __restrict__ done, const float* __restrict__ last_value,
+                                                      int T, int N, float gamma, float gl, float* __restrict__ adv,
+                                                      float* __restrict__ ret) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float next_v = last_value[n];
+  float last = 0.0f;
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t k = (size_t)t * N + n;
+    const float nnt = __fsub_rn(1.0f, done[k] ? 1.0f : 0.0f);
+    const float v = val[k];
+    // delta = r + GAMMA * next_values * next_non_terminal - v
+    const float delta = __fsub_rn(__fadd_rn(rew[k], __fmul_rn(__fmul_rn(gamma, next_v), nnt)), v);
+    // last = delta + GAMMA * GAE_LAMBDA * next_non_terminal * last   (GAMMA * GAE_LAMBDA is one Python float)
+    last = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nnt), last));
+    adv[k] = last;
+    ret[k] = __fadd_rn(last, v);
+    next_v = v;
+  }
+}
+
+}  // namespace mdx
+
+// ------------------------------------------------------------------------------------------------
+// checkpoint blob: header, then every array in a fixed order
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct CkptHeader {
+  uint64_t magic;  // "MDXCKPT1"
+  int32_t n, R, P, T, E, Pp8, Pp16, has_greedy, gfree_words, reserved;
+  int64_t bytes;
+};
+constexpr uint64_t kMagic = 0x3154504b4358444dull;
+
+struct Seg {
+  void* dev;
+  size_t bytes;
+};
+
+std::vector<Seg> device_segments(mdx_env* e) {
+  const size_t n = (size_t)e->n;
+  const KParams& b = e->base;
+  std::vector<Seg> s = {
+      {e->d_t, sizeof(int32_t) * n},
+      {e->d_ep, sizeof(int32_t) * n},
+      {e->d_ep_avail, sizeof(int32_t) * n},
+      {e->d_total, sizeof(double) * n},
+      {e->d_robots, sizeof(uint32_t) * n * e->R},
+      {e->d_status, n * b.Pp16},
+      {e->d_sched, sizeof(uint16_t) * (size_t)e->E * n * 4 * b.Pp8},
+      {e->d_sched_robots, sizeof(uint16_t) * (size_t)e->E * n * 32},
+      {e->d_counters, sizeof(uint32_t) * n * 8},
+  };
+  if (e->d_greedy) {
+    s.push_back({e->d_greedy, sizeof(uint32_t) * n * 32});
+    s.push_back({e->d_gfree, sizeof(uint32_t) * n * (size_t)e->gfree_words});
+  }
+  return s;
+}
+
+size_t host_bytes(const mdx_env* e) {
+  const size_t n = (size_t)e->n;
+  return n * (sizeof(uint32_t) * 624 + sizeof(int32_t)) + 2 * n * sizeof(int32_t);  // rng state + pos, sampled, ep_host
+}
+
+int ensure_greedy(mdx_env* e) {
+  if (e->d_greedy) return MDX_OK;
+  DeviceGuard g(e->device);
+  e->gfree_words = (2 * std::max(1, e->P) + 31) / 32;
+  const size_t n = (size_t)e->n;
+  CU(cudaMalloc(&e->d_greedy, sizeof(uint32_t) * n * 32));
+  CU(cudaMalloc(&e->d_gfree, sizeof(uint32_t) * n * (size_t)e->gfree_words));
+  CU(cudaMemset(e->d_greedy, 0, sizeof(uint32_t) * n * 32));
+  CU(cudaMemset(e->d_gfree, 0xff, sizeof(uint32_t) * n * (size_t)e->gfree_words));
+  return MDX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t mdx_greedy_actions(mdx_env* e, const int32_t* d_env_ids, int32_t n, uint8_t* d_actions, void* stream) {
+  if (!e || !d_actions) return fail(MDX_E_INVALID, "null argument");
+  if (d_env_ids == nullptr && n != e->n) return fail(MDX_E_INVALID, "n must equal n_envs when env ids are not given (got %d, have %d)", n, e->n);
+  if (n < 0 || n > e->n) return fail(MDX_E_INVALID, "bad env count %d", n);
+  if (n == 0) return MDX_OK;
+  int rc = ensure_bfs(e);
+  if (rc != MDX_OK) return rc;
+  if ((rc = ensure_greedy(e)) != MDX_OK) return rc;
+  DeviceGuard g(e->device);
+  KParams kp = e->base;
+  kp.env_ids = d_env_ids;
+  kp.n = n;
+  GreedyArgs a{e->d_greedy, e->d_gfree, e->gfree_words, d_actions};
+  const size_t smem = sizeof(uint32_t) * 4 * (size_t)e->gfree_words;
+  mdx_greedy_kernel<<<(unsigned)((n + 3) / 4), 128, smem, static_cast<cudaStream_t>(stream)>>>(kp, a);
+  CU(cudaGetLastError());
+  return MDX_OK;
+}
+
+int32_t mdx_bfs_table(mdx_env* e, int32_t map_id, uint16_t* h_out) {
+  if (!e || !h_out) return fail(MDX_E_INVALID, "null argument");
+  if (map_id < 0 || map_id >= (int)e->maps.size()) return fail(MDX_E_INVALID, "map id %d out of range", map_id);
+  int rc = ensure_bfs(e);
+  if (rc != MDX_OK) return rc;
+  DeviceGuard g(e->device);
+  const size_t per = (size_t)e->base.HW * e->base.HW;
+  CU(cudaMemcpy(h_out, e->d_bfs + per * (size_t)map_id, sizeof(uint16_t) * per, cudaMemcpyDeviceToHost));
+  return MDX_OK;
+}
+
+int32_t mdx_gae(const float* d_rewards, const float* d_values, const uint8_t* d_dones, const float* d_last_value, int32_t T,
+                int32_t N, double gamma, double gae_lambda, float* d_advantages, float* d_returns, void* stream) {
+  if (!d_rewards || !d_values || !d_dones || !d_last_value || !d_advantages || !d_returns) return fail(MDX_E_INVALID, "null argument");
+  if (T < 0 || N < 0) return fail(MDX_E_INVALID, "negative rollout shape");
+  if (T == 0 || N == 0) return MDX_OK;
+  // a Python float scalar times a float32 tensor is evaluated in float32 with the scalar rounded once
+  const float g32 = (float)gamma, gl32 = (float)(gamma * gae_lambda);
+  mdx_gae_kernel<<<(unsigned)((N + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_rewards, d_values, d_dones, d_last_value,
+                                                                                           T, N, g32, gl32, d_advantages, d_returns);
+  CU(cudaGetLastError());
+  return MDX_OK;
+}
+
+int64_t mdx_checkpoint_bytes(const mdx_env* e) {
+  if (!e) return 0;
+  size_t total = sizeof(CkptHeader) + host_bytes(e);
+  for (const Seg& s : device_segments(const_cast<mdx_env*>(e))) total += s.bytes;
+  return (int64_t)total;
+}
+
+int32_t mdx_checkpoint_save(mdx_env* e, void* h_buf, int64_t bytes, void* stream) {
+  if (!e || !h_buf) return fail(MDX_E_INVALID, "null argument");
+  const int64_t need = mdx_checkpoint_bytes(e);
+  if (bytes < need) return fail(MDX_E_INVALID, "checkpoint buffer too small (%lld < %lld bytes)", (long long)bytes, (long long)need);
+  DeviceGuard g(e->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaStreamSynchronize(st));
+  unsigned char* p = static_cast<unsigned char*>(h_buf);
+  CkptHeader h{};
+  h.magic = kMagic;
+  h.n = e->n, h.R = e->R, h.P = e->P, h.T = e->T, h.E = e->E, h.Pp8 = e->base.Pp8, h.Pp16 = e->base.Pp16;
+  h.has_greedy = e->d_greedy ? 1 : 0;
+  h.gfree_words = e->gfree_words;
+  h.bytes = need;
+  std::memcpy(p, &h, sizeof(h));
+  p += sizeof(h);
+  for (const Seg& s : device_segments(e)) {
+    CU(cudaMemcpy(p, s.dev, s.bytes, cudaMemcpyDeviceToHost));
+    p += s.bytes;
+  }
+  for (int i = 0; i < e->n; ++i) {
+    std::memcpy(p, e->rng[(size_t)i].mt, sizeof(uint32_t) * 624);
+    p += sizeof(uint32_t) * 624;
+    const int32_t pos = e->rng[(size_t)i].pos;
+    std::memcpy(p, &pos, sizeof(pos));
+    p += sizeof(pos);
+  }
+  std::memcpy(p, e->sampled.data(), sizeof(int32_t) * (size_t)e->n);
+  p += sizeof(int32_t) * (size_t)e->n;
+  // the device episode cursor is authoritative; ep_host is refreshed from it on load
+  std::memcpy(p, e->ep_host.data(), sizeof(int32_t) * (size_t)e->n);
+  return MDX_OK;
+}
+
+int32_t mdx_checkpoint_load(mdx_env* e, const void* h_buf, int64_t bytes, void* stream) {
+  if (!e || !h_buf) return fail(MDX_E_INVALID, "null argument");
+  if (bytes < (int64_t)sizeof(CkptHeader)) return fail(MDX_E_INVALID, "not an mdx checkpoint");
+  CkptHeader h;
+  std::memcpy(&h, h_buf, sizeof(h));
+  if (h.magic != kMagic) return fail(MDX_E_INVALID, "not an mdx checkpoint");
+  if (h.n != e->n || h.R != e->R || h.P != e->P || h.T != e->T || h.E != e->E || h.Pp8 != e->base.Pp8 || h.Pp16 != e->base.Pp16)
+    return fail(MDX_E_INVALID, "checkpoint shape (n=%d R=%d P=%d T=%d E=%d) does not match this instance (n=%d R=%d P=%d T=%d E=%d)", h.n,
+                h.R, h.P, h.T, h.E, e->n, e->R, e->P, e->T, e->E);
+  if (h.has_greedy) {
+    int rc = ensure_greedy(e);
+    if (rc != MDX_OK) return rc;
+    if (h.gfree_words != e->gfree_words) return fail(MDX_E_INVALID, "checkpoint greedy state does not match");
+  }
+  DeviceGuard g(e->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaStreamSynchronize(st));
+  std::vector<Seg> segs = device_segments(e);
+  if (!h.has_greedy && e->d_greedy) segs.resize(segs.size() - 2);
+  size_t need = sizeof(CkptHeader) + host_bytes(e);
+  for (const Seg& s : segs) need += s.bytes;
+  if ((int64_t)need != h.bytes || bytes < h.bytes) return fail(MDX_E_INVALID, "truncated or inconsistent checkpoint");
+  const unsigned char* p = static_cast<const unsigned char*>(h_buf) + sizeof(h);
+  for (const Seg& s : segs) {
+    CU(cudaMemcpy(s.dev, p, s.bytes, cudaMemcpyHostToDevice));
+    p += s.bytes;
+  }
+  for (int i = 0; i < e->n; ++i) {
+    std::memcpy(e->rng[(size_t)i].mt, p, sizeof(uint32_t) * 624);
+    p += sizeof(uint32_t) * 624;
+    int32_t pos;
+    std::memcpy(&pos, p, sizeof(pos));
+    p += sizeof(pos);
+    if (pos < 0 || pos > 624) return fail(MDX_E_INVALID, "corrupt generator state in checkpoint");
+    e->rng[(size_t)i].pos = pos;
+  }
+  std::memcpy(e->sampled.data(), p, sizeof(int32_t) * (size_t)e->n);
+  p += sizeof(int32_t) * (size_t)e->n;
+  std::memcpy(e->ep_host.data(), p, sizeof(int32_t) * (size_t)e->n);
+  return MDX_OK;
+}
+
+}  // extern "C"

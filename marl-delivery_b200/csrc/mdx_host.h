@@ -100,6 +100,11 @@ struct mdx_env {
   int32_t* h_i32 = nullptr;     // pinned scratch [n]
   uint16_t* d_stage = nullptr;
   int32_t* d_ids = nullptr;     // [2][n]
+  // f2: greedy policy + BFS tables (allocated on first use)
+  uint16_t* d_bfs = nullptr;       // [n_maps][HW][HW]
+  uint32_t* d_greedy = nullptr;    // [n][32]  target id | carried id seen at the previous call << 16
+  uint32_t* d_gfree = nullptr;     // [n][gfree_words] packages_free bits over the agent's own list
+  int gfree_words = 0;
   int wpb_override = 0;
   size_t smem_configured[96] = {};
   int no_fixed = 0;       // MDX_NOFIX=1: never use the shape-specialised instantiation
@@ -113,4 +118,6 @@ namespace mdx {
 int launch_env_kernel_1(mdx_env* e, const KParams& kp, cudaStream_t st);
 int launch_env_kernel_2(mdx_env* e, const KParams& kp, cudaStream_t st);
 int launch_env_kernel_3(mdx_env* e, const KParams& kp, cudaStream_t st);
+// builds the all-pairs BFS tables and publishes them in the map descriptors (idempotent)
+int ensure_bfs(mdx_env* e);
 }  // namespace mdx

@@ -57,6 +57,8 @@ struct MapDev {
   const float* qr;            // [2*H_out-1]  qr[d + H_out-1] = (float)((double)d / H)
   const float* qc;            // [2*W_out-1]
   const uint16_t* rank;       // [(2*H_out-1) * (2*W_out-1)] dense rank of the float64 sort key
+  const uint16_t* bfs;        // [HW][HW] all-pairs shortest-path length over free cells (output-plane cell ids,
+                              // 0xFFFF = unreachable / obstacle); nullptr until the greedy policy or BFS shaping needs it
 };
 
 struct KParams {
@@ -86,7 +88,7 @@ struct KParams {
   // rewards
   double move_cost, delivery_reward, delay_reward;
   float shaping[9];
-  int32_t pad0;
+  int32_t shaping_bfs;     // 1: shaped distance terms use the BFS table instead of Manhattan distance (opt-in)
   // state
   int32_t* t;
   int32_t* ep;

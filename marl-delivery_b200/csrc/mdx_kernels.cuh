@@ -202,8 +202,11 @@ struct Scan {
 // package within 3" (:360-365) and the lowest-id waiting package on its new cell (env.py:267-274,
 // MAPPO/helper.py:312-317).  Package-parallel: lanes own list entries (64 / LPE of them in registers
 // when P <= 64), one group reduction per robot.
-template <int LPE, bool kSmall>
-__device__ __forceinline__ Scan scan_waiting(const Env& w, const Grp<LPE>& g, int R, int nw, int r0, int c0, int r1, int c1) {
+// kBfs: distances are shortest-path lengths from the per-map BFS table (row of the robot's old cell) instead of
+// Manhattan distances (opt-in shaping mode).
+template <int LPE, bool kSmall, bool kBfs>
+__device__ __forceinline__ Scan scan_waiting(const Env& w, const Grp<LPE>& g, int R, int nw, int r0, int c0, int r1, int c1,
+                                             const uint16_t* bfs, int HW, int Wo) {
   constexpr int EPL = 64 / LPE;  // entries per lane when P <= 64
   Scan mine{MDX_NONE32, MDX_NONE32, false};
   if (nw == 0) return mine;
@@ -217,13 +220,15 @@ __device__ __forceinline__ Scan scan_waiting(const Env& w, const Grp<LPE>& g, in
   for (int i = 0; i < R; ++i) {
     const int ri = g.shfl(r0, i), ci = g.shfl(c0, i);
     const uint32_t rci = g.shfl(rc1, i);
+    const uint16_t* brow = kBfs ? bfs + (size_t)(ri * Wo + ci) * HW : nullptr;
     uint32_t best = MDX_NONE32, at_new = MDX_NONE32;
     if (kSmall) {
 #pragma unroll
       for (int s = 0; s < EPL; ++s) {
         if (e[s] != MDX_NONE32) {
           const uint32_t k = (uint32_t)(g.sl + LPE * s);
-          const int d = abs((int)(e[s] >> 8) - ri) + abs((int)(e[s] & 255u) - ci);
+          const int d = kBfs ? (int)__ldg(brow + (e[s] >> 8) * Wo + (e[s] & 255u))
+                             : abs((int)(e[s] >> 8) - ri) + abs((int)(e[s] & 255u) - ci);
           best = min(best, ((uint32_t)d << 16) | k);
           if (e[s] == rci) at_new = min(at_new, k);
         }
@@ -232,7 +237,8 @@ __device__ __forceinline__ Scan scan_waiting(const Env& w, const Grp<LPE>& g, in
 #pragma unroll 1
       for (int k = g.sl; k < nw; k += LPE) {
         const uint32_t rc = w.wrc[k];
-        const int d = abs((int)(rc >> 8) - ri) + abs((int)(rc & 255u) - ci);
+        const int d = kBfs ? (int)__ldg(brow + (rc >> 8) * Wo + (rc & 255u))
+                           : abs((int)(rc >> 8) - ri) + abs((int)(rc & 255u) - ci);
         best = min(best, ((uint32_t)d << 16) | (uint32_t)k);
         if (rc == rci) at_new = min(at_new, (uint32_t)k);
       }
@@ -250,10 +256,10 @@ __device__ __forceinline__ Scan scan_waiting(const Env& w, const Grp<LPE>& g, in
 
 // Shaped team reward of one transition (MAPPO/helper.py:257-369).  Per lane (robot): old / new
 // position and carried id, decoded action, the scan above; w.status still holds the PREVIOUS statuses.
-template <int LPE>
+template <int LPE, bool kBfs>
 __device__ __forceinline__ float shaped_team_reward(const KParams& p, const Env& w, const Grp<LPE>& g, int t_cur, int r0,
                                                     int c0, int k0, int r1, int c1, int k1, int mv, int op, int nw,
-                                                    const Scan& sc, double env_reward) {
+                                                    const Scan& sc, double env_reward, const uint16_t* bfs) {
   float acc = 0.0f;
   if (g.sl < p.R) {
     const uint8_t st0 = k0 ? w.status[k0 - 1] : (uint8_t)ST_NONE;
@@ -297,8 +303,15 @@ __device__ __forceinline__ float shaped_team_reward(const KParams& p, const Env&
       have_goal = true;
     }
     if (have_goal && moved) {
-      const int d_before = abs(r0 - gr) + abs(c0 - gc);
-      const int d_after = abs(r1 - gr) + abs(c1 - gc);
+      int d_before, d_after;
+      if (kBfs) {
+        const uint16_t* brow = bfs + (size_t)(gr * p.W_out + gc) * p.HW;
+        d_before = (int)__ldg(brow + r0 * p.W_out + c0);
+        d_after = (int)__ldg(brow + r1 * p.W_out + c1);
+      } else {
+        d_before = abs(r0 - gr) + abs(c0 - gc);
+        d_after = abs(r1 - gr) + abs(c1 - gc);
+      }
       if (d_after < d_before)
         acc = __fadd_rn(acc, p.shaping[3]);
       else if (d_after > d_before)
@@ -833,7 +846,14 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? MDX_FEAT_BLOCKS : 8) mdx_en
   int action = 3;
   double total0 = 0.0;
   if (kMode & 1) {
-    if (active) action = (int)__ldg(p.actions + (size_t)widx * R + sl);
+    if (active) {
+      if (p.flags & 2u) {  // MDX_F_ACTIONS_I64: the policy's int64 samples, decoded like MAPPO/trainer.py:195-204
+        const long long a64 = __ldg(reinterpret_cast<const long long*>(p.actions) + (size_t)widx * R + sl);
+        action = a64 < 0 ? 18 : (a64 < 15 ? (int)a64 : (int)(a64 % 5));  // package op index >= 3 is clamped to '0'
+      } else {
+        action = (int)__ldg(p.actions + (size_t)widx * R + sl);
+      }
+    }
     total0 = p.total_reward[env];
   }
   load_episode<LPE>(p, w, env, ep % p.E, sl);
@@ -890,7 +910,9 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? MDX_FEAT_BLOCKS : 8) mdx_en
     // robots stand on distinct cells, so pickups never contend across robots: each takes the
     // lowest-id waiting package on its own cell
     const int nw_prev = build_waiting<LPE>(p, w, g, t);
-    const Scan sc = scan_waiting<LPE, kSmall>(w, g, R, nw_prev, r, c, r1, c1);
+    const bool bfs_mode = kFix == 0 && p.shaping_bfs != 0;
+    const Scan sc = bfs_mode ? scan_waiting<LPE, kSmall, true>(w, g, R, nw_prev, r, c, r1, c1, map.bfs, p.HW, Wo)
+                             : scan_waiting<LPE, kSmall, false>(w, g, R, nw_prev, r, c, r1, c1, nullptr, 0, 0);
     const bool want_pick = active && op == 1 && carry == 0;
     const int picked = (want_pick && sc.at_new != MDX_NONE32) ? (int)w.wlist[sc.at_new] : -1;
     const int tgt0 = carry ? (int)w.target[carry - 1] : -1;
@@ -910,7 +932,8 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? MDX_FEAT_BLOCKS : 8) mdx_en
     // shaped reward reads the PREVIOUS statuses, so evaluate it before they change
     float shaped = 0.0f;
     if (p.out_shaped != nullptr)
-      shaped = shaped_team_reward<LPE>(p, w, g, t + 1, r, c, carry, r1, c1, carry1, mv, op, nw_prev, sc, rew);
+      shaped = bfs_mode ? shaped_team_reward<LPE, true>(p, w, g, t + 1, r, c, carry, r1, c1, carry1, mv, op, nw_prev, sc, rew, map.bfs)
+                        : shaped_team_reward<LPE, false>(p, w, g, t + 1, r, c, carry, r1, c1, carry1, mv, op, nw_prev, sc, rew, nullptr);
     g.sync();
     if (delivered) w.status[carry - 1] = ST_DELIVERED;
     if (picked >= 0) w.status[picked] = ST_IN_TRANSIT;

@@ -64,7 +64,7 @@ int launch_env_kernel(mdx_env* e, const KParams& kp, cudaStream_t st) {
   const int ks = kMode == 1 ? 0 : slices(lpe);
   // the headline MAPPO shape has a fully specialised instantiation
   const KParams& b = e->base;
-  if (kMode != 1 && lpe == 32 && ks == 1 && !e->no_fixed && b.R == 5 && b.Pp8 == 56 && b.Pp16 == 64 && b.H_out == 10 && b.W_out == 10 &&
+  if (kMode != 1 && lpe == 32 && ks == 1 && !e->no_fixed && !b.shaping_bfs && b.R == 5 && b.Pp8 == 56 && b.Pp16 == 64 && b.H_out == 10 && b.W_out == 10 &&
       b.K_o == 4 && b.K_p == 5 && b.sel_k == 5 && b.MR == 100 && b.MP == 100 && b.vec_rows_per_flush == 5 && b.stage_b == 44)
     return launch_variant<kMode, 32, 1, true, 1>(e, kp, st);
   if (lpe == 8) return launch_lpe<kMode, 8>(e, kp, st, ks);

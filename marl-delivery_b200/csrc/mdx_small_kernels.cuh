@@ -32,9 +32,17 @@ __global__ void __launch_bounds__(128) mdx_shape_kernel(const __grid_constant__ 
   const int r0 = (int)__umulhi(rob0 & 0xffffu, p.mul_wout), c0 = (int)(rob0 & 0xffffu) - r0 * p.W_out;
   const int r1 = (int)__umulhi(rob1 & 0xffffu, p.mul_wout), c1 = (int)(rob1 & 0xffffu) - r1 * p.W_out;
   const int nw = build_waiting<32>(p, w, g, t);
-  const Scan sc = scan_waiting<32, false>(w, g, R, nw, r0, c0, r1, c1);
-  const float s = shaped_team_reward<32>(p, w, g, p.cur_t[env], r0, c0, (int)(rob0 >> 16), r1, c1, (int)(rob1 >> 16), mv, op,
-                                         nw, sc, p.global_reward[env]);
+  const MapDev map = p.env_map ? p.maps[p.env_map[env]] : p.map0;
+  float s;
+  if (p.shaping_bfs) {
+    const Scan sc = scan_waiting<32, false, true>(w, g, R, nw, r0, c0, r1, c1, map.bfs, p.HW, p.W_out);
+    s = shaped_team_reward<32, true>(p, w, g, p.cur_t[env], r0, c0, (int)(rob0 >> 16), r1, c1, (int)(rob1 >> 16), mv, op, nw, sc,
+                                     p.global_reward[env], map.bfs);
+  } else {
+    const Scan sc = scan_waiting<32, false, false>(w, g, R, nw, r0, c0, r1, c1, nullptr, 0, 0);
+    s = shaped_team_reward<32, false>(p, w, g, p.cur_t[env], r0, c0, (int)(rob0 >> 16), r1, c1, (int)(rob1 >> 16), mv, op, nw, sc,
+                                      p.global_reward[env], nullptr);
+  }
   if (lane == 0) p.out_shaped[env] = s;
 }
 

@@ -35,6 +35,12 @@ class Package:
         self.status = status
 
 
+class StateDict(dict):
+    """The state dict of env.py:139-146 plus a back-reference to the environment slot it was read from, so that
+    drop-in policies (greedyagent.GreedyAgents) can run on the device-resident state instead of re-parsing lists."""
+    __slots__ = ("_view",)
+
+
 class EnvView:
     """One environment slot of a DeliveryBatch with the reference Environment's API."""
 
@@ -92,10 +98,12 @@ class EnvView:
         pk = [(j + 1, int(s["pkg_start_row"][j]) + 1, int(s["pkg_start_col"][j]) + 1, int(s["pkg_target_row"][j]) + 1,
                int(s["pkg_target_col"][j]) + 1, int(s["pkg_start_time"][j]), int(s["pkg_deadline"][j]))
               for j in range(self.n_packages) if int(s["pkg_start_time"][j]) == t]
-        return {"time_step": t, "map": self.grid,
-                "robots": [(int(r) + 1, int(c) + 1, int(k)) for r, c, k in
-                           zip(s["robot_row"], s["robot_col"], s["robot_carry"])],
-                "packages": pk}
+        out = StateDict({"time_step": t, "map": self.grid,
+                         "robots": [(int(r) + 1, int(c) + 1, int(k)) for r, c, k in
+                                    zip(s["robot_row"], s["robot_col"], s["robot_carry"])],
+                         "packages": pk})
+        out._view = self
+        return out
 
     def reset(self):
         self._b.reset(self._ids)

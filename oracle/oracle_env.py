@@ -303,17 +303,46 @@ def global_state(env: OracleEnv, snap, MR=100, MP=100):
     return g.reshape(4, H, W), np.array(v, dtype=np.float32)
 
 
-def shaped_reward(env: OracleEnv, reward, prev, cur, actions, consts=MAPPO_SHAPING):
+def bfs_all_pairs(grid):
+    """greedyagent.py:6-29 (4-neighbour BFS over free cells) from every free cell -> uint16 [H*W, H*W],
+    0xFFFF = unreachable / obstacle.  Used by the greedy-policy checks and the opt-in BFS shaping mode."""
+    grid = np.asarray(grid)
+    H, W = grid.shape
+    out = np.full((H * W, H * W), 0xFFFF, np.uint16)
+    for g in range(H * W):
+        if grid[g // W, g % W]:
+            continue
+        d = out[g]
+        d[g] = 0
+        q = [g]
+        for cur in q:
+            r, c = divmod(cur, W)
+            for nr, nc in ((r - 1, c), (r + 1, c), (r, c - 1), (r, c + 1)):
+                if 0 <= nr < H and 0 <= nc < W and grid[nr, nc] == 0 and d[nr * W + nc] == 0xFFFF:
+                    d[nr * W + nc] = d[cur] + 1
+                    q.append(nr * W + nc)
+    return out
+
+
+def shaped_reward(env: OracleEnv, reward, prev, cur, actions, consts=MAPPO_SHAPING, bfs=None):
     """compute_shaped_rewards, MAPPO/helper.py:257-369: float32 per-agent accumulators in the
     reference's order of terms, numpy float32 `.sum()`, then `python float + np.float32` which numpy>=2
     evaluates in float32.  `prev` / `cur` are snapshots before / after the step (the
-    after-snapshot is taken BEFORE any auto-reset, Q10)."""
+    after-snapshot is taken BEFORE any auto-reset, Q10).
+
+    `bfs` (an all-pairs table from bfs_all_pairs) switches the distance function from the reference's
+    Manhattan distance (MAPPO/helper.py:284-285) to shortest-path length: the OPT-IN mode of the build
+    (BASELINE.json north star vs SURVEY.md Q9).  That mode has no reference behaviour to pin against --
+    PARITY UNPINNED for bfs is not None; it is checked for equality with the Manhattan mode on maps
+    without inner walls and against this restatement elsewhere."""
     (c_pick, c_ontime, c_late, c_closer, c_wpick, c_wdrop, c_stuck, c_idle, c_away) = consts
     W = env.W
     pstat, pt = prev["status"], prev["t"]
     acc = np.zeros(env.R, dtype=np.float32)
 
     def md(a, b):
+        if bfs is not None:
+            return int(bfs[b, a])
         return abs(a // W - b // W) + abs(a % W - b % W)
 
     def tracked(pid):  # "pid in persistent_packages_at_prev_state"
@@ -423,3 +452,22 @@ def mappo_rollout_step(venv: OracleVecEnv, actions, K_o, K_p, MR=100, MP=100, co
         obs.append(np.stack([observation(e, s, i) for i in range(R)]))
         vec.append(np.stack([vector_features(e, s, i, K_o, K_p) for i in range(R)]))
     return shaped, dones, np.stack(obs), np.stack(vec), np.stack(gst), np.stack(gvec)
+
+
+def gae_reference(rewards, values, dones, last_value, gamma, gae_lambda):
+    """The GAE loop of MAPPO/trainer.py:288-301 restated with torch CPU float32 tensors (same expressions,
+    same Python-float scalars) -> (advantages, returns).  The plain-torch reference of the CUDA GAE kernel."""
+    import torch
+
+    rewards, values = torch.as_tensor(rewards, dtype=torch.float32), torch.as_tensor(values, dtype=torch.float32)
+    dones = torch.as_tensor(dones).bool()
+    T = rewards.shape[0]
+    advantages = torch.zeros_like(rewards)
+    last_gae_lambda = 0
+    next_value = torch.as_tensor(last_value, dtype=torch.float32)
+    for t in reversed(range(T)):
+        next_non_terminal = 1.0 - dones[t].float()
+        next_values_step = next_value if t == T - 1 else values[t + 1]
+        delta = rewards[t] + gamma * next_values_step * next_non_terminal - values[t]
+        advantages[t] = last_gae_lambda = delta + gamma * gae_lambda * next_non_terminal * last_gae_lambda
+    return advantages, advantages + values

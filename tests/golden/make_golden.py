@@ -432,6 +432,99 @@ def gen_greedy():
     print("kats_greedy.npz", os.path.getsize(os.path.join(HERE, "kats_greedy.npz")) // 1024, "KiB")
 
 
+def _load_ref_module(name, rel):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+    mod = importlib.util.module_from_spec(spec)
+    with contextlib.redirect_stdout(io.StringIO()):
+        spec.loader.exec_module(mod)
+    return mod
+
+
+def gen_alt():
+    """the other featurisers / shaping of the same boundary, recorded from the
+    unmodified reference along env trajectories -- IDQ/networks.py convert_state (:112-217; identical code in
+    qmix/networks.py:243-348, asserted), qmix/networks.py convert_global_state_to_tensor (:350-468) with the
+    trainer's (7, H, W) shape, IDQ/networks.py reward_shaping (:228-349) both with the (move_str, op_str)
+    tuples the IDQ trainer passes (only the stay penalty can fire: '1' == 1 is False) and with integer package
+    ops (every branch), QMIX/helper.py generate_vector_features / convert_global_state with the QMIX/config.yaml
+    sizes (10 / 20)."""
+    idq = _load_ref_module("idq_networks_ref", "IDQ/networks.py")
+    legacy = _load_ref_module("legacy_qmix_networks_ref", "qmix/networks.py")
+    cases = [("alt_map1", "map1.txt", 5, 50, 120, 31, 200, "homing"), ("alt_map5", "map5.txt", 10, 100, 150, 32, 170, "random"),
+             ("alt_map7", "map.txt", 4, 12, 40, 33, 100, "homing"), ("alt_map3", "map3.txt", 6, 30, 90, 34, 120, "homing")]
+    out, meta = {}, []
+    for name, map_name, R, P, T, seed, n_steps, policy in cases:
+        e = ref_env.Environment(os.path.join(REF, map_name), T, R, P, seed=seed)
+        H, W = e.n_rows, e.n_cols
+        state = e.reset()
+        trk = Tracker(1)
+        trk.update(0, state)
+        rs = np.random.RandomState(seed + 1000)
+        acts_rec = np.zeros((n_steps, R), np.uint8)
+        obs6 = np.zeros((n_steps + 1, R, 6, H, W), np.float32)
+        g7 = np.zeros((n_steps + 1, 7, H, W), np.float32)
+        sh_str = np.zeros((n_steps, R), np.float64)
+        sh_int = np.zeros((n_steps, R), np.float64)
+        qvec = np.zeros((n_steps + 1, R, 6 + 5 * (R - 1) + 5 * 5 + 1), np.float32)
+        qg = np.zeros((n_steps + 1, 6 * 10 + 7 * 20 + 1), np.float32)
+        done_rec = np.zeros(n_steps, np.uint8)
+
+        def feats(k, st, pp):
+            for i in range(R):
+                a = idq.convert_state(st, pp, i)
+                assert np.array_equal(a, legacy.convert_state(st, pp, i))
+                obs6[k, i] = a
+                qvec[k, i] = qmix_helper.generate_vector_features(st, pp, i, T, R - 1, 5)
+            g7[k] = legacy.convert_global_state_to_tensor(st, pp, (7, H, W))
+            qg[k] = qmix_helper.convert_global_state(st, pp, T, 10, 20)[1]
+
+        feats(0, state, trk.persistent_packages_list[0])
+        for s in range(n_steps):
+            a = rs.randint(0, 15, size=R)
+            if policy == "homing":
+                for i, rb in enumerate(e.robots):
+                    if rs.rand() < 0.2:
+                        continue
+                    if rb.carrying:
+                        goal, op_at = e.packages[rb.carrying - 1].target, "2"
+                    else:
+                        wait = [p for p in e.packages if p.status == "waiting"]
+                        if not wait:
+                            continue
+                        goal = min(wait, key=lambda p: abs(p.start[0] - rb.position[0]) + abs(p.start[1] - rb.position[1])).start
+                        op_at = "1"
+                    dr, dc = goal[0] - rb.position[0], goal[1] - rb.position[1]
+                    if dr == 0 and dc == 0:
+                        a[i] = encode("S", op_at)
+                    elif dr != 0 and (dc == 0 or rs.rand() < 0.5):
+                        a[i] = encode("D" if dr > 0 else "U", op_at if (abs(dr) == 1 and dc == 0) else str(rs.randint(0, 3)))
+                    else:
+                        a[i] = encode("R" if dc > 0 else "L", op_at if (abs(dc) == 1 and dr == 0) else str(rs.randint(0, 3)))
+            acts = [decode(x) for x in a]
+            pp_prev = {k: dict(v) for k, v in trk.persistent_packages_list[0].items()}
+            nxt, r, done, info = e.step(acts)
+            acts_rec[s] = a
+            done_rec[s] = done
+            sh_str[s] = idq.reward_shaping(state, nxt, acts, pp_prev, R)
+            sh_int[s] = idq.reward_shaping(state, nxt, [(m, int(o)) for (m, o) in acts], pp_prev, R)
+            if done:
+                nxt = e.reset()
+                trk.clear(0)
+            trk.update(0, nxt)
+            state = nxt
+            feats(s + 1, state, trk.persistent_packages_list[0])
+        out.update({f"{name}_actions": acts_rec, f"{name}_obs6": obs6, f"{name}_g7": g7, f"{name}_shape_str": sh_str,
+                    f"{name}_shape_int": sh_int, f"{name}_qvec": qvec, f"{name}_qgvec": qg, f"{name}_done": done_rec,
+                    f"{name}_grid": grid_of(map_name)})
+        meta.append(dict(name=name, map=map_name, R=R, P=P, T=T, seed=seed, n_steps=n_steps,
+                         urgency_cells=int((obs6[:, :, 1] > 0).sum()), frac_cells=int(((g7[:, 6] > 0) & (g7[:, 6] < 1)).sum()),
+                         int_branches=sorted(set(np.round(sh_int.reshape(-1), 6).tolist()))))
+        print("alt case", meta[-1])
+    out["meta"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(HERE, "kats_alt.npz"), **out)
+    print("kats_alt.npz", os.path.getsize(os.path.join(HERE, "kats_alt.npz")) // 1024, "KiB")
+
+
 def main():
     os.makedirs(HERE, exist_ok=True)
     gen_reset_blocks()
@@ -459,6 +552,9 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "greedy":
         gen_greedy()
+    elif len(sys.argv) > 1 and sys.argv[1] == "alt":
+        gen_alt()
     else:
         main()
         gen_greedy()
+        gen_alt()
