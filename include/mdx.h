@@ -194,6 +194,27 @@ int32_t mdx_greedy_actions(mdx_env* env, const int32_t* d_env_ids, int32_t n, ui
  * [rows_out*cols_out][rows_out*cols_out] uint16 in output-plane cell ids, 0xFFFF = unreachable. */
 int32_t mdx_bfs_table(mdx_env* env, int32_t map_id, uint16_t* h_out);
 
+/* The other featurisers of the same boundary, for every listed env and robot in one launch:
+ * d_obs6 [n, R, 6, rows_out, cols_out] = convert_state of IDQ/networks.py:112-217 (identical code in
+ * qmix/networks.py:243-348): map, urgency of waiting packages and their start cells (both only when the
+ * robot carries nothing), other robots, this robot, target of the carried package;
+ * d_gstate7 [n, 7, rows_out, cols_out] = convert_global_state_to_tensor of qmix/networks.py:350-468 with the
+ * trainer's (7, H, W) shape: map, robots, carrying robots, waiting starts, waiting targets, in-transit
+ * targets, urgency.  float32, either may be NULL. */
+int32_t mdx_featurize_alt(mdx_env* env, const int32_t* d_env_ids, int32_t n, float* d_obs6, float* d_gstate7, void* stream);
+
+/* mdx_step that also evaluates IDQ's per-agent reward_shaping (IDQ/networks.py:228-349) of the transition:
+ * d_agent_rewards [n, n_robots] f64 (the reference returns Python floats).  ops_as_int = 0 reproduces what
+ * IDQ/trainer.py:276-291 does -- it passes (move_str, op_str) tuples, so `package_op == 1` never holds and
+ * only the stay penalty fires; ops_as_int = 1 evaluates every branch as for integer package ops. */
+int32_t mdx_step_idq(mdx_env* env, const uint8_t* d_actions, const int32_t* d_env_ids, int32_t n, double* d_reward,
+                     double* d_agent_rewards, uint8_t* d_done, int32_t ops_as_int, uint32_t flags, void* stream);
+
+/* IDQ reward_shaping on caller-supplied "current" robots against the stored state as "previous" (the per-call
+ * drop-in of IDQ/networks.py:228-349; same inputs as mdx_shaped_reward) -> d_out [n_envs, n_robots] f64. */
+int32_t mdx_reward_shaping_idq(mdx_env* env, const uint32_t* d_cur_robots, const int32_t* d_cur_t, const uint8_t* d_actions,
+                               int32_t ops_as_int, double* d_out, void* stream);
+
 /* GAE + returns of MAPPO/trainer.py:288-301 for a [T, N] rollout, float32 with the reference's order of
  * operations: delta = r + gamma*v_next*nonterminal - v; adv = last = delta + (gamma*lambda)*nonterminal*last;
  * ret = adv + v.  d_rewards/d_values [T, N] f32, d_dones [T, N] u8, d_last_value [N] f32 ->

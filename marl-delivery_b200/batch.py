@@ -257,6 +257,31 @@ class DeliveryBatch:
         _lib.check(self._L.mdx_greedy_actions(self._h, _ptr(d_ids), n, _ptr(out), self._stream()))
         return out
 
+    def featurize_alt(self, ids=None, obs6=True, gstate7=True, out=None):
+        """IDQ / legacy-qmix convert_state (IDQ/networks.py:112-217) for every robot and the legacy 7-channel
+        global tensor (qmix/networks.py:350-468) -> (obs6 [n,R,6,H,W], gstate7 [n,7,H,W]) float32 on the GPU."""
+        d_ids, _, n = self._ids(ids)
+        R, H, W = self.n_robots, self.rows_out, self.cols_out
+        if out is None:
+            out = (self._buf("obs6", (n, R, 6, H, W), torch.float32) if obs6 else None,
+                   self._buf("gstate7", (n, 7, H, W), torch.float32) if gstate7 else None)
+        _lib.check(self._L.mdx_featurize_alt(self._h, _ptr(d_ids), n, _ptr(out[0]), _ptr(out[1]), self._stream()))
+        return out
+
+    def step_idq(self, actions, ids=None, auto_reset: bool = False, ops_as_int: bool = False, out=None):
+        """step + IDQ's per-agent reward_shaping (IDQ/networks.py:228-349) -> (reward f64 [n], agent rewards
+        f64 [n, R], done u8 [n]).  ops_as_int=False is what IDQ/trainer.py does (string ops: stay penalty only)."""
+        d_ids, _, n = self._ids(ids)
+        actions, aflags = self._check_actions(actions, n)
+        if out is None:
+            out = (self._buf("reward", (n,), torch.float64), self._buf("agent_rewards", (n, self.n_robots), torch.float64),
+                   self._buf("done", (n,), torch.uint8))
+        reward, agent, done = out
+        _lib.check(self._L.mdx_step_idq(self._h, _ptr(actions), _ptr(d_ids), n, _ptr(reward), _ptr(agent), _ptr(done),
+                                        1 if ops_as_int else 0, (MDX_F_AUTO_RESET if auto_reset else 0) | aflags, self._stream()))
+        self._version += 1
+        return reward, agent, done
+
     def bfs_table(self, map_id: int = 0) -> np.ndarray:
         """All-pairs shortest-path lengths of one map, uint16 [H*W, H*W] in output-plane cell ids (0xFFFF =
         unreachable): run_bfs (greedyagent.py:6-29) from every free cell."""
@@ -277,6 +302,20 @@ class DeliveryBatch:
         blob = blob.detach().to("cpu", torch.uint8).contiguous()
         _lib.check(self._L.mdx_checkpoint_load(self._h, C.c_void_p(blob.data_ptr()), int(blob.numel()), self._stream()))
         self._version += 1
+
+    def reward_shaping_idq(self, cur_robots, cur_t, actions, ops_as_int: bool = False):
+        """IDQ reward_shaping with the stored state as 'previous' (IDQ/networks.py:228-349) -> f64 [n, R]."""
+        n = self.n_envs
+        cur_robots = cur_robots.to(self.device, torch.int64).contiguous()
+        packed = (cur_robots[..., 0] | (cur_robots[..., 1] << 16)).to(torch.int32).contiguous()
+        cur_t = cur_t.to(self.device, torch.int32).contiguous()
+        actions, aflags = self._check_actions(actions, n)
+        if aflags:
+            raise ValueError("reward_shaping_idq takes uint8 action codes")
+        out = torch.empty((n, self.n_robots), dtype=torch.float64, device=self.device)
+        _lib.check(self._L.mdx_reward_shaping_idq(self._h, _ptr(packed), _ptr(cur_t), _ptr(actions), 1 if ops_as_int else 0,
+                                                  _ptr(out), self._stream()))
+        return out
 
     # ------------------------------------------------------------------ introspection
     def get_state(self, i: int) -> dict:

@@ -534,7 +534,7 @@ int32_t mdx_prefetch(mdx_env* e, int32_t ahead, void* stream) {
 
 static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int32_t* d_env_ids, int32_t n, double* d_reward,
                        float* d_shaped, uint8_t* d_done, float* d_obs, float* d_vec, float* d_gstate, float* d_gvec,
-                       uint32_t flags, void* stream) {
+                       uint32_t flags, void* stream, double* d_agent = nullptr, int ops_as_int = 0) {
   if (!e) return fail(MDX_E_INVALID, "null env");
   if ((mode & 1) && !d_actions) return fail(MDX_E_INVALID, "actions are required");
   if (d_env_ids == nullptr && n != e->n) return fail(MDX_E_INVALID, "n must equal n_envs when env ids are not given (got %d, have %d)", n, e->n);
@@ -557,6 +557,8 @@ static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int
   kp.vec = d_vec;
   kp.gstate = d_gstate;
   kp.gvec = d_gvec;
+  kp.out_agent = d_agent;
+  kp.idq_ops_int = ops_as_int;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (mode == 1) return launch_env_kernel_1(e, kp, st);
   if (mode == 2) return launch_env_kernel_2(e, kp, st);
@@ -566,6 +568,13 @@ static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int
 int32_t mdx_step(mdx_env* e, const uint8_t* d_actions, const int32_t* d_env_ids, int32_t n, double* d_reward, float* d_shaped,
                  uint8_t* d_done, uint32_t flags, void* stream) {
   return step_common(e, 1, d_actions, d_env_ids, n, d_reward, d_shaped, d_done, nullptr, nullptr, nullptr, nullptr, flags, stream);
+}
+
+int32_t mdx_step_idq(mdx_env* e, const uint8_t* d_actions, const int32_t* d_env_ids, int32_t n, double* d_reward, double* d_agent_rewards,
+                     uint8_t* d_done, int32_t ops_as_int, uint32_t flags, void* stream) {
+  if (!d_agent_rewards) return fail(MDX_E_INVALID, "agent reward output is required");
+  return step_common(e, 1, d_actions, d_env_ids, n, d_reward, nullptr, d_done, nullptr, nullptr, nullptr, nullptr, flags, stream,
+                     d_agent_rewards, ops_as_int ? 1 : 0);
 }
 
 int32_t mdx_featurize(mdx_env* e, const int32_t* d_env_ids, int32_t n, float* d_obs, float* d_vec, float* d_gstate, float* d_gvec,
@@ -579,11 +588,27 @@ int32_t mdx_step_featurize(mdx_env* e, const uint8_t* d_actions, const int32_t* 
   return step_common(e, 3, d_actions, d_env_ids, n, d_reward, d_shaped, d_done, d_obs, d_vec, d_gstate, d_gvec, flags, stream);
 }
 
+static int shape_common(mdx_env* e, const uint32_t* d_cur_robots, const int32_t* d_cur_t, const uint8_t* d_actions,
+                        const double* d_global_reward, float* d_out, double* d_agent, int ops_as_int, void* stream);
+
 int32_t mdx_shaped_reward(mdx_env* e, const uint32_t* d_cur_robots, const int32_t* d_cur_t, const uint8_t* d_actions,
                           const double* d_global_reward, float* d_out, void* stream) {
   if (!e || !d_cur_robots || !d_cur_t || !d_actions || !d_global_reward || !d_out) return fail(MDX_E_INVALID, "null argument");
+  return shape_common(e, d_cur_robots, d_cur_t, d_actions, d_global_reward, d_out, nullptr, 0, stream);
+}
+
+int32_t mdx_reward_shaping_idq(mdx_env* e, const uint32_t* d_cur_robots, const int32_t* d_cur_t, const uint8_t* d_actions,
+                               int32_t ops_as_int, double* d_out, void* stream) {
+  if (!e || !d_cur_robots || !d_cur_t || !d_actions || !d_out) return fail(MDX_E_INVALID, "null argument");
+  return shape_common(e, d_cur_robots, d_cur_t, d_actions, nullptr, nullptr, d_out, ops_as_int ? 1 : 0, stream);
+}
+
+static int shape_common(mdx_env* e, const uint32_t* d_cur_robots, const int32_t* d_cur_t, const uint8_t* d_actions,
+                        const double* d_global_reward, float* d_out, double* d_agent, int ops_as_int, void* stream) {
   DeviceGuard g(e->device);
   KParams kp = e->base;
+  kp.out_agent = d_agent;
+  kp.idq_ops_int = ops_as_int;
   kp.cur_robots = d_cur_robots;
   kp.cur_t = d_cur_t;
   kp.actions = d_actions;

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "mdx_host.h"
+#include "mdx_alt.cuh"
 
 using namespace mdx;
 
@@ -295,6 +296,26 @@ int32_t mdx_greedy_actions(mdx_env* e, const int32_t* d_env_ids, int32_t n, uint
   GreedyArgs a{e->d_greedy, e->d_gfree, e->gfree_words, d_actions};
   const size_t smem = sizeof(uint32_t) * 4 * (size_t)e->gfree_words;
   mdx_greedy_kernel<<<(unsigned)((n + 3) / 4), 128, smem, static_cast<cudaStream_t>(stream)>>>(kp, a);
+  CU(cudaGetLastError());
+  return MDX_OK;
+}
+
+int32_t mdx_featurize_alt(mdx_env* e, const int32_t* d_env_ids, int32_t n, float* d_obs6, float* d_gstate7, void* stream) {
+  if (!e) return fail(MDX_E_INVALID, "null env");
+  if (d_env_ids == nullptr && n != e->n) return fail(MDX_E_INVALID, "n must equal n_envs when env ids are not given (got %d, have %d)", n, e->n);
+  if (n < 0 || n > e->n) return fail(MDX_E_INVALID, "bad env count %d", n);
+  if (n == 0) return MDX_OK;
+  if ((reinterpret_cast<uintptr_t>(d_obs6) | reinterpret_cast<uintptr_t>(d_gstate7)) & 15u)
+    return fail(MDX_E_INVALID, "feature tensors must be 16-byte aligned");
+  DeviceGuard g(e->device);
+  KParams kp = e->base;
+  kp.env_ids = d_env_ids;
+  kp.n = n;
+  const int HW = e->base.HW;
+  AltArgs a{d_obs6, d_gstate7, (int32_t)(sizeof(float) * ((HW + 3) & ~3) + sizeof(uint32_t) * 6 * e->base.W32 + 15) / 16 * 16};
+  const size_t smem = (size_t)4 * a.smem_per_warp;
+  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(mdx_alt_featurize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mdx_alt_featurize_kernel<<<(unsigned)((n + 3) / 4), 128, smem, static_cast<cudaStream_t>(stream)>>>(kp, a);
   CU(cudaGetLastError());
   return MDX_OK;
 }

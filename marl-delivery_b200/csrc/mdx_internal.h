@@ -116,6 +116,9 @@ struct KParams {
   float* vec;
   float* gstate;
   float* gvec;
+  double* out_agent;        // [n, R] IDQ per-agent reward_shaping (IDQ/networks.py:228-349), nullptr = off
+  int32_t idq_ops_int;      // 0: package ops arrive as strings like in IDQ/trainer.py (only the stay penalty can fire); 1: ints
+  int32_t pad1;
   // shaped-reward-only call
   const uint32_t* cur_robots;
   const int32_t* cur_t;

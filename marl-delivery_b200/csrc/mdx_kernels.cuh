@@ -325,6 +325,37 @@ __device__ __forceinline__ float shaped_team_reward(const KParams& p, const Env&
   return __fadd_rn(__double2float_rn(env_reward), s);
 }
 
+// IDQ's per-agent reward_shaping (IDQ/networks.py:228-349) for one robot, Python-float accumulation in the
+// reference's order.  w.status / the waiting list still describe the state BEFORE the transition.
+__device__ __forceinline__ double idq_agent_reward(const Env& w, int nw, bool moved, int op, int r0, int c0, int k0, int k1,
+                                                   bool at_target, int t_cur, int dl0, int ops_int) {
+  double acc = 0.0;
+  if (!moved) acc = __dadd_rn(acc, -0.1);  // SHAPING_STAY_PENALTY (:283-284)
+  if (ops_int) {  // with the trainer's string ops `package_op == 1` is never true (IDQ/trainer.py:276-291)
+    if (op == 1) {  // :300-318
+      if (k0 == 0 && k1 != 0) {
+        acc = __dadd_rn(acc, 2.0);
+      } else if (k0 != 0) {
+        acc = __dadd_rn(acc, -0.1);
+      } else {  // failed pickup: was a waiting package on the robot's PREVIOUS cell?
+        const uint32_t rc_old = ((uint32_t)r0 << 8) | (uint32_t)c0;
+        bool avail = false;
+        for (int k = 0; k < nw; ++k) avail = avail || (uint32_t)w.wrc[k] == rc_old;
+        if (!avail) acc = __dadd_rn(acc, -0.1);
+      }
+    } else if (op == 2) {  // :321-347 (a wasted drop costs 0)
+      if (k0 != 0 && k1 == 0) {
+        const uint8_t st0 = w.status[k0 - 1];
+        if ((st0 == ST_WAITING || st0 == ST_IN_TRANSIT) && at_target) {
+          acc = __dadd_rn(acc, 10.0);
+          if (t_cur > dl0) acc = __dadd_rn(acc, -5.0);
+        }
+      }
+    }
+  }
+  return acc;
+}
+
 __device__ __forceinline__ void decode_action(int a, int& mv, int& op) {
   if (a < 15) {
     mv = a % 5;
@@ -934,6 +965,8 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? MDX_FEAT_BLOCKS : 8) mdx_en
     if (p.out_shaped != nullptr)
       shaped = bfs_mode ? shaped_team_reward<LPE, true>(p, w, g, t + 1, r, c, carry, r1, c1, carry1, mv, op, nw_prev, sc, rew, map.bfs)
                         : shaped_team_reward<LPE, false>(p, w, g, t + 1, r, c, carry, r1, c1, carry1, mv, op, nw_prev, sc, rew, nullptr);
+    if (p.out_agent != nullptr && active)
+      p.out_agent[(size_t)widx * R + sl] = idq_agent_reward(w, nw_prev, moved, op, r, c, carry, carry1, cell1 == tgt0, t + 1, dl0, p.idq_ops_int);
     g.sync();
     if (delivered) w.status[carry - 1] = ST_DELIVERED;
     if (picked >= 0) w.status[picked] = ST_IN_TRANSIT;

@@ -33,6 +33,13 @@ __global__ void __launch_bounds__(128) mdx_shape_kernel(const __grid_constant__ 
   const int r1 = (int)__umulhi(rob1 & 0xffffu, p.mul_wout), c1 = (int)(rob1 & 0xffffu) - r1 * p.W_out;
   const int nw = build_waiting<32>(p, w, g, t);
   const MapDev map = p.env_map ? p.maps[p.env_map[env]] : p.map0;
+  if (p.out_agent != nullptr && active) {  // IDQ reward_shaping on the injected transition
+    const int k0 = (int)(rob0 >> 16);
+    const int tg = k0 ? (int)w.target[k0 - 1] : -1;
+    p.out_agent[(size_t)env * R + lane] = idq_agent_reward(w, nw, (rob0 & 0xffffu) != (rob1 & 0xffffu), op, r0, c0, k0, (int)(rob1 >> 16),
+                                                           (int)(rob1 & 0xffffu) == tg, p.cur_t[env], k0 ? (int)w.dl[k0 - 1] : 0, p.idq_ops_int);
+  }
+  if (p.out_shaped == nullptr) return;
   float s;
   if (p.shaping_bfs) {
     const Scan sc = scan_waiting<32, false, true>(w, g, R, nw, r0, c0, r1, c1, map.bfs, p.HW, p.W_out);

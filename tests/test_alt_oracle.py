@@ -12,8 +12,9 @@ from oracle import oracle_env as orc
 
 def replay_alt_case(z, m, visit):
     """Drive an OracleEnv along the recorded actions (auto-reset on done) and call
-    visit(k, env, snapshot, step) for the state the features of row k were taken from; `step` is
-    (before, after, actions) of the transition that led there (None for the initial state)."""
+    visit(k, env, snapshot, shaping) for the state the features of row k were taken from; `shaping` is
+    the oracle's (string-op, int-op) IDQ reward_shaping of the transition that led there, evaluated before
+    any auto-reset (None for the initial state)."""
     e = orc.OracleEnv(z[f"{m['name']}_grid"], m["T"], m["R"], m["P"], seed=m["seed"])
     e.reset()
     visit(0, e, e.snapshot(), None)
@@ -23,9 +24,10 @@ def replay_alt_case(z, m, visit):
         r, d = e.step(a)
         after = e.snapshot()
         assert d == bool(z[f"{m['name']}_done"][s])
+        shaping = (alt.idq_reward_shaping(e, before, after, a, False), alt.idq_reward_shaping(e, before, after, a, True))
         if d:
             e.reset()
-        visit(s + 1, e, e.snapshot(), (before, after, a))
+        visit(s + 1, e, e.snapshot(), shaping)
 
 
 def test_alt_oracle_matches_reference():
@@ -42,8 +44,7 @@ def test_alt_oracle_matches_reference():
             assert np.array_equal(alt.legacy_global_tensor(e, snap).view(np.uint32), z[f"{n}_g7"][k].view(np.uint32)), (n, k)
             assert np.array_equal(orc.global_state(e, snap, 10, 20)[1].view(np.uint32), z[f"{n}_qgvec"][k].view(np.uint32)), (n, k)
             if step is not None:
-                before, after, a = step
-                assert alt.idq_reward_shaping(e, before, after, a, False) == list(z[f"{n}_shape_str"][k - 1]), (n, k)
-                assert alt.idq_reward_shaping(e, before, after, a, True) == list(z[f"{n}_shape_int"][k - 1]), (n, k)
+                assert step[0] == list(z[f"{n}_shape_str"][k - 1]), (n, k)
+                assert step[1] == list(z[f"{n}_shape_int"][k - 1]), (n, k)
 
         replay_alt_case(z, m, visit)

@@ -1,0 +1,132 @@
+"""GPU parity tests of the f3 row: IDQ / legacy-qmix featurisers, IDQ reward_shaping
+and the QMIX-sized MAPPO featurisers, against values recorded from the unmodified reference
+(tests/golden/kats_alt.npz) and, on fresh seeds, against the pinned oracle.  All through the C ABI."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import marl_delivery_b200 as mdb
+from golden_util import GOLDEN
+from oracle import alt_oracle as alt
+from oracle import oracle_env as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(x):
+    return np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+
+
+def _cases():
+    z = np.load(os.path.join(GOLDEN, "kats_alt.npz"))
+    return z, json.loads(str(z["meta"]))
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2, 3])
+def test_alt_golden_replay(idx):
+    z, metas = _cases()
+    m = metas[idx]
+    n, R = m["name"], m["R"]
+    mk = lambda: mdb.DeliveryBatch([z[f"{n}_grid"]], 1, R, m["P"], m["T"], seeds=[m["seed"]], k_others=R - 1, k_packages=5,  # noqa: E731
+                                   max_robots_in_state=10, max_packages_in_state=20, shaping=mdb.QMIX_SHAPING)
+    b_int, b_str = mk(), mk()
+    for b in (b_int, b_str):
+        b.reset()
+
+    def check(k):
+        o6, g7 = [t.cpu().numpy() for t in b_int.featurize_alt()]
+        assert np.array_equal(_bits(o6[0]), _bits(z[f"{n}_obs6"][k])), (n, k)
+        assert np.array_equal(_bits(g7[0]), _bits(z[f"{n}_g7"][k])), (n, k)
+        _, v, _, gv = [t.cpu().numpy() for t in b_int.featurize()]
+        assert np.array_equal(_bits(v[0]), _bits(z[f"{n}_qvec"][k])), (n, k)
+        assert np.array_equal(_bits(gv[0]), _bits(z[f"{n}_qgvec"][k])), (n, k)
+
+    check(0)
+    for s in range(m["n_steps"]):
+        a = torch.from_numpy(z[f"{n}_actions"][s][None].copy())
+        _, ag_int, d = b_int.step_idq(a, ops_as_int=True)
+        _, ag_str, d2 = b_str.step_idq(a, ops_as_int=False)
+        assert np.array_equal(ag_int.cpu().numpy()[0], z[f"{n}_shape_int"][s]), (n, s)
+        assert np.array_equal(ag_str.cpu().numpy()[0], z[f"{n}_shape_str"][s]), (n, s)
+        assert int(d.cpu()[0]) == z[f"{n}_done"][s] == int(d2.cpu()[0])
+        if int(d.cpu()[0]):
+            b_int.reset()
+            b_str.reset()
+        check(s + 1)
+
+
+@pytest.mark.parametrize("maps,R,P,T", [(["map1.txt"], 5, 50, 40), (["map.txt"], 6, 20, 30), (["map5.txt"], 32, 200, 45),
+                                        (["map1.txt", "map3.txt", "map5.txt"], 9, 80, 35)])
+def test_alt_random_sweep_vs_oracle(maps, R, P, T):
+    """Fresh seeds, random + pickup-heavy actions, on-device auto-reset, heterogeneous (padded) maps."""
+    grids = [mdb.maps.stock_map(x) for x in maps]
+    N = 12
+    ve = mdb.VectorizedEnv(mdb.Environment, N, map_file=maps if len(maps) > 1 else maps[0], n_robots=R, n_packages=P,
+                           max_time_steps=T, seed=501)
+    b = ve.batch
+    b.reset()
+    b.prefetch(3)
+    envs = [orc.OracleEnv(grids[i % len(grids)], T, R, P, seed=501 + i) for i in range(N)]
+    for e in envs:
+        e.reset()
+    rs = np.random.RandomState(6)
+    for s in range(2 * T + 5):
+        a = rs.randint(0, 15, size=(N, R)).astype(np.uint8)
+        if s % 3 == 0:
+            a = (a % 5 + 5).astype(np.uint8)  # everybody tries to pick up
+        _, ag, d = b.step_idq(torch.from_numpy(a), auto_reset=True, ops_as_int=True)
+        ag, d = ag.cpu().numpy(), d.cpu().numpy()
+        o6, g7 = [t.cpu().numpy() for t in b.featurize_alt()]
+        for n, e in enumerate(envs):
+            before = e.snapshot()
+            _, dd = e.step(a[n])
+            assert list(ag[n]) == alt.idq_reward_shaping(e, before, e.snapshot(), a[n], True), (s, n)
+            assert bool(d[n]) == dd
+            if dd:
+                e.reset()
+            if (s + n) % 4 == 0:
+                snap = e.snapshot()
+                H, W = e.H, e.W
+                want6 = np.stack([alt.idq_observation(e, snap, i) for i in range(R)])
+                assert np.array_equal(_bits(o6[n][:, :, :H, :W]), _bits(want6)), (s, n)
+                assert np.array_equal(_bits(g7[n][:, :H, :W]), _bits(alt.legacy_global_tensor(e, snap))), (s, n)
+                assert o6[n].sum() == want6.sum()  # padding stays zero
+
+
+def _tracker_of(env):
+    return {p.package_id: {"id": p.package_id, "start_pos": p.start, "target_pos": p.target, "start_time": p.start_time,
+                           "deadline": p.deadline, "status": p.status}
+            for p in env.packages if p.status in ("waiting", "in_transit")}
+
+
+def test_idq_and_qmix_drop_in_functions():
+    """Per-call drop-ins with the reference's signatures, driven from state dicts like the trainers do."""
+    z, metas = _cases()
+    m = metas[0]
+    n, R = m["name"], m["R"]
+    env = mdb.Environment("map1.txt", max_time_steps=m["T"], n_robots=R, n_packages=m["P"], seed=m["seed"])
+    state = env.reset()
+    for s in range(60):
+        pp = _tracker_of(env)
+        if s % 6 == 0:
+            for i in range(R):
+                assert np.array_equal(_bits(mdb.idq.convert_state(state, pp, i)), _bits(z[f"{n}_obs6"][s, i])), (s, i)
+                got = mdb.qmix_helper.generate_vector_features(state, pp, i, m["T"], R - 1, 5)
+                assert np.array_equal(_bits(got), _bits(z[f"{n}_qvec"][s, i])), (s, i)
+            assert np.array_equal(_bits(mdb.idq.convert_global_state_to_tensor(state, pp, (7, 10, 10))), _bits(z[f"{n}_g7"][s]))
+            assert np.array_equal(_bits(mdb.qmix_helper.convert_global_state(state, pp, m["T"], 10, 20)[1]), _bits(z[f"{n}_qgvec"][s]))
+        a = z[f"{n}_actions"][s]
+        acts = [("DLRSU"[x % 5], str(x // 5)) for x in a]
+        nxt, r, done, _ = env.step(acts)
+        assert mdb.idq.reward_shaping(state, nxt, acts, pp, R) == list(z[f"{n}_shape_str"][s]), s
+        assert mdb.idq.reward_shaping(state, nxt, [(mv, int(o)) for mv, o in acts], pp, R) == list(z[f"{n}_shape_int"][s]), s
+        if done:
+            nxt = env.reset()
+        state = nxt
+    with pytest.raises(TypeError):
+        mdb.qmix_helper.generate_vector_features(state, pp, 0, 100)  # QMIX/helper.py:70 has no defaults
+    with pytest.raises(ValueError):
+        mdb.idq.convert_global_state_to_tensor(state, pp, (7, 12, 12))
