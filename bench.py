@@ -53,6 +53,13 @@ WORKLOADS = {
                MP=100, envs=16384, feat=True),
     "c5": dict(desc="C5: map5 20x20, 32 robots (full warp), 500 packages, T=1000, K_o=31, K_p=5",
                maps=["map5.txt"], R=32, P=500, T=1000, K_o=31, K_p=5, MR=100, MP=100, envs=32768, feat=True),
+    # callers either side of the path; secondary lines kept under profiles/
+    "greedy": dict(desc="f2: batched GreedyAgents on the all-pairs BFS table + env step (2 launches per step); README evaluation shape: "
+                        "map1, 5 robots, 100 packages, T=1000", maps=["map1.txt"], R=5, P=100, T=1000, K_o=4, K_p=5, MR=100, MP=100,
+                   envs=65536, feat=False, kind="greedy"),
+    "idq": dict(desc="f3: one IDQ trainer iteration: step + per-agent reward_shaping, then convert_state x R + legacy 7-channel global "
+                     "tensor (2 launches per step); map1, 5 robots, 50 packages, T=500", maps=["map1.txt"], R=5, P=50, T=500, K_o=4,
+                K_p=5, MR=100, MP=100, envs=65536, feat=False, kind="idq"),
 }
 WL = dict(WORKLOADS["c3"])
 
@@ -77,9 +84,31 @@ def _cpu_worker(args):
     ve.reset()
     rs = np.random.RandomState(seed)
     acts = rs.randint(0, 15, size=(n_steps, n_envs, R))
+    kind = wl.get("kind", "path")
+    if kind == "greedy":
+        from oracle.greedy_oracle import GreedyOracle
+        agents = [GreedyOracle(e) for e in ve.envs]
+    elif kind == "idq":
+        from oracle import alt_oracle as alt
     t0 = time.perf_counter()
     for s in range(n_steps):
-        if wl["feat"]:
+        if kind == "greedy":  # f2: GreedyAgents.get_actions + env.step per env
+            for n, e in enumerate(ve.envs):
+                _, d = e.step(agents[n].get_actions())
+                if d:
+                    e.reset()
+                    agents[n] = GreedyOracle(e)
+        elif kind == "idq":  # f3: one IDQ trainer iteration per env
+            for n, e in enumerate(ve.envs):
+                before = e.snapshot()
+                _, d = e.step(acts[s, n])
+                alt.idq_reward_shaping(e, before, e.snapshot(), acts[s, n], True)
+                if d:
+                    e.reset()
+                snap = e.snapshot()
+                [alt.idq_observation(e, snap, i) for i in range(R)]
+                alt.legacy_global_tensor(e, snap)
+        elif wl["feat"]:
             orc.mappo_rollout_step(ve, acts[s], wl["K_o"], wl["K_p"], wl["MR"], wl["MP"])
         else:  # C2: step + shaped reward, auto-reset, no featurisation
             for n, e in enumerate(ve.envs):
@@ -204,8 +233,24 @@ def gpu_arm(args):
     out = (torch.empty(N, dtype=torch.float64, device=dev), torch.empty(N, dtype=torch.float32, device=dev),
            torch.empty(N, dtype=torch.uint8, device=dev))
 
+    kind = wl.get("kind", "path")
+    launches_per_step = 1
+    if kind == "greedy":
+        launches_per_step = 2
+        g_act = torch.empty((N, R), dtype=torch.uint8, device=dev)
+    elif kind == "idq":
+        launches_per_step = 2
+        idq_out = (out[0], torch.empty((N, R), dtype=torch.float64, device=dev), out[2])
+        alt_out = (torch.empty((N, R, 6, b.rows_out, b.cols_out), dtype=torch.float32, device=dev),
+                   torch.empty((N, 7, b.rows_out, b.cols_out), dtype=torch.float32, device=dev))
+
     def one_step(a):
-        if feat_on:
+        if kind == "greedy":
+            b.step(b.greedy_actions(out=g_act), auto_reset=True, out=out)
+        elif kind == "idq":
+            b.step_idq(a, auto_reset=True, ops_as_int=True, out=idq_out)
+            b.featurize_alt(out=alt_out)
+        elif feat_on:
             b.step_featurize(a, auto_reset=True, out=out, feat_out=feat)
         else:
             b.step(a, auto_reset=True, out=out)
@@ -275,7 +320,13 @@ def gpu_arm(args):
     h_done = torch.empty(N, dtype=torch.uint8).pin_memory()
 
     def api_step(a):
-        if feat_on:
+        if kind == "greedy":
+            _, shaped, done = ve.batch.step(ve.batch.greedy_actions(out=g_act), auto_reset=True, out=out)
+        elif kind == "idq":
+            _, agent, done = ve.batch.step_idq(a, auto_reset=True, ops_as_int=True, out=idq_out)
+            ve.batch.featurize_alt(out=alt_out)
+            shaped = out[1]
+        elif feat_on:
             _, shaped, done, *_ = ve.rollout_step(a, out=out, feat_out=feat)
         else:
             _, shaped, done = ve.batch.step(a, auto_reset=True, out=out)
@@ -310,10 +361,16 @@ def gpu_arm(args):
     # algorithmic bytes per env-step, SURVEY.md section 8(d): feature tensors + reward/done/actions, or
     # the state model for the step-only workload
     Bytes = b.bytes_per_env_step if feat_on else R * 9 + P * 10 + 37
+    if kind == "idq":  # obs6 + 7-channel tensor + per-agent f64 rewards + reward/done/actions
+        Bytes = 4 * (R * 6 + 7) * b.rows_out * b.cols_out + 8 * R + 8 + 1 + R
     mean_launch_ms = statistics.mean(per_launch)
     achieved = Bytes * N / (mean_launch_ms * 1e-3) / 1e9
     value = world * N * K / (ms_total_max * 1e-3)
     kern = "mdx_env_kernel<3,...> (fused step+featurise)" if feat_on else "mdx_env_kernel<1,...> (step+rewards)"
+    if kind == "greedy":
+        kern = "mdx_greedy_kernel + mdx_env_kernel<1,...> (both launches of a step)"
+    elif kind == "idq":
+        kern = "mdx_env_kernel<1,...> + mdx_alt_featurize_kernel (both launches of a step)"
     line = {
         "metric": "env-steps/sec (map1, 5 robots, 50 pkgs, T=500) with obs+state+vector featurisation" if args.workload == "c3"
                   else f"env-steps/sec ({args.workload})",
@@ -332,7 +389,7 @@ def gpu_arm(args):
         "e2e": {"value": world * N * Ke / (e2e_ms * 1e-3), "unit": "env-steps/s", "steps": Ke,
                 "h2d_bytes_per_step": N * R, "d2h_bytes_per_step": N * 5,
                 "note": "actions from pinned host memory, shaped reward + done read back every step; features stay in HBM"},
-        "gpu_launches": K + 1,
+        "gpu_launches": K * launches_per_step + 1,
         "clocks": clocks,
         "episode_stats": dict(zip(mdb.STAT_NAMES, stats_h)), "starved_envs": starved,
     }

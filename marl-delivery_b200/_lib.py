@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmdx.so")
+LIB_PATH = os.environ.get("MDX_LIB_PATH") or os.path.join(_HERE, "csrc", "libmdx.so")  # override: A/B builds of the same library
 
 MDX_OK, MDX_E_INVALID, MDX_E_CUDA, MDX_E_STARVED, MDX_E_NOMEM = 0, -1, -2, -3, -4
 MDX_F_AUTO_RESET = 1

@@ -182,6 +182,7 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   if (const char* s = getenv("MDX_GENERIC")) e->force_generic = atoi(s);
   if (const char* s = getenv("MDX_LPE")) e->lpe_override = atoi(s);
   if (const char* s = getenv("MDX_NOFIX")) e->no_fixed = atoi(s);
+  if (const char* s = getenv("MDX_CARVEOUT")) e->carveout = atoi(s);
 
   // ---- maps
   int Ho = 0, Wo = 0;

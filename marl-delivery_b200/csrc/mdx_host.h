@@ -106,6 +106,7 @@ struct mdx_env {
   uint32_t* d_gfree = nullptr;     // [n][gfree_words] packages_free bits over the agent's own list
   int gfree_words = 0;
   int wpb_override = 0;
+  int carveout = -1;      // MDX_CARVEOUT=0..100: preferred shared-memory carve-out of the env kernels (-1 = driver default)
   size_t smem_configured[96] = {};
   int no_fixed = 0;       // MDX_NOFIX=1: never use the shape-specialised instantiation
   int lpe_override = 0;   // MDX_LPE=8|16|32: minimum lanes per environment (experiments / tests)

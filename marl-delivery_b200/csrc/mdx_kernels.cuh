@@ -31,8 +31,14 @@
 namespace mdx {
 
 #define MDX_NONE32 0xffffffffu
+// Resident CTAs per SM the featurising variants are compiled for (register cap 65536 / 128 / n).  Measured on B200
+// (C3, 65 536 envs): 7 CTAs (72 regs) 251.6 M env-steps/s, 8 (64 regs) 268.4 M, 9 (56 regs, 4 B spill) 279.3 M, 10 (48 regs)
+// 275.5 M -- the kernel is bound by dependent-instruction latency, so more resident warps win until spills bite.
 #ifndef MDX_FEAT_BLOCKS
-#define MDX_FEAT_BLOCKS 7  // resident CTAs per SM the featurising variants are compiled for (register cap 65536 / 128 / n)
+#define MDX_FEAT_BLOCKS 7  // generic (run-time shape) variants
+#endif
+#ifndef MDX_FIX_BLOCKS
+#define MDX_FIX_BLOCKS 9   // shape-specialised variant (kFix = 1)
 #endif
 constexpr int kLutBytes = 256;  // block-shared nibble -> float4 table at the start of dynamic smem
 
@@ -839,7 +845,7 @@ __device__ __forceinline__ void specialise(KParams& p) {
 }
 
 template <int kMode, int LPE, int kS, bool kSmall, int kFix>
-__global__ void __launch_bounds__(128, (kMode & 2) ? MDX_FEAT_BLOCKS : 8) mdx_env_kernel(const __grid_constant__ KParams pg) {
+__global__ void __launch_bounds__(128, (kMode & 2) ? (kFix ? MDX_FIX_BLOCKS : MDX_FEAT_BLOCKS) : 8) mdx_env_kernel(const __grid_constant__ KParams pg) {
   KParams p = pg;
   specialise<kFix>(p);
   extern __shared__ __align__(16) unsigned char smem_raw[];

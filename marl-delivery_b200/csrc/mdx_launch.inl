@@ -21,6 +21,8 @@ int launch_variant(mdx_env* e, const KParams& kp, cudaStream_t st) {
   if (smem > e->smem_configured[slot]) {
     CU(cudaFuncSetAttribute(mdx_env_kernel<kMode, LPE, kS, kSmall, kFix>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)std::max<size_t>(smem, 48 * 1024)));
+    if (e->carveout >= 0)
+      CU(cudaFuncSetAttribute(mdx_env_kernel<kMode, LPE, kS, kSmall, kFix>, cudaFuncAttributePreferredSharedMemoryCarveout, e->carveout));
     e->smem_configured[slot] = smem;
   }
   KParams q = kp;
