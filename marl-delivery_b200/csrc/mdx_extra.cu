@@ -198,7 +198,9 @@ __global__ void __launch_bounds__(128) mdx_greedy_kernel(const __grid_constant__
 // every load/store is coalesced across envs.  float32, no FMA contraction (-fmad=false), the reference's
 // order of operations.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) mdx_gae_kernel(const float* __restrict__ rew, const float* __restrict__ val,
+constexpr int kGaeChunk = 16;  // time steps whose loads are issued together before the dependent recurrence runs
+
+__global__ void __launch_bounds__(128) mdx_gae_kernel(const float* __restrict__ rew, const float* __restrict__ val,
                                                       const uint8_t* __restrict__ done, const float* __restrict__ last_value,
                                                       int T, int N, float gamma, float gl, float* __restrict__ adv,
                                                       float* __restrict__ ret) {
@@ -206,17 +208,34 @@ __global__ void __launch_bounds__(256) mdx_gae_kernel(const float* __restrict__ 
   if (n >= N) return;
   float next_v = last_value[n];
   float last = 0.0f;
-  for (int t = T - 1; t >= 0; --t) {
-    const size_t k = (size_t)t * N + n;
-    const float nnt = __fsub_rn(1.0f, done[k] ? 1.0f : 0.0f);
-    const float v = val[k];
-    // delta = r + GAMMA * next_values * next_non_terminal - v
-    const float delta = __fsub_rn(__fadd_rn(rew[k], __fmul_rn(__fmul_rn(gamma, next_v), nnt)), v);
-    // last = delta + GAMMA * GAE_LAMBDA * next_non_terminal * last   (GAMMA * GAE_LAMBDA is one Python float)
-    last = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nnt), last));
-    adv[k] = last;
-    ret[k] = __fadd_rn(last, v);
-    next_v = v;
+  for (int t1 = T; t1 > 0; t1 -= kGaeChunk) {
+    float r[kGaeChunk], v[kGaeChunk];
+    uint8_t d[kGaeChunk];
+#pragma unroll
+    for (int u = 0; u < kGaeChunk; ++u) {  // independent, coalesced loads: the recurrence below never waits on DRAM
+      const int t = t1 - 1 - u;
+      if (t >= 0) {
+        const size_t k = (size_t)t * N + n;
+        r[u] = __ldcs(rew + k);
+        v[u] = __ldcs(val + k);
+        d[u] = __ldcs(done + k);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGaeChunk; ++u) {
+      const int t = t1 - 1 - u;
+      if (t >= 0) {
+        const size_t k = (size_t)t * N + n;
+        const float nnt = __fsub_rn(1.0f, d[u] ? 1.0f : 0.0f);
+        // delta = r + GAMMA * next_values * next_non_terminal - v
+        const float delta = __fsub_rn(__fadd_rn(r[u], __fmul_rn(__fmul_rn(gamma, next_v), nnt)), v[u]);
+        // last = delta + GAMMA * GAE_LAMBDA * next_non_terminal * last   (GAMMA * GAE_LAMBDA is one Python float)
+        last = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nnt), last));
+        __stcs(adv + k, last);
+        __stcs(ret + k, __fadd_rn(last, v[u]));
+        next_v = v[u];
+      }
+    }
   }
 }
 
@@ -338,7 +357,7 @@ int32_t mdx_gae(const float* d_rewards, const float* d_values, const uint8_t* d_
   if (T == 0 || N == 0) return MDX_OK;
   // a Python float scalar times a float32 tensor is evaluated in float32 with the scalar rounded once
   const float g32 = (float)gamma, gl32 = (float)(gamma * gae_lambda);
-  mdx_gae_kernel<<<(unsigned)((N + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_rewards, d_values, d_dones, d_last_value,
+  mdx_gae_kernel<<<(unsigned)((N + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(d_rewards, d_values, d_dones, d_last_value,
                                                                                            T, N, g32, gl32, d_advantages, d_returns);
   CU(cudaGetLastError());
   return MDX_OK;

@@ -160,8 +160,16 @@ __device__ __forceinline__ void flush_seg(float* gdst, const float* stage, int o
 #pragma unroll 1
   for (int i = sl; i < live; i += LPE) __stcs(g4 + i, s4[i]);
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  int i = live + sl;
 #pragma unroll 1
-  for (int i = live + sl; i < body; i += LPE) __stcs(g4 + i, z4);
+  for (; i + 3 * LPE < body; i += 4 * LPE) {  // four independent stores per trip: the zero tail is most of a gvec row
+    __stcs(g4 + i, z4);
+    __stcs(g4 + i + LPE, z4);
+    __stcs(g4 + i + 2 * LPE, z4);
+    __stcs(g4 + i + 3 * LPE, z4);
+  }
+#pragma unroll 1
+  for (; i < body; i += LPE) __stcs(g4 + i, z4);
   const int done = head + (body << 2);
   if (sl < n_total - done) __stcs(gdst + done + sl, done + sl < n_data ? s[done + sl] : 0.0f);
 }
@@ -384,7 +392,7 @@ __device__ __forceinline__ void decode_action(int a, int& mv, int& op) {
 //          = 0: generic flat loops over per-robot bit planes (any H*W).
 //   kSmall:     P <= 64, so a lane owns at most 64/LPE waiting-list entries and keeps their selection
 //               keys in registers.
-template <int LPE, int kS, bool kSmall>
+template <int LPE, int kS, bool kSmall, int kFix>
 __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, const Grp<LPE>& g, const float4* lut,
                                               const MapDev& map, int row, int t, int cell, int carry) {
   constexpr int EPL = 64 / LPE;
@@ -648,7 +656,96 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
       //   (remaining deadline * nranks + rank of the float64 distance key) << wbits | list index;
       // the winner of round q for the ii-th robot of a pass is remembered by lane ii*Ksel+q, which then
       // writes that row.
-      if (nsel > 0 && lane_sel) {
+      if (kFix == 1 && nsel > 0) {
+        // Shape-specialised selection (5 robots, 5 slots, one pass): the rounds of all five robots run
+        // interleaved -- five independent group reductions in flight per round instead of 25 dependent ones --
+        // and a lane holds ONE key per robot while the waiting list fits the group (nw <= LPE).
+        constexpr int NR = 5;
+        int bi[NR];
+#pragma unroll
+        for (int ii = 0; ii < NR; ++ii) {
+          const uint32_t rci = w.rrc[ii];
+          bi[ii] = (Hm1 - (int)(rci >> 8)) * NC + (Wm1 - (int)(rci & 255u));
+        }
+        uint32_t mysel = 0;
+        if (nw <= LPE) {
+          uint32_t key[NR];
+          const bool has = sl < nw;
+          int off = 0;
+          uint32_t dlk = 0;
+          if (has) {
+            const uint32_t rc = w.wrc[sl];
+            off = (int)(rc >> 8) * NC + (int)(rc & 255u);
+            dlk = (uint32_t)w.wdl[sl] * (uint32_t)p.nranks_max;
+          }
+#pragma unroll
+          for (int ii = 0; ii < NR; ++ii)
+            key[ii] = has ? (((dlk + (uint32_t)__ldg(map.rank + off + bi[ii])) << p.key_wbits) | (uint32_t)sl) : MDX_NONE32;
+#pragma unroll 1
+          for (int q = 0; q < nsel; ++q) {
+            uint32_t b[NR];
+#pragma unroll
+            for (int ii = 0; ii < NR; ++ii) b[ii] = g.rmin(key[ii]);
+#pragma unroll
+            for (int ii = 0; ii < NR; ++ii)
+              if (key[ii] == b[ii]) key[ii] = MDX_NONE32;  // keys are unique: exactly one entry is retired
+            uint32_t pick = b[0];
+#pragma unroll
+            for (int ii = 1; ii < NR; ++ii)
+              if (sel_ii == ii) pick = b[ii];
+            if (sel_q == q) mysel = pick & wmask;
+          }
+        } else {
+          uint32_t k0[NR], k1[NR];
+          const bool has1 = sl + LPE < nw;  // nw > LPE: every lane owns entry sl
+          const uint32_t rc0 = w.wrc[sl];
+          const int off0 = (int)(rc0 >> 8) * NC + (int)(rc0 & 255u);
+          const uint32_t dl0k = (uint32_t)w.wdl[sl] * (uint32_t)p.nranks_max;
+          int off1 = 0;
+          uint32_t dl1k = 0;
+          if (has1) {
+            const uint32_t rc1 = w.wrc[sl + LPE];
+            off1 = (int)(rc1 >> 8) * NC + (int)(rc1 & 255u);
+            dl1k = (uint32_t)w.wdl[sl + LPE] * (uint32_t)p.nranks_max;
+          }
+#pragma unroll
+          for (int ii = 0; ii < NR; ++ii) {
+            k0[ii] = ((dl0k + (uint32_t)__ldg(map.rank + off0 + bi[ii])) << p.key_wbits) | (uint32_t)sl;
+            k1[ii] = has1 ? (((dl1k + (uint32_t)__ldg(map.rank + off1 + bi[ii])) << p.key_wbits) | (uint32_t)(sl + LPE)) : MDX_NONE32;
+          }
+#pragma unroll 1
+          for (int q = 0; q < nsel; ++q) {
+            uint32_t b[NR];
+#pragma unroll
+            for (int ii = 0; ii < NR; ++ii) b[ii] = g.rmin(min(k0[ii], k1[ii]));
+#pragma unroll
+            for (int ii = 0; ii < NR; ++ii) {
+              if (k0[ii] == b[ii]) k0[ii] = MDX_NONE32;
+              if (k1[ii] == b[ii]) k1[ii] = MDX_NONE32;
+            }
+            uint32_t pick = b[0];
+#pragma unroll
+            for (int ii = 1; ii < NR; ++ii)
+              if (sel_ii == ii) pick = b[ii];
+            if (sel_q == q) mysel = pick & wmask;
+          }
+        }
+        if (sel_ii < NR && sel_q < nsel) {
+          const uint32_t rci = w.rrc[sel_ii];
+          const int ri = (int)(rci >> 8), ci = (int)(rci & 255u);
+          const int k = (int)mysel;
+          const int j = w.wlist[k];
+          const uint32_t rc = w.wrc[k];
+          const uint32_t tc_ = w.target[j];
+          const int tr = (int)__umulhi(tc_, p.mul_wout), tcol = (int)tc_ - tr * Wo;
+          float* o = chunk + sel_ii * D + 6 + K_o * 5 + sel_q * 5;
+          o[0] = __ldg(qr + ((int)(rc >> 8) - ri + Hm1));
+          o[1] = __ldg(qc + ((int)(rc & 255u) - ci + Wm1));
+          o[2] = __ldg(qr + (tr - ri + Hm1));
+          o[3] = __ldg(qc + (tcol - ci + Wm1));
+          o[4] = tnorm(p, (int)w.wdl[k]);
+        }
+      } else if (nsel > 0 && lane_sel) {
 #pragma unroll 1
         for (int ib = i0; ib < i0 + nrows; ib += RP) {
           const int npass = min(RP, i0 + nrows - ib);
@@ -1049,7 +1146,7 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? (kFix ? MDX_FIX_BLOCKS : MD
     }
   }
 
-  if (kMode & 2) featurize_env<LPE, kS, kSmall>(p, w, g, lut, map, widx, t, cell, carry);
+  if (kMode & 2) featurize_env<LPE, kS, kSmall, kFix>(p, w, g, lut, map, widx, t, cell, carry);
 }
 
 }  // namespace mdx
