@@ -794,6 +794,42 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
             o[4] = tnorm(p, (int)w.wdl[k]);
           }
         }
+      } else if (nsel > 0 && 2 * nsel >= nw) {
+        // Most (or all) of the waiting list is selected -- the K = 100 defaults of generate_vector_features
+        // (MAPPO/helper.py:70): rank every entry by counting the smaller keys (O(nw) per entry, no rounds) and let
+        // the entry's owner write its row at that position.
+#pragma unroll 1
+        for (int i = i0; i < i0 + nrows; ++i) {
+          const uint32_t rci = w.rrc[i];
+          const int ri = (int)(rci >> 8), ci = (int)(rci & 255u);
+#pragma unroll 1
+          for (int k = sl; k < nw; k += LPE) {
+            const uint32_t rc = w.wrc[k];
+            const uint32_t rk = __ldg(map.rank + ((int)(rc >> 8) - ri + Hm1) * NC + ((int)(rc & 255u) - ci + Wm1));
+            w.wkey[k] = (((uint32_t)w.wdl[k] * (uint32_t)p.nranks_max + rk) << p.key_wbits) | (uint32_t)k;
+          }
+          g.sync();
+#pragma unroll 1
+          for (int k = sl; k < nw; k += LPE) {
+            const uint32_t key = w.wkey[k];
+            int pos = 0;
+#pragma unroll 4
+            for (int m = 0; m < nw; ++m) pos += (w.wkey[m] < key) ? 1 : 0;  // same address for all lanes: broadcast
+            if (pos < nsel) {
+              const int j = w.wlist[k];
+              const uint32_t rc = w.wrc[k];
+              const uint32_t tc_ = w.target[j];
+              const int tr = (int)__umulhi(tc_, p.mul_wout), tcol = (int)tc_ - tr * Wo;
+              float* o = chunk + (i - i0) * D + 6 + K_o * 5 + pos * 5;
+              o[0] = __ldg(qr + ((int)(rc >> 8) - ri + Hm1));
+              o[1] = __ldg(qc + ((int)(rc & 255u) - ci + Wm1));
+              o[2] = __ldg(qr + (tr - ri + Hm1));
+              o[3] = __ldg(qc + (tcol - ci + Wm1));
+              o[4] = tnorm(p, (int)w.wdl[k]);
+            }
+          }
+          g.sync();
+        }
       } else if (nsel > 0) {
 #pragma unroll 1
         for (int i = i0; i < i0 + nrows; ++i) {
