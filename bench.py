@@ -230,8 +230,9 @@ def gpu_arm(args):
     n_act = min(K + W, 64)  # distinct pre-generated action batches, cycled
     actions = torch.randint(0, 15, (n_act, N, R), dtype=torch.uint8, device=dev, generator=gen)
     feat = b.alloc_features(N) if feat_on else None
-    out = (torch.empty(N, dtype=torch.float64, device=dev), torch.empty(N, dtype=torch.float32, device=dev),
-           torch.empty(N, dtype=torch.uint8, device=dev))
+    # shaped reward (f32) and done (u8) share one allocation so that the end-to-end arm reads both back with ONE copy
+    sd_dev = torch.empty(5 * N, dtype=torch.uint8, device=dev)
+    out = (torch.empty(N, dtype=torch.float64, device=dev), sd_dev[:4 * N].view(torch.float32), sd_dev[4 * N:])
 
     kind = wl.get("kind", "path")
     launches_per_step = 1
@@ -316,8 +317,7 @@ def gpu_arm(args):
     prefetch_for(Ke + 3)
     h_act = torch.randint(0, 15, (min(Ke, 16), N, R), dtype=torch.uint8).pin_memory()
     d_act = torch.empty((N, R), dtype=torch.uint8, device=dev)
-    h_shaped = torch.empty(N, dtype=torch.float32).pin_memory()
-    h_done = torch.empty(N, dtype=torch.uint8).pin_memory()
+    h_sd = torch.empty(5 * N, dtype=torch.uint8).pin_memory()  # [shaped f32 | done u8], one D2H copy per step
 
     def api_step(a):
         if kind == "greedy":
@@ -340,9 +340,8 @@ def gpu_arm(args):
     e0.record()
     for s in range(Ke):
         d_act.copy_(h_act[s % len(h_act)], non_blocking=True)
-        shaped, done = api_step(d_act)
-        h_shaped.copy_(shaped, non_blocking=True)
-        h_done.copy_(done, non_blocking=True)
+        api_step(d_act)
+        h_sd.copy_(sd_dev, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads reward/done before choosing actions
     e1.record()
     barrier()

@@ -637,8 +637,9 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
             okey = ((uint32_t)__ldg(map.rank + (dr + Hm1) * NC + (dc + Wm1)) << 5) | (uint32_t)gj;
           }
           int pos = 0;
-#pragma unroll 1
-          for (int k = 0; k < R; ++k) pos += (g.shfl(okey, gi * R + k) < okey) ? 1 : 0;
+          const int kbase = gi * R;
+#pragma unroll 8
+          for (int k = 0; k < R; ++k) pos += (g.shfl(okey, kbase + k) < okey) ? 1 : 0;
           const float cf_j = g.shfl(cflag, gj);
           const float otr_j = g.shfl(ot_r, gj), otc_j = g.shfl(ot_c, gj);
           if (valid && pos < K_o) {
@@ -829,6 +830,58 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
             }
           }
           g.sync();
+        }
+      } else if (nsel > 0 && Ksel <= 5) {
+        // Few slots, long waiting list (C4 / C5): while it computes the keys of its entries, every lane keeps its
+        // own five smallest in sorted registers; a round is then one group arg-min over the lanes' heads and a
+        // register shift in the winning lane -- no key array in shared memory, no rescans.
+#pragma unroll 1
+        for (int i = i0; i < i0 + nrows; ++i) {
+          const uint32_t rci = w.rrc[i];
+          const int bi = (Hm1 - (int)(rci >> 8)) * NC + (Wm1 - (int)(rci & 255u));
+          uint16_t* selp = w.sel + (i - i0) * Ksel;
+          uint32_t a0 = MDX_NONE32, a1 = MDX_NONE32, a2 = MDX_NONE32, a3 = MDX_NONE32, a4 = MDX_NONE32;
+#pragma unroll 2
+          for (int k = sl; k < nw; k += LPE) {
+            const uint32_t rc = w.wrc[k];
+            const uint32_t rk = __ldg(map.rank + ((int)(rc >> 8) * NC + (int)(rc & 255u) + bi));
+            uint32_t x = (((uint32_t)w.wdl[k] * (uint32_t)p.nranks_max + rk) << p.key_wbits) | (uint32_t)k;
+            uint32_t lo;
+            lo = min(a0, x), x = max(a0, x), a0 = lo;
+            lo = min(a1, x), x = max(a1, x), a1 = lo;
+            lo = min(a2, x), x = max(a2, x), a2 = lo;
+            lo = min(a3, x), x = max(a3, x), a3 = lo;
+            a4 = min(a4, x);
+          }
+#pragma unroll 1
+          for (int q = 0; q < nsel; ++q) {
+            const uint32_t best = g.rmin(a0);
+            if (a0 == best) {  // exactly one lane: keys are unique
+              selp[q] = (uint16_t)(best & wmask);
+              a0 = a1, a1 = a2, a2 = a3, a3 = a4, a4 = MDX_NONE32;
+            }
+          }
+        }
+        g.sync();
+        const int nslot = nrows * Ksel;
+#pragma unroll 1
+        for (int x = sl; x < nslot; x += LPE) {
+          const int ii = (int)__umulhi((uint32_t)x, p.mul_ksel), q = x - ii * Ksel;
+          if (q < nsel) {
+            const uint32_t rci = w.rrc[i0 + ii];
+            const int ri = (int)(rci >> 8), ci = (int)(rci & 255u);
+            const int k = w.sel[ii * Ksel + q];
+            const int j = w.wlist[k];
+            const uint32_t rc = w.wrc[k];
+            const uint32_t tc_ = w.target[j];
+            const int tr = (int)__umulhi(tc_, p.mul_wout), tcol = (int)tc_ - tr * Wo;
+            float* o = chunk + ii * D + 6 + K_o * 5 + q * 5;
+            o[0] = __ldg(qr + ((int)(rc >> 8) - ri + Hm1));
+            o[1] = __ldg(qc + ((int)(rc & 255u) - ci + Wm1));
+            o[2] = __ldg(qr + (tr - ri + Hm1));
+            o[3] = __ldg(qc + (tcol - ci + Wm1));
+            o[4] = tnorm(p, (int)w.wdl[k]);
+          }
         }
       } else if (nsel > 0) {
 #pragma unroll 1
