@@ -42,8 +42,7 @@ __global__ void __launch_bounds__(128) mdx_alt_featurize_kernel(const __grid_con
   MapDev map = p.map0;
   if (p.env_map) map = p.maps[__ldg(p.env_map + env)];
   const int t = p.t[env];
-  const int slot = p.ep[env] % p.E;
-  const uint16_t* S = p.sched + ((size_t)slot * p.n_envs + env) * 4 * p.Pp8;
+  const uint16_t* S = p.cur + (size_t)env * 4 * p.Pp8;
   const uint16_t *G = S + p.Pp8, *T0 = S + 2 * p.Pp8, *DL = S + 3 * p.Pp8;
   const uint8_t* status = p.status + (size_t)env * p.Pp16;
   const bool active = lane < R;

@@ -141,6 +141,7 @@ int32_t mdx_destroy(mdx_env* e) {
   cudaFree(e->d_robots);
   cudaFree(e->d_status);
   cudaFree(e->d_sched);
+  cudaFree(e->d_cur);
   cudaFree(e->d_sched_robots);
   cudaFree(e->d_counters);
   cudaFree(e->d_env_map);
@@ -381,6 +382,8 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   CUX(cudaMalloc(&raw->d_robots, sizeof(uint32_t) * n * e->R));
   CUX(cudaMalloc(&raw->d_status, n * b.Pp16));
   CUX(cudaMalloc(&raw->d_sched, sizeof(uint16_t) * (size_t)e->E * n * 4 * b.Pp8));
+  CUX(cudaMalloc(&raw->d_cur, sizeof(uint16_t) * n * 4 * b.Pp8));
+  CUX(cudaMemset(raw->d_cur, 0, sizeof(uint16_t) * n * 4 * b.Pp8));
   CUX(cudaMalloc(&raw->d_sched_robots, sizeof(uint16_t) * (size_t)e->E * n * 32));
   CUX(cudaMalloc(&raw->d_counters, sizeof(uint32_t) * n * 8));
   CUX(cudaMalloc(&raw->d_env_map, sizeof(int32_t) * n));
@@ -414,6 +417,7 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   b.robots = raw->d_robots;
   b.status = raw->d_status;
   b.sched = raw->d_sched;
+  b.cur = raw->d_cur;
   b.sched_robots = raw->d_sched_robots;
   b.counters = raw->d_counters;
   b.env_map = cfg->n_maps > 1 ? raw->d_env_map : nullptr;
@@ -647,8 +651,7 @@ int32_t mdx_get_state(mdx_env* e, int32_t id, mdx_state_view* out, void* stream)
   CU(cudaMemcpy(&total, e->d_total + id, sizeof(total), cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(rob.data(), e->d_robots + (size_t)id * e->R, sizeof(uint32_t) * e->R, cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(status.data(), e->d_status + (size_t)id * b.Pp16, (size_t)b.Pp16, cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(sched.data(), e->d_sched + ((size_t)(ep % e->E) * e->n + id) * 4 * b.Pp8, sizeof(uint16_t) * 4 * b.Pp8,
-                cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(sched.data(), e->d_cur + (size_t)id * 4 * b.Pp8, sizeof(uint16_t) * 4 * b.Pp8, cudaMemcpyDeviceToHost));
   out->t = t;
   out->episode = ep;
   out->map_id = e->env_map[(size_t)id];
@@ -710,16 +713,13 @@ int32_t mdx_set_state(mdx_env* e, int32_t id, const mdx_state_view* in, void* st
     status[(size_t)j] = (uint8_t)in->pkg_status[j];
   }
   CU(cudaStreamSynchronize(st));
-  int32_t ep = 0;
-  CU(cudaMemcpy(&ep, e->d_ep + id, sizeof(ep), cudaMemcpyDeviceToHost));
   const int32_t t = in->t;
   const double total = in->total_reward;
   CU(cudaMemcpy(e->d_t + id, &t, sizeof(t), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(e->d_total + id, &total, sizeof(total), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(e->d_robots + (size_t)id * e->R, rob.data(), sizeof(uint32_t) * e->R, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(e->d_status + (size_t)id * b.Pp16, status.data(), (size_t)b.Pp16, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(e->d_sched + ((size_t)(ep % e->E) * e->n + id) * 4 * b.Pp8, sched.data(), sizeof(uint16_t) * 4 * b.Pp8,
-                cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(e->d_cur + (size_t)id * 4 * b.Pp8, sched.data(), sizeof(uint16_t) * 4 * b.Pp8, cudaMemcpyHostToDevice));
   return MDX_OK;
 }
 

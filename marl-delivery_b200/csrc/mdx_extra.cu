@@ -92,8 +92,7 @@ __global__ void __launch_bounds__(128) mdx_greedy_kernel(const __grid_constant__
   if (p.env_map) map = p.maps[__ldg(p.env_map + env)];
   const int R = p.R, P = p.P, Wo = p.W_out, HW = p.HW;
   const int t = p.t[env];
-  const int slot = p.ep[env] % p.E;
-  const uint16_t* S = p.sched + ((size_t)slot * p.n_envs + env) * 4 * p.Pp8;  // start cells
+  const uint16_t* S = p.cur + (size_t)env * 4 * p.Pp8;  // start cells of the current episode
   const uint16_t* G = S + p.Pp8;                                                // target cells
   const uint16_t* T0 = S + 2 * p.Pp8;                                           // start times
   int n0 = 0, cnt = 0;
@@ -269,6 +268,7 @@ std::vector<Seg> device_segments(mdx_env* e) {
       {e->d_robots, sizeof(uint32_t) * n * e->R},
       {e->d_status, n * b.Pp16},
       {e->d_sched, sizeof(uint16_t) * (size_t)e->E * n * 4 * b.Pp8},
+      {e->d_cur, sizeof(uint16_t) * n * 4 * b.Pp8},
       {e->d_sched_robots, sizeof(uint16_t) * (size_t)e->E * n * 32},
       {e->d_counters, sizeof(uint32_t) * n * 8},
   };

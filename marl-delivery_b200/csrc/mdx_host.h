@@ -91,6 +91,7 @@ struct mdx_env {
   uint32_t* d_robots = nullptr;
   uint8_t* d_status = nullptr;
   uint16_t* d_sched = nullptr;
+  uint16_t* d_cur = nullptr;
   uint16_t* d_sched_robots = nullptr;
   uint32_t* d_counters = nullptr;
   int32_t* d_env_map = nullptr;

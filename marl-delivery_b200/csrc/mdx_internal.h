@@ -96,7 +96,9 @@ struct KParams {
   double* total_reward;
   uint32_t* robots;        // [n_envs][R]  cell | carry << 16
   uint8_t* status;         // [n_envs][Pp16]
-  uint16_t* sched;         // [E][n_envs][4][Pp8]
+  uint16_t* sched;         // [E][n_envs][4][Pp8]   ring of pre-sampled episodes: read only when an env resets
+  uint16_t* cur;           // [n_envs][4][Pp8]      schedule of the env's CURRENT episode: what every step reads, at an
+                           //                       address that does not depend on a loaded value (no dependent DRAM trip)
   uint16_t* sched_robots;  // [E][n_envs][32]
   uint32_t* counters;      // [n_envs][8]
   const int32_t* env_map;  // [n_envs]

@@ -109,13 +109,30 @@ __device__ __forceinline__ float tnorm(const KParams& p, int k) {
   return p.T > 0 ? tnorm_slow(k, p.T) : 0.0f;
 }
 
+// Schedule of the env's current episode -> shared memory (one LDG.128 per lane for 50 packages).
 template <int LPE>
-__device__ __forceinline__ void load_episode(const KParams& p, const Env& w, int env, int slot, int sl) {
-  const uint4* src = reinterpret_cast<const uint4*>(p.sched + ((size_t)slot * p.n_envs + env) * 4 * p.Pp8);
+__device__ __forceinline__ void load_episode(const KParams& p, const Env& w, int env, int sl) {
+  const uint4* src = reinterpret_cast<const uint4*>(p.cur + (size_t)env * 4 * p.Pp8);
   uint4* dst = reinterpret_cast<uint4*>(w.start);
   const int n16 = p.Pp8 >> 1;  // 4 rows * Pp8 u16 * 2 B / 16 B
 #pragma unroll 1
   for (int i = sl; i < n16; i += LPE) dst[i] = __ldg(src + i);
+}
+
+// Auto-reset: the next pre-sampled episode moves from ring slot `slot` into shared memory AND into the env's
+// current-episode block (once per episode; every later step reads only that block).
+template <int LPE>
+__device__ __forceinline__ void advance_episode(const KParams& p, const Env& w, int env, int slot, int sl) {
+  const uint4* src = reinterpret_cast<const uint4*>(p.sched + ((size_t)slot * p.n_envs + env) * 4 * p.Pp8);
+  uint4* cur = reinterpret_cast<uint4*>(p.cur + (size_t)env * 4 * p.Pp8);
+  uint4* dst = reinterpret_cast<uint4*>(w.start);
+  const int n16 = p.Pp8 >> 1;
+#pragma unroll 1
+  for (int i = sl; i < n16; i += LPE) {
+    const uint4 v = __ldg(src + i);
+    dst[i] = v;
+    cur[i] = v;
+  }
 }
 
 // numpy float32 add.reduce over the R robot lanes (pairwise_sum: plain loop for n < 8, eight running
@@ -1057,8 +1074,8 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? (kFix ? MDX_FIX_BLOCKS : MD
   MapDev map = p.map0;
   if (p.env_map) map = p.maps[__ldg(p.env_map + env)];
 
-  // Issue every global load of the env's state up front so that their latencies overlap; only the
-  // schedule block depends on a loaded value (the episode cursor selects the ring slot).
+  // Issue every global load of the env's state up front so that their latencies overlap; no address depends
+  // on a loaded value (the current episode's schedule has its own block, the ring is touched on resets only).
   int t = p.t[env];
   int ep = p.ep[env];
   const uint4* st_src = reinterpret_cast<const uint4*>(p.status + (size_t)env * p.Pp16);
@@ -1079,7 +1096,7 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? (kFix ? MDX_FIX_BLOCKS : MD
     }
     total0 = p.total_reward[env];
   }
-  load_episode<LPE>(p, w, env, ep % p.E, sl);
+  load_episode<LPE>(p, w, env, sl);
   {
     uint4* dst = reinterpret_cast<uint4*>(w.status);
     if (sl < n_st16) dst[sl] = st0;
@@ -1205,7 +1222,7 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? (kFix ? MDX_FIX_BLOCKS : MD
       if (ep + 1 < __ldg(p.ep_avail + env)) {
         ep += 1;
         const int slot = ep % p.E;
-        load_episode<LPE>(p, w, env, slot, sl);
+        advance_episode<LPE>(p, w, env, slot, sl);
         g.sync();
         for (int j = sl; j < p.Pp16; j += LPE)
           w.status[j] = (j < P && w.t0[j] == 0) ? (uint8_t)ST_WAITING : (uint8_t)ST_NONE;

@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(128) mdx_shape_kernel(const __grid_constant__ 
   const int R = p.R;
   const bool active = lane < R;
   const int t = p.t[env];
-  load_episode<32>(p, w, env, p.ep[env] % p.E, lane);
+  load_episode<32>(p, w, env, lane);
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.status + (size_t)env * p.Pp16);
     uint4* dst = reinterpret_cast<uint4*>(w.status);
@@ -62,7 +62,13 @@ __global__ void __launch_bounds__(256) mdx_reset_kernel(const __grid_constant__ 
   const int env = p.env_ids ? p.env_ids[widx] : widx;
   const int ep = p.ep[env] + (int)(p.flags & 1u);  // flags bit 0: advance (0 = re-initialise in place)
   const int slot = ep % p.E;
-  const uint16_t* t0 = p.sched + ((size_t)slot * p.n_envs + env) * 4 * p.Pp8 + 2 * p.Pp8;
+  const uint16_t* blk = p.sched + ((size_t)slot * p.n_envs + env) * 4 * p.Pp8;
+  const uint16_t* t0 = blk + 2 * p.Pp8;
+  {  // the block becomes the env's current-episode schedule
+    const uint4* src = reinterpret_cast<const uint4*>(blk);
+    uint4* cur = reinterpret_cast<uint4*>(p.cur + (size_t)env * 4 * p.Pp8);
+    for (int i = lane; i < (p.Pp8 >> 1); i += 32) cur[i] = src[i];
+  }
   for (int j = lane; j < p.Pp16; j += 32)
     p.status[(size_t)env * p.Pp16 + j] = (j < p.P && t0[j] == 0) ? (uint8_t)ST_WAITING : (uint8_t)ST_NONE;
   if (lane < p.R) p.robots[(size_t)env * p.R + lane] = p.sched_robots[((size_t)slot * p.n_envs + env) * 32 + lane];
