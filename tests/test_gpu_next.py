@@ -263,3 +263,45 @@ def test_checkpoint_resume_is_bit_identical():
     assert int(wstats[0]) >= 96 * 2 and int(wstats[7]) == 0  # several auto-resets happened, nobody starved
     with pytest.raises(ValueError):
         mdb.DeliveryBatch([mdb.maps.stock_map("map1.txt")], 4, 5, 20, 50).load_state_dict(blob)
+
+
+def test_collect_rollouts_matches_trainer_loop():
+    """MAPPO/trainer.py:154-318 with a deterministic stand-in policy: every rollout buffer, the advantages and the
+    returns equal what the trainer's loop computes from the reference path (oracle) on the same actions."""
+    N, R, P, T_env, K = 6, 5, 50, 25, 60  # 60 rollout steps over 25-step episodes: two auto-resets per env
+    ve = mdb.VectorizedEnv(mdb.Environment, N, map_file="map1.txt", n_robots=R, n_packages=P, max_time_steps=T_env, seed=91,
+                           k_others=R - 1, k_packages=5)
+    ve.batch.reset()
+    ve.batch.prefetch(3)
+    gen = torch.Generator(device="cuda").manual_seed(17)
+
+    def policy(obs, vec, gstate, gvec):
+        a = torch.randint(0, 15, (N, R), dtype=torch.int64, device="cuda", generator=gen)
+        return a, vec[:, :, 0] - 1.0, gvec[:, :30].sum(1) * 0.1  # any deterministic functions of the features
+
+    def value(gstate, gvec):
+        return gvec[:, :30].sum(1) * 0.1
+
+    out = mdb.rollout.collect_rollouts(ve, policy, value, K, gamma=0.99, gae_lambda=0.95)
+    b_obs, b_vec, b_gs, b_gv, b_act, b_lp, b_adv, b_ret, mb_rewards, buf = out
+    assert b_obs.shape == (K * N * R, 6, 10, 10) and b_vec.shape == (K * N * R, 52)  # MAPPO/trainer.py:304-305
+    assert b_gs.shape == (K * N, 4, 10, 10) and b_gv.shape == (K * N, 1301)
+    assert b_act.shape == (K * N * R,) and b_adv.shape == (K * N * R,) and b_ret.shape == (K * N,)
+    # the reference loop on the CPU
+    grid = mdb.maps.stock_map("map1.txt")
+    ov = orc.OracleVecEnv(N, grid, seed=91, max_time_steps=T_env, n_robots=R, n_packages=P)
+    ov.reset()
+    acts = buf.actions.cpu().numpy()
+    snap = [e.snapshot() for e in ov.envs]
+    o0 = np.stack([np.stack([orc.observation(e, s, i) for i in range(R)]) for e, s in zip(ov.envs, snap)])
+    assert np.array_equal(buf.obs[0].cpu().numpy(), o0)
+    for t in range(K):
+        shaped, dones, o, v, g, gv = orc.mappo_rollout_step(ov, acts[t], R - 1, 5)
+        assert np.array_equal(buf.rewards[t].cpu().numpy(), shaped), t
+        assert np.array_equal(buf.dones[t].cpu().numpy().astype(bool), dones), t
+        assert np.array_equal(buf.obs[t + 1].cpu().numpy(), o) and np.array_equal(_bits(buf.vector_obs[t + 1].cpu().numpy()), _bits(v)), t
+        assert np.array_equal(buf.global_states[t + 1].cpu().numpy(), g) and np.array_equal(_bits(buf.global_vector[t + 1].cpu().numpy()), _bits(gv)), t
+    assert int(buf.dones.sum()) == 2 * N
+    wadv, wret = orc.gae_reference(buf.rewards.cpu(), buf.values.cpu(), buf.dones.cpu(), value(buf.global_states[K], buf.global_vector[K]).cpu(), 0.99, 0.95)
+    assert torch.equal(b_adv.cpu(), wadv.reshape(K * N, 1).repeat(1, R).reshape(-1)) and torch.equal(b_ret.cpu(), wret.reshape(-1))
+    assert torch.equal(b_lp, (buf.vector_obs[:K, :, :, 0] - 1.0).reshape(-1))
