@@ -1044,6 +1044,18 @@ __device__ __forceinline__ void specialise(KParams& p) {
     p.mul_plane = 42949673u;   // ceil(2^32 / 100)
     p.pair_g = 6;
     p.stage_b = 44;            // round_up(6 * 5 + 12, 4)
+    // shared-memory carve-up of this shape (mdx_create's formula; the launcher checks it): constant offsets fold
+    // into the LDS/STS immediates instead of living in registers
+    p.off_sched = 0;
+    p.off_status = 448;
+    p.off_wlist = 512;
+    p.off_wkey = 848;
+    p.off_rinfo = 1072;
+    p.off_alist = 1392;
+    p.off_sel = 1504;
+    p.off_masks = 1568;
+    p.off_stage = 1728;
+    p.key_wbits = 6;           // ceil(log2(P)) for 33..64 packages
   }
 }
 
