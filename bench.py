@@ -57,8 +57,8 @@ WORKLOADS = {
     "greedy": dict(desc="f2: batched GreedyAgents on the all-pairs BFS table + env step (2 launches per step); README evaluation shape: "
                         "map1, 5 robots, 100 packages, T=1000", maps=["map1.txt"], R=5, P=100, T=1000, K_o=4, K_p=5, MR=100, MP=100,
                    envs=65536, feat=False, kind="greedy"),
-    "idq": dict(desc="f3: one IDQ trainer iteration: step + per-agent reward_shaping, then convert_state x R + legacy 7-channel global "
-                     "tensor (2 launches per step); map1, 5 robots, 50 packages, T=500", maps=["map1.txt"], R=5, P=50, T=500, K_o=4,
+    "idq": dict(desc="f3: one IDQ trainer iteration: step + per-agent reward_shaping + convert_state x R + legacy 7-channel global "
+                     "tensor (1 fused launch per step); map1, 5 robots, 50 packages, T=500", maps=["map1.txt"], R=5, P=50, T=500, K_o=4,
                 K_p=5, MR=100, MP=100, envs=65536, feat=False, kind="idq"),
 }
 WL = dict(WORKLOADS["c3"])
@@ -240,7 +240,7 @@ def gpu_arm(args):
         launches_per_step = 2
         g_act = torch.empty((N, R), dtype=torch.uint8, device=dev)
     elif kind == "idq":
-        launches_per_step = 2
+        launches_per_step = 1
         idq_out = (out[0], torch.empty((N, R), dtype=torch.float64, device=dev), out[2])
         alt_out = (torch.empty((N, R, 6, b.rows_out, b.cols_out), dtype=torch.float32, device=dev),
                    torch.empty((N, 7, b.rows_out, b.cols_out), dtype=torch.float32, device=dev))
@@ -249,8 +249,7 @@ def gpu_arm(args):
         if kind == "greedy":
             b.step(b.greedy_actions(out=g_act), auto_reset=True, out=out)
         elif kind == "idq":
-            b.step_idq(a, auto_reset=True, ops_as_int=True, out=idq_out)
-            b.featurize_alt(out=alt_out)
+            b.step_idq_featurize(a, auto_reset=True, ops_as_int=True, out=idq_out, feat_out=alt_out)
         elif feat_on:
             b.step_featurize(a, auto_reset=True, out=out, feat_out=feat)
         else:
@@ -323,8 +322,7 @@ def gpu_arm(args):
         if kind == "greedy":
             _, shaped, done = ve.batch.step(ve.batch.greedy_actions(out=g_act), auto_reset=True, out=out)
         elif kind == "idq":
-            _, agent, done = ve.batch.step_idq(a, auto_reset=True, ops_as_int=True, out=idq_out)
-            ve.batch.featurize_alt(out=alt_out)
+            _, agent, done, *_ = ve.batch.step_idq_featurize(a, auto_reset=True, ops_as_int=True, out=idq_out, feat_out=alt_out)
             shaped = out[1]
         elif feat_on:
             _, shaped, done, *_ = ve.rollout_step(a, out=out, feat_out=feat)
@@ -349,6 +347,36 @@ def gpu_arm(args):
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_ms = float(t_e2e.item())
+
+    # ---- the same, double-buffered (VectorizedEnv.host_pipeline): the H2D copy of step n+1 and the read-back of step
+    # n-1 overlap the kernel of step n; every step still moves its actions in and its shaped reward + done out
+    pipe_ms = None
+    if kind == "path" and feat_on:
+        prefetch_for(Ke + 6)
+        pipe = ve.host_pipeline(feat_out=feat)
+        acc = 0.0
+        for s in range(3):
+            pipe.result(pipe.submit(h_act[s % len(h_act)]))
+        pipe.drain()
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        prev = None
+        for s in range(Ke):
+            slot = pipe.submit(h_act[s % len(h_act)])
+            if prev is not None:
+                sh, dn = pipe.result(prev)  # the host consumes step s-1 while step s runs
+                acc += float(sh[0]) + float(dn[0])
+            prev = slot
+        sh, dn = pipe.result(prev)
+        acc += float(sh[0]) + float(dn[0])
+        pipe.drain()
+        p1.record()
+        barrier()
+        t_p = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_p, op=dist.ReduceOp.MAX)
+        pipe_ms = float(t_p.item())
     starved = int(b.episode_stats().cpu()[7])
     if world > 1:
         dist.barrier()
@@ -369,7 +397,7 @@ def gpu_arm(args):
     if kind == "greedy":
         kern = "mdx_greedy_kernel + mdx_env_kernel<1,...> (both launches of a step)"
     elif kind == "idq":
-        kern = "mdx_env_kernel<1,...> + mdx_alt_featurize_kernel (both launches of a step)"
+        kern = "mdx_env_kernel<5,...> (fused step + IDQ shaping + convert_state x R + 7-channel tensor)"
     line = {
         "metric": "env-steps/sec (map1, 5 robots, 50 pkgs, T=500) with obs+state+vector featurisation" if args.workload == "c3"
                   else f"env-steps/sec ({args.workload})",
@@ -387,7 +415,11 @@ def gpu_arm(args):
                      "median_launch_ms": statistics.median(per_launch)},
         "e2e": {"value": world * N * Ke / (e2e_ms * 1e-3), "unit": "env-steps/s", "steps": Ke,
                 "h2d_bytes_per_step": N * R, "d2h_bytes_per_step": N * 5,
-                "note": "actions from pinned host memory, shaped reward + done read back every step; features stay in HBM"},
+                "note": "synchronous: actions from pinned host memory, shaped reward + done read back and waited for every step; "
+                        "features stay in HBM",
+                **({"pipelined_value": world * N * Ke / (pipe_ms * 1e-3),
+                    "pipelined_note": "VectorizedEnv.host_pipeline(): same copies every step, double-buffered on copy streams so "
+                                      "that they overlap the kernel (the host reads step n-1 while step n runs)"} if pipe_ms else {})},
         "gpu_launches": K * launches_per_step + 1,
         "clocks": clocks,
         "episode_stats": dict(zip(mdb.STAT_NAMES, stats_h)), "starved_envs": starved,

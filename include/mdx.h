@@ -210,6 +210,13 @@ int32_t mdx_featurize_alt(mdx_env* env, const int32_t* d_env_ids, int32_t n, flo
 int32_t mdx_step_idq(mdx_env* env, const uint8_t* d_actions, const int32_t* d_env_ids, int32_t n, double* d_reward,
                      double* d_agent_rewards, uint8_t* d_done, int32_t ops_as_int, uint32_t flags, void* stream);
 
+/* One IDQ trainer iteration in ONE launch (IDQ/trainer.py:276-300): mdx_step_idq, then -- on the state after the step and
+ * after any on-device auto-reset, like the trainer's convert_state calls on the next state -- mdx_featurize_alt into d_obs6 /
+ * d_gstate7 (either may be NULL).  Maps whose planes are not whole float4s fall back to the two launches internally. */
+int32_t mdx_step_idq_featurize(mdx_env* env, const uint8_t* d_actions, const int32_t* d_env_ids, int32_t n, double* d_reward,
+                               double* d_agent_rewards, uint8_t* d_done, float* d_obs6, float* d_gstate7, int32_t ops_as_int,
+                               uint32_t flags, void* stream);
+
 /* IDQ reward_shaping on caller-supplied "current" robots against the stored state as "previous" (the per-call
  * drop-in of IDQ/networks.py:228-349; same inputs as mdx_shaped_reward) -> d_out [n_envs, n_robots] f64. */
 int32_t mdx_reward_shaping_idq(mdx_env* env, const uint32_t* d_cur_robots, const int32_t* d_cur_t, const uint8_t* d_actions,

@@ -282,6 +282,24 @@ class DeliveryBatch:
         self._version += 1
         return reward, agent, done
 
+    def step_idq_featurize(self, actions, ids=None, auto_reset: bool = False, ops_as_int: bool = False, out=None, feat_out=None):
+        """One IDQ trainer iteration in ONE launch (IDQ/trainer.py:276-300): step_idq, then featurize_alt of the state after
+        the step (and after any auto-reset) -> (reward, agent rewards, done, obs6, gstate7)."""
+        d_ids, _, n = self._ids(ids)
+        actions, aflags = self._check_actions(actions, n)
+        if out is None:
+            out = (self._buf("reward", (n,), torch.float64), self._buf("agent_rewards", (n, self.n_robots), torch.float64),
+                   self._buf("done", (n,), torch.uint8))
+        reward, agent, done = out
+        R, H, W = self.n_robots, self.rows_out, self.cols_out
+        if feat_out is None:
+            feat_out = (self._buf("obs6", (n, R, 6, H, W), torch.float32), self._buf("gstate7", (n, 7, H, W), torch.float32))
+        _lib.check(self._L.mdx_step_idq_featurize(self._h, _ptr(actions), _ptr(d_ids), n, _ptr(reward), _ptr(agent), _ptr(done),
+                                                  _ptr(feat_out[0]), _ptr(feat_out[1]), 1 if ops_as_int else 0,
+                                                  (MDX_F_AUTO_RESET if auto_reset else 0) | aflags, self._stream()))
+        self._version += 1
+        return reward, agent, done, feat_out[0], feat_out[1]
+
     def bfs_table(self, map_id: int = 0) -> np.ndarray:
         """All-pairs shortest-path lengths of one map, uint16 [H*W, H*W] in output-plane cell ids (0xFFFF =
         unreachable): run_bfs (greedyagent.py:6-29) from every free cell."""

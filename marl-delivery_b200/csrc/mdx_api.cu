@@ -183,6 +183,7 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   if (const char* s = getenv("MDX_GENERIC")) e->force_generic = atoi(s);
   if (const char* s = getenv("MDX_LPE")) e->lpe_override = atoi(s);
   if (const char* s = getenv("MDX_NOFIX")) e->no_fixed = atoi(s);
+  if (const char* s = getenv("MDX_NOFAT")) e->no_fat = atoi(s);
   if (const char* s = getenv("MDX_CARVEOUT")) e->carveout = atoi(s);
 
   // ---- maps
@@ -294,35 +295,59 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
     return fail(MDX_E_INVALID, "configuration too large for the 32-bit package selection key (T=%d, P=%d, map %dx%d)", e->T, e->P, Ho, Wo);
 
   // ---- shared-memory carve-up per warp
-  int off = 0;
-  auto take = [&](int bytes) {
-    const int at = off;
-    off = round_up(off + bytes, 16);
-    return at;
-  };
-  b.off_sched = take(8 * b.Pp8);
-  b.off_status = take(b.Pp16);
-  b.off_wlist = take(3 * 2 * b.Pp8);  // wlist, wrc, wdl
-  b.off_wkey = take(4 * b.Pp8);
-  b.off_rinfo = take(2 * 5 * 32);
-  b.off_alist = take(2 * std::max(8, round_up(std::min(b.MP, std::max(1, e->P)), 8)));
-  int rpf = e->R;
-  // bytes of vec rows staged per flush (MDX_STAGE_BYTES overrides).  Rows longer than 2 KB (the K = 100 defaults: 4 KB
-  // per row) are flushed one at a time: a smaller stage means more resident CTAs (measured: K=100 80 -> 94 M env-steps/s)
-  int stage_cap = b.D * 4 > 2048 ? 4096 : 8192;
-  if (const char* sc = getenv("MDX_STAGE_BYTES")) stage_cap = std::max(1024, atoi(sc));
-  while (rpf > 1 && rpf * b.D * 4 > stage_cap) --rpf;
-  b.vec_rows_per_flush = rpf;
+  // `rpf` = vec rows staged per flush.  Rows longer than 2 KB (the K = 100 defaults: 4 KB per row) are flushed one at a time (a
+  // smaller stage means more resident CTAs: K=100 80 -> 94 M env-steps/s); otherwise up to 8 KB of rows per flush, reduced as
+  // long as that lets one more CTA fit an SM (C5: 10 rows = 73 KB per CTA = 3 CTAs/SM, 4 rows = 49 KB = 4 CTAs/SM: 12.5 -> 13.5 M
+  // env-steps/s).  MDX_STAGE_BYTES overrides the cap and disables the search.
   b.sel_k = std::min(b.K_p, e->P);
   b.mul_ksel = magic((uint32_t)std::max(1, b.sel_k));
   b.sel_rp = std::max(1, 32 / std::max(1, b.sel_k));
-  b.off_sel = take(2 * std::max(8, round_up(rpf * std::max(1, b.sel_k), 8)));
-  b.off_masks = take(4 * 10 * b.W32);
-  b.off_stage = off;
   b.stage_b = round_up(6 * std::min(e->R, b.MR) + 12, 4);
-  const int stage_floats = std::max(rpf * b.D + 8, b.stage_b + 7 * std::min(e->P, b.MP) + 12);
-  off = round_up(off + 4 * stage_floats, 16);
-  b.smem_per_warp = off;
+  // the key array is only touched by the selection paths for more than 5 slots per robot on a long waiting list (P > 64);
+  // with <= 5 slots those environments keep their candidates in registers (featurize_env), so C4 / C5 do not pay for it
+  const bool need_wkey = e->P <= 64 || b.sel_k > 5;
+  auto carve = [&](int rpf, bool commit) {
+    int off = 0;
+    auto take = [&](int bytes) {
+      const int at = off;
+      off = round_up(off + bytes, 16);
+      return at;
+    };
+    const int o_sched = take(8 * b.Pp8);
+    const int o_status = take(b.Pp16);
+    const int o_wlist = take(3 * 2 * b.Pp8);  // wlist, wrc, wdl
+    const int o_wkey = take(need_wkey ? 4 * b.Pp8 : 0);
+    const int o_rinfo = take(2 * 5 * 32);
+    const int o_alist = take(2 * std::max(8, round_up(std::min(b.MP, std::max(1, e->P)), 8)));
+    const int o_sel = take(2 * std::max(8, round_up(rpf * std::max(1, b.sel_k), 8)));
+    const int o_masks = take(4 * 10 * b.W32);
+    const int o_stage = off;
+    // (the fused IDQ featuriser keeps its H*W urgency plane in the stage)
+    const int stage_floats = std::max(std::max(rpf * b.D + 8, b.stage_b + 7 * std::min(e->P, b.MP) + 12), b.HW + 4);
+    off = round_up(off + 4 * stage_floats, 16);
+    if (commit) {
+      b.off_sched = o_sched, b.off_status = o_status, b.off_wlist = o_wlist, b.off_wkey = o_wkey, b.off_rinfo = o_rinfo;
+      b.off_alist = o_alist, b.off_sel = o_sel, b.off_masks = o_masks, b.off_stage = o_stage;
+      b.vec_rows_per_flush = rpf;
+      b.smem_per_warp = off;
+    }
+    return off;
+  };
+  auto ctas_per_sm = [&](int spw) { return std::min(7, (int)((227 * 1024) / ((size_t)kLutBytes + 4 * (size_t)spw + 1024))); };  // + 1 KB the driver reserves per CTA
+  int rpf = e->R;
+  int stage_cap = b.D * 4 > 2048 ? 4096 : 8192;
+  const char* sc = getenv("MDX_STAGE_BYTES");
+  if (sc) stage_cap = std::max(1024, atoi(sc));
+  while (rpf > 1 && rpf * b.D * 4 > stage_cap) --rpf;
+  if (!sc) {
+    int best = rpf, best_ctas = ctas_per_sm(carve(rpf, false));
+    for (int r = rpf - 1; r >= 1; --r) {
+      const int c = ctas_per_sm(carve(r, false));
+      if (c > best_ctas) best = r, best_ctas = c;
+    }
+    rpf = best;
+  }
+  carve(rpf, true);
   if (b.smem_per_warp > 220 * 1024)
     return fail(MDX_E_INVALID, "per-environment working set (%d bytes) exceeds shared memory", b.smem_per_warp);
 
@@ -543,7 +568,8 @@ int32_t mdx_prefetch(mdx_env* e, int32_t ahead, void* stream) {
 
 static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int32_t* d_env_ids, int32_t n, double* d_reward,
                        float* d_shaped, uint8_t* d_done, float* d_obs, float* d_vec, float* d_gstate, float* d_gvec,
-                       uint32_t flags, void* stream, double* d_agent = nullptr, int ops_as_int = 0) {
+                       uint32_t flags, void* stream, double* d_agent = nullptr, int ops_as_int = 0, float* d_obs6 = nullptr,
+                       float* d_g7 = nullptr) {
   if (!e) return fail(MDX_E_INVALID, "null env");
   if ((mode & 1) && !d_actions) return fail(MDX_E_INVALID, "actions are required");
   if (d_env_ids == nullptr && n != e->n) return fail(MDX_E_INVALID, "n must equal n_envs when env ids are not given (got %d, have %d)", n, e->n);
@@ -568,7 +594,10 @@ static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int
   kp.gvec = d_gvec;
   kp.out_agent = d_agent;
   kp.idq_ops_int = ops_as_int;
+  kp.alt_obs6 = d_obs6;
+  kp.alt_g7 = d_g7;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode == 5) return launch_env_kernel_5(e, kp, st);
   if (mode == 1) return launch_env_kernel_1(e, kp, st);
   if (mode == 2) return launch_env_kernel_2(e, kp, st);
   return launch_env_kernel_3(e, kp, st);
@@ -584,6 +613,22 @@ int32_t mdx_step_idq(mdx_env* e, const uint8_t* d_actions, const int32_t* d_env_
   if (!d_agent_rewards) return fail(MDX_E_INVALID, "agent reward output is required");
   return step_common(e, 1, d_actions, d_env_ids, n, d_reward, nullptr, d_done, nullptr, nullptr, nullptr, nullptr, flags, stream,
                      d_agent_rewards, ops_as_int ? 1 : 0);
+}
+
+int32_t mdx_step_idq_featurize(mdx_env* e, const uint8_t* d_actions, const int32_t* d_env_ids, int32_t n, double* d_reward,
+                               double* d_agent_rewards, uint8_t* d_done, float* d_obs6, float* d_gstate7, int32_t ops_as_int,
+                               uint32_t flags, void* stream) {
+  if (!d_agent_rewards) return fail(MDX_E_INVALID, "agent reward output is required");
+  int rc;
+  if ((rc = check_ptr16(d_obs6, "obs6")) || (rc = check_ptr16(d_gstate7, "gstate7"))) return rc;
+  rc = getenv("MDX_IDQ_UNFUSED") ? MDX_E_UNSUPPORTED_SHAPE
+                                 : step_common(e, 5, d_actions, d_env_ids, n, d_reward, nullptr, d_done, nullptr, nullptr, nullptr, nullptr,
+                                               flags, stream, d_agent_rewards, ops_as_int ? 1 : 0, d_obs6, d_gstate7);
+  if (rc != MDX_E_UNSUPPORTED_SHAPE) return rc;
+  // maps whose planes are not whole float4s (or larger than 4 x 32 float4): the same result from two launches
+  rc = mdx_step_idq(e, d_actions, d_env_ids, n, d_reward, d_agent_rewards, d_done, ops_as_int, flags, stream);
+  if (rc != MDX_OK) return rc;
+  return mdx_featurize_alt(e, d_env_ids, n, d_obs6, d_gstate7, stream);
 }
 
 int32_t mdx_featurize(mdx_env* e, const int32_t* d_env_ids, int32_t n, float* d_obs, float* d_vec, float* d_gstate, float* d_gvec,

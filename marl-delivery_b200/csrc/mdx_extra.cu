@@ -197,9 +197,59 @@ __global__ void __launch_bounds__(128) mdx_greedy_kernel(const __grid_constant__
 // every load/store is coalesced across envs.  float32, no FMA contraction (-fmad=false), the reference's
 // order of operations.
 // ------------------------------------------------------------------------------------------------
-constexpr int kGaeChunk = 16;  // time steps whose loads are issued together before the dependent recurrence runs
+#ifndef MDX_GAE_CHUNK
+#define MDX_GAE_CHUNK 16
+#endif
+#ifndef MDX_GAE_THREADS
+#define MDX_GAE_THREADS 128
+#endif
+#ifndef MDX_GAE_DB
+#define MDX_GAE_DB 1
+#endif
+constexpr int kGaeChunk = MDX_GAE_CHUNK;  // time steps whose loads are issued together before the dependent recurrence runs
+constexpr int kGaeThreads = MDX_GAE_THREADS;
 
-__global__ void __launch_bounds__(128) mdx_gae_kernel(const float* __restrict__ rew, const float* __restrict__ val,
+struct GaeChunk {
+  float r[kGaeChunk], v[kGaeChunk];
+  uint8_t d[kGaeChunk];
+};
+
+__device__ __forceinline__ void gae_load(GaeChunk& c, const float* __restrict__ rew, const float* __restrict__ val,
+                                         const uint8_t* __restrict__ done, int t1, int N, int n) {
+#pragma unroll
+  for (int u = 0; u < kGaeChunk; ++u) {  // independent, coalesced loads: the recurrence never waits on DRAM
+    const int t = t1 - 1 - u;
+    if (t >= 0) {
+      const size_t k = (size_t)t * N + n;
+      c.r[u] = __ldcs(rew + k);
+      c.v[u] = __ldcs(val + k);
+      c.d[u] = __ldcs(done + k);
+    }
+  }
+}
+
+__device__ __forceinline__ void gae_scan(const GaeChunk& c, int t1, int N, int n, float gamma, float gl, float& next_v, float& last,
+                                         float* __restrict__ adv, float* __restrict__ ret) {
+#pragma unroll
+  for (int u = 0; u < kGaeChunk; ++u) {
+    const int t = t1 - 1 - u;
+    if (t >= 0) {
+      const size_t k = (size_t)t * N + n;
+      const float nnt = __fsub_rn(1.0f, c.d[u] ? 1.0f : 0.0f);
+      // delta = r + GAMMA * next_values * next_non_terminal - v
+      const float delta = __fsub_rn(__fadd_rn(c.r[u], __fmul_rn(__fmul_rn(gamma, next_v), nnt)), c.v[u]);
+      // last = delta + GAMMA * GAE_LAMBDA * next_non_terminal * last   (GAMMA * GAE_LAMBDA is one Python float)
+      last = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nnt), last));
+      __stcs(adv + k, last);
+      __stcs(ret + k, __fadd_rn(last, c.v[u]));
+      next_v = c.v[u];
+    }
+  }
+}
+
+// Two chunks are in flight: the loads of the next 16 time steps are issued before the recurrence of the current 16 runs, so
+// the (few: one thread per env) warps always have DRAM requests outstanding.
+__global__ void __launch_bounds__(kGaeThreads) mdx_gae_kernel(const float* __restrict__ rew, const float* __restrict__ val,
                                                       const uint8_t* __restrict__ done, const float* __restrict__ last_value,
                                                       int T, int N, float gamma, float gl, float* __restrict__ adv,
                                                       float* __restrict__ ret) {
@@ -207,34 +257,135 @@ __global__ void __launch_bounds__(128) mdx_gae_kernel(const float* __restrict__ 
   if (n >= N) return;
   float next_v = last_value[n];
   float last = 0.0f;
+#if MDX_GAE_DB
+  GaeChunk a, b;
+  gae_load(a, rew, val, done, T, N, n);
+  for (int t1 = T; t1 > 0; t1 -= 2 * kGaeChunk) {
+    gae_load(b, rew, val, done, t1 - kGaeChunk, N, n);
+    gae_scan(a, t1, N, n, gamma, gl, next_v, last, adv, ret);
+    gae_load(a, rew, val, done, t1 - 2 * kGaeChunk, N, n);
+    gae_scan(b, t1 - kGaeChunk, N, n, gamma, gl, next_v, last, adv, ret);
+  }
+#else
+  GaeChunk a;
   for (int t1 = T; t1 > 0; t1 -= kGaeChunk) {
-    float r[kGaeChunk], v[kGaeChunk];
-    uint8_t d[kGaeChunk];
+    gae_load(a, rew, val, done, t1, N, n);
+    gae_scan(a, t1, N, n, gamma, gl, next_v, last, adv, ret);
+  }
+#endif
+}
+
+// ---- TMA variant -----------------------------------------------------------------------------------------------------
+// One thread per env leaves only ~14 warps per SM, and what they can keep in flight from registers (two chunks) is ~9 MB
+// chip-wide -- short of what HBM3e needs.  Here the loads do not occupy registers at all: a CTA owns 128 adjacent columns and
+// streams them through a ring of shared-memory stages filled by bulk async copies (cp.async.bulk, one 512-byte row segment
+// per array and time step, completion counted on an mbarrier per stage); kGaeTmaStages - 1 stages are always in flight while
+// the threads run the recurrence on the landed one.  Needs N % 16 == 0 and 16-byte aligned arrays (row segments of the uint8
+// dones must be 16-byte aligned); anything else takes the register kernel above.
+#ifndef MDX_GAE_TMA_ROWS
+#define MDX_GAE_TMA_ROWS 10
+#endif
+#ifndef MDX_GAE_TMA_STAGES
+#define MDX_GAE_TMA_STAGES 4
+#endif
+constexpr int kGaeTmaRows = MDX_GAE_TMA_ROWS, kGaeTmaStages = MDX_GAE_TMA_STAGES, kGaeTmaCols = 128;
+constexpr int kGaeStageBytes = kGaeTmaRows * kGaeTmaCols * 9;  // rewards f32 + values f32 + dones u8
+constexpr int kGaeTmaSmem = 128 + kGaeTmaStages * kGaeStageBytes;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* b, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(b)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(b))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kGaeTmaCols) mdx_gae_tma_kernel(const float* __restrict__ rew, const float* __restrict__ val,
+                                                                 const uint8_t* __restrict__ done, const float* __restrict__ last_value,
+                                                                 int T, int N, float gamma, float gl, float* __restrict__ adv,
+                                                                 float* __restrict__ ret) {
+  extern __shared__ __align__(128) unsigned char gae_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(gae_smem);  // [kGaeTmaStages]
+  unsigned char* ring = gae_smem + 128;
+  const int tid = threadIdx.x;
+  const int c0 = blockIdx.x * kGaeTmaCols;
+  const int cols = min(kGaeTmaCols, N - c0);  // a multiple of 16
+  const int n = c0 + tid;
+  const bool act = tid < cols;
+  const int nchunks = (T + kGaeTmaRows - 1) / kGaeTmaRows;
+  if (tid == 0) {
+    for (int s = 0; s < kGaeTmaStages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  // chunk k = time steps [T - k*rows - rows, T - k*rows), newest first; warp 0 issues it, one row per lane
+  auto issue = [&](int k) {
+    const int s = k % kGaeTmaStages;
+    const int t1 = T - k * kGaeTmaRows;
+    const int rows = min(kGaeTmaRows, t1);
+    float* s_rew = reinterpret_cast<float*>(ring + (size_t)s * kGaeStageBytes);
+    float* s_val = s_rew + kGaeTmaRows * kGaeTmaCols;
+    unsigned char* s_done = reinterpret_cast<unsigned char*>(s_val + kGaeTmaRows * kGaeTmaCols);
+    if (tid == 0) mbar_expect_tx(&full[s], (unsigned)(rows * cols * 9));
+    __syncwarp();
+    for (int u = tid; u < rows; u += 32) {
+      const size_t g = (size_t)(t1 - 1 - u) * N + c0;
+      bulk_g2s(s_rew + u * kGaeTmaCols, rew + g, (unsigned)cols * 4u, &full[s]);
+      bulk_g2s(s_val + u * kGaeTmaCols, val + g, (unsigned)cols * 4u, &full[s]);
+      bulk_g2s(s_done + u * kGaeTmaCols, done + g, (unsigned)cols, &full[s]);
+    }
+  };
+  if (tid < 32)
+    for (int k = 0; k < min(kGaeTmaStages, nchunks); ++k) issue(k);
+  float next_v = act ? last_value[n] : 0.0f;
+  float last = 0.0f;
+  for (int k = 0; k < nchunks; ++k) {
+    const int s = k % kGaeTmaStages;
+    const unsigned parity = (unsigned)(k / kGaeTmaStages) & 1u;
+    unsigned spins = 0;
+    while (!mbar_try_wait(&full[s], parity))
+      if (++spins > (1u << 24)) __trap();  // a lost copy must not hang the GPU
+    const int t1 = T - k * kGaeTmaRows;
+    const int rows = min(kGaeTmaRows, t1);
+    const float* s_rew = reinterpret_cast<const float*>(ring + (size_t)s * kGaeStageBytes);
+    const float* s_val = s_rew + kGaeTmaRows * kGaeTmaCols;
+    const unsigned char* s_done = reinterpret_cast<const unsigned char*>(s_val + kGaeTmaRows * kGaeTmaCols);
+    if (act) {
 #pragma unroll
-    for (int u = 0; u < kGaeChunk; ++u) {  // independent, coalesced loads: the recurrence below never waits on DRAM
-      const int t = t1 - 1 - u;
-      if (t >= 0) {
-        const size_t k = (size_t)t * N + n;
-        r[u] = __ldcs(rew + k);
-        v[u] = __ldcs(val + k);
-        d[u] = __ldcs(done + k);
+      for (int u = 0; u < kGaeTmaRows; ++u) {
+        if (u < rows) {
+          const size_t g = (size_t)(t1 - 1 - u) * N + n;
+          const float r = s_rew[u * kGaeTmaCols + tid], v = s_val[u * kGaeTmaCols + tid];
+          const float nnt = __fsub_rn(1.0f, s_done[u * kGaeTmaCols + tid] ? 1.0f : 0.0f);
+          const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, next_v), nnt)), v);
+          last = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nnt), last));
+          __stcs(adv + g, last);
+          __stcs(ret + g, __fadd_rn(last, v));
+          next_v = v;
+        }
       }
     }
-#pragma unroll
-    for (int u = 0; u < kGaeChunk; ++u) {
-      const int t = t1 - 1 - u;
-      if (t >= 0) {
-        const size_t k = (size_t)t * N + n;
-        const float nnt = __fsub_rn(1.0f, d[u] ? 1.0f : 0.0f);
-        // delta = r + GAMMA * next_values * next_non_terminal - v
-        const float delta = __fsub_rn(__fadd_rn(r[u], __fmul_rn(__fmul_rn(gamma, next_v), nnt)), v[u]);
-        // last = delta + GAMMA * GAE_LAMBDA * next_non_terminal * last   (GAMMA * GAE_LAMBDA is one Python float)
-        last = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nnt), last));
-        __stcs(adv + k, last);
-        __stcs(ret + k, __fadd_rn(last, v[u]));
-        next_v = v[u];
-      }
-    }
+    __syncthreads();  // every thread has consumed stage s: it can be refilled
+    if (tid < 32 && k + kGaeTmaStages < nchunks) issue(k + kGaeTmaStages);
   }
 }
 
@@ -332,9 +483,25 @@ int32_t mdx_featurize_alt(mdx_env* e, const int32_t* d_env_ids, int32_t n, float
   kp.n = n;
   const int HW = e->base.HW;
   AltArgs a{d_obs6, d_gstate7, (int32_t)(sizeof(float) * ((HW + 3) & ~3) + sizeof(uint32_t) * 6 * e->base.W32 + 15) / 16 * 16};
-  const size_t smem = (size_t)4 * a.smem_per_warp;
-  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(mdx_alt_featurize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mdx_alt_featurize_kernel<<<(unsigned)((n + 3) / 4), 128, smem, static_cast<cudaStream_t>(stream)>>>(kp, a);
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((n + 3) / 4);
+  if ((HW & 3) == 0 && HW <= 4 * 32 * 4 && !getenv("MDX_ALT_GENERIC")) {
+    // plane-sliced variants: a plane is at most NS slices of 32 float4
+    const size_t smem = (size_t)kLutBytes + (size_t)4 * a.smem_per_warp;
+    const int ns = (HW / 4 + 31) / 32;
+    auto go = [&](auto kern) -> int {
+      if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, 128, smem, st>>>(kp, a);
+      return MDX_OK;
+    };
+    int rc = ns == 1 ? go(mdx_alt_featurize_sliced<1>) : ns == 2 ? go(mdx_alt_featurize_sliced<2>)
+           : ns == 3 ? go(mdx_alt_featurize_sliced<3>) : go(mdx_alt_featurize_sliced<4>);
+    if (rc != MDX_OK) return rc;
+  } else {
+    const size_t smem = (size_t)4 * a.smem_per_warp;
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(mdx_alt_featurize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mdx_alt_featurize_kernel<<<grid, 128, smem, st>>>(kp, a);
+  }
   CU(cudaGetLastError());
   return MDX_OK;
 }
@@ -357,8 +524,18 @@ int32_t mdx_gae(const float* d_rewards, const float* d_values, const uint8_t* d_
   if (T == 0 || N == 0) return MDX_OK;
   // a Python float scalar times a float32 tensor is evaluated in float32 with the scalar rounded once
   const float g32 = (float)gamma, gl32 = (float)(gamma * gae_lambda);
-  mdx_gae_kernel<<<(unsigned)((N + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(d_rewards, d_values, d_dones, d_last_value,
-                                                                                           T, N, g32, gl32, d_advantages, d_returns);
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  if (N % 16 == 0 && al16(d_rewards) && al16(d_values) && al16(d_dones) && !getenv("MDX_GAE_NO_TMA")) {
+    if (mdx::kGaeTmaSmem > 48 * 1024)
+      CU(cudaFuncSetAttribute(mdx::mdx_gae_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mdx::kGaeTmaSmem));
+    mdx::mdx_gae_tma_kernel<<<(unsigned)((N + mdx::kGaeTmaCols - 1) / mdx::kGaeTmaCols), mdx::kGaeTmaCols, mdx::kGaeTmaSmem, st>>>(
+        d_rewards, d_values, d_dones, d_last_value, T, N, g32, gl32, d_advantages, d_returns);
+  } else {
+    mdx_gae_kernel<<<(unsigned)((N + mdx::kGaeThreads - 1) / mdx::kGaeThreads), mdx::kGaeThreads, 0, st>>>(d_rewards, d_values, d_dones,
+                                                                                                  d_last_value, T, N, g32, gl32,
+                                                                                                  d_advantages, d_returns);
+  }
   CU(cudaGetLastError());
   return MDX_OK;
 }

@@ -110,6 +110,7 @@ struct mdx_env {
   int carveout = -1;      // MDX_CARVEOUT=0..100: preferred shared-memory carve-out of the env kernels (-1 = driver default)
   size_t smem_configured[96] = {};
   int no_fixed = 0;       // MDX_NOFIX=1: never use the shape-specialised instantiation
+  int no_fat = 0;         // MDX_NOFAT=1: never use the uncapped-register instantiation for big environments
   int lpe_override = 0;   // MDX_LPE=8|16|32: minimum lanes per environment (experiments / tests)
   int force_generic = 0;  // MDX_GENERIC=1: always take the generic featuriser path (tests)
 };
@@ -120,6 +121,8 @@ namespace mdx {
 int launch_env_kernel_1(mdx_env* e, const KParams& kp, cudaStream_t st);
 int launch_env_kernel_2(mdx_env* e, const KParams& kp, cudaStream_t st);
 int launch_env_kernel_3(mdx_env* e, const KParams& kp, cudaStream_t st);
+int launch_env_kernel_5(mdx_env* e, const KParams& kp, cudaStream_t st);  // step + IDQ featurisers; MDX_E_UNSUPPORTED_SHAPE: use two launches
+constexpr int MDX_E_UNSUPPORTED_SHAPE = -100;  // internal: never crosses the C ABI
 // builds the all-pairs BFS tables and publishes them in the map descriptors (idempotent)
 int ensure_bfs(mdx_env* e);
 }  // namespace mdx

@@ -121,6 +121,8 @@ struct KParams {
   double* out_agent;        // [n, R] IDQ per-agent reward_shaping (IDQ/networks.py:228-349), nullptr = off
   int32_t idq_ops_int;      // 0: package ops arrive as strings like in IDQ/trainer.py (only the stay penalty can fire); 1: ints
   int32_t pad1;
+  float* alt_obs6;          // [n, R, 6, H, W] IDQ convert_state, fused behind the step (kernel mode 5), nullptr = off
+  float* alt_g7;            // [n, 7, H, W] legacy global tensor
   // shaped-reward-only call
   const uint32_t* cur_robots;
   const int32_t* cur_t;

@@ -40,6 +40,12 @@ namespace mdx {
 #ifndef MDX_FIX_BLOCKS
 #define MDX_FIX_BLOCKS 9   // shape-specialised variant (kFix = 1)
 #endif
+#ifndef MDX_FAT_BLOCKS
+#define MDX_FAT_BLOCKS 4   // big-environment variant (kFix = 2): shared memory already limits it to <= 4 CTAs/SM, so registers are free
+#endif
+#ifndef MDX_FIX_THREADS
+#define MDX_FIX_THREADS 128  // CTA size of the shape-specialised variant (one warp per env)
+#endif
 constexpr int kLutBytes = 256;  // block-shared nibble -> float4 table at the start of dynamic smem
 
 // A lane group: LPE consecutive lanes of a warp that own one environment.
@@ -812,7 +818,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
             o[4] = tnorm(p, (int)w.wdl[k]);
           }
         }
-      } else if (nsel > 0 && 2 * nsel >= nw) {
+      } else if (nsel > 0 && 2 * nsel >= nw && (kSmall || Ksel > 5)) {
         // Most (or all) of the waiting list is selected -- the K = 100 defaults of generate_vector_features
         // (MAPPO/helper.py:70): rank every entry by counting the smaller keys (O(nw) per entry, no rounds) and let
         // the entry's owner write its row at that position.
@@ -1015,8 +1021,123 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
 }
 
 // ------------------------------------------------------------------------------------------------
-// kMode bit 0: step (+ shaped reward, + optional auto-reset);  bit 1: featurise.
+// IDQ / legacy-qmix featurisers (IDQ/networks.py:112-217, qmix/networks.py:350-468) of the env held in shared memory,
+// fused behind the step (kMode bit 2): obs6 [R, 6, H, W] per robot and the 7-channel global tensor.  Plane-sliced like
+// featurize_env: a lane owns float4 number (sl + 32*s) of every plane; six bit planes live in w.planes, the urgency
+// float plane in w.stage.
+// urgency of a waiting package whose start_time has passed (IDQ/networks.py:172-179): float64 quotient,
+// clamped, then stored into a float32 array
+__device__ __forceinline__ float alt_urgency(int t, int st, int dl) {
+  if (dl > st) {
+    double u = __ddiv_rn((double)(t - st), (double)(dl - st));
+    u = u > 1.0 ? 1.0 : u;
+    return __double2float_rn(u);
+  }
+  return dl == st ? 1.0f : 0.0f;
+}
+
+template <int kS>
+__device__ __forceinline__ void featurize_alt_env(const KParams& p, const Env& w, const Grp<32>& g, const float4* lut, const MapDev& map,
+                                                  int row, int t, int cell, int carry) {
+  constexpr int NS = kS > 0 ? kS : 1;
+  const int sl = g.sl;
+  const int R = p.R, P = p.P, HW = p.HW, W32 = p.W32;
+  const bool active = sl < R;
+  float* urg = w.stage;
+  uint32_t* planes = w.planes;
+  const int n4p = HW >> 2;
+#pragma unroll 1
+  for (int i = sl; i < n4p; i += 32) reinterpret_cast<float4*>(urg)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int i = sl; i < W32; i += 32) {
+    planes[i] = __ldg(map.grid_bits + i);
+#pragma unroll
+    for (int k = 1; k < 6; ++k) planes[k * W32 + i] = 0u;
+  }
+  g.sync();
+  // planes: 0 grid, 1 robots, 2 robots that carry, 3 waiting starts, 4 waiting targets, 5 in-transit targets
+  int own_tgt = 0xFFFF;
+  if (active) {
+    atomicOr(&planes[W32 + (cell >> 5)], 1u << (cell & 31));
+    if (carry != 0) {
+      atomicOr(&planes[2 * W32 + (cell >> 5)], 1u << (cell & 31));
+      const uint8_t st = w.status[carry - 1];
+      if (st == ST_WAITING || st == ST_IN_TRANSIT) own_tgt = w.target[carry - 1];  // "id in persistent_packages"
+    }
+  }
+#pragma unroll 1
+  for (int j = sl; j < P; j += 32) {
+    const uint8_t st = w.status[j];
+    if (st != ST_WAITING && st != ST_IN_TRANSIT) continue;
+    const int t0 = w.t0[j];
+    if (t < t0) continue;
+    const int tc = w.target[j];
+    if (st == ST_WAITING) {
+      const int sc = w.start[j];
+      atomicOr(&planes[3 * W32 + (sc >> 5)], 1u << (sc & 31));
+      atomicOr(&planes[4 * W32 + (tc >> 5)], 1u << (tc & 31));
+      atomicMax(reinterpret_cast<int*>(urg + sc), __float_as_int(alt_urgency(t, t0, (int)w.dl[j])));
+    } else {
+      atomicOr(&planes[5 * W32 + (tc >> 5)], 1u << (tc & 31));
+    }
+  }
+  g.sync();
+  uint32_t nib[NS][6];
+  float4 u4[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const int q = sl + 32 * s;
+    const bool ok = q < n4p;
+    const int wi = q >> 3;
+    const uint32_t sh = (uint32_t)(q & 7) << 2;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) nib[s][k] = ok ? (planes[k * W32 + wi] >> sh) & 15u : 0u;
+    u4[s] = ok ? reinterpret_cast<const float4*>(urg)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.alt_g7 != nullptr) {
+    float4* out4 = reinterpret_cast<float4*>(p.alt_g7 + (size_t)row * 7 * HW);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const int q = sl + 32 * s;
+      if (q < n4p) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) __stcs(out4 + k * n4p + q, lut[nib[s][k]]);
+        __stcs(out4 + 6 * n4p + q, u4[s]);
+      }
+    }
+  }
+  if (p.alt_obs6 != nullptr) {
+    float4* base4 = reinterpret_cast<float4*>(p.alt_obs6 + (size_t)row * R * 6 * HW);
+#pragma unroll 1
+    for (int i = 0; i < R; ++i) {
+      const uint32_t ci = (uint32_t)g.shfl(cell, i), ti = (uint32_t)g.shfl(own_tgt, i);
+      const bool free_i = g.shfl(carry, i) == 0;
+      float4* out4 = base4 + (size_t)i * 6 * n4p;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const int q = sl + 32 * s;
+        if (q < n4p) {
+          const uint32_t oh_r = ((ci >> 2) == (uint32_t)q) ? (1u << (ci & 3u)) : 0u;
+          const uint32_t oh_t = ((ti >> 2) == (uint32_t)q) ? (1u << (ti & 3u)) : 0u;  // 0xFFFF (none) matches no q
+          __stcs(out4 + q, lut[nib[s][0]]);
+          __stcs(out4 + n4p + q, free_i ? u4[s] : z4);
+          __stcs(out4 + 2 * n4p + q, lut[free_i ? nib[s][3] : 0u]);
+          __stcs(out4 + 3 * n4p + q, lut[nib[s][1] & ~oh_r]);
+          __stcs(out4 + 4 * n4p + q, lut[oh_r]);
+          __stcs(out4 + 5 * n4p + q, lut[oh_t]);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kMode bit 0: step (+ shaped reward, + optional auto-reset);  bit 1: featurise (MAPPO);  bit 2: featurise (IDQ / legacy, whole warps only).
 // LPE lanes per environment: a 128-thread CTA holds 128 / LPE environments.
+// kFix: 2 = like 0, compiled without the register cap of the 7-CTAs/SM variants, for environments whose shared-memory working set
+// allows <= 4 CTAs/SM anyway (C5: 32 robots, 500 packages): the compiler then keeps several LDS.128 -> STG.128 pairs in flight
+// per warp instead of recycling one register quad.
 // kFix: shape specialisation.  0 = every shape parameter is read from KParams at run time; 1 = the
 // headline MAPPO shape (C3: map1 10x10, 5 robots, <= 56 packages, K_o = 4, K_p = 5, MR = MP = 100) is baked
 // in as compile-time constants, so loops over robots / planes / rows unroll and the index arithmetic folds.
@@ -1060,12 +1181,14 @@ __device__ __forceinline__ void specialise(KParams& p) {
 }
 
 template <int kMode, int LPE, int kS, bool kSmall, int kFix>
-__global__ void __launch_bounds__(128, (kMode & 2) ? (kFix ? MDX_FIX_BLOCKS : MDX_FEAT_BLOCKS) : 8) mdx_env_kernel(const __grid_constant__ KParams pg) {
+__global__ void __launch_bounds__((kFix == 1 && (kMode & 2)) ? MDX_FIX_THREADS : 128,
+                                   (kMode & 2) ? (kFix == 1 ? MDX_FIX_BLOCKS : kFix == 2 ? MDX_FAT_BLOCKS : MDX_FEAT_BLOCKS)
+                                               : ((kMode & 4) && kS > 2) ? 6 : 8) mdx_env_kernel(const __grid_constant__ KParams pg) {
   KParams p = pg;
   specialise<kFix>(p);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const float4* lut = reinterpret_cast<const float4*>(smem_raw);
-  if (kMode & 2) {
+  if (kMode & 6) {
     if (threadIdx.x < 16) {
       const unsigned n = threadIdx.x;
       reinterpret_cast<float4*>(smem_raw)[n] =
@@ -1162,7 +1285,7 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? (kFix ? MDX_FIX_BLOCKS : MD
     // robots stand on distinct cells, so pickups never contend across robots: each takes the
     // lowest-id waiting package on its own cell
     const int nw_prev = build_waiting<LPE>(p, w, g, t);
-    const bool bfs_mode = kFix == 0 && p.shaping_bfs != 0;
+    const bool bfs_mode = kFix != 1 && p.shaping_bfs != 0;
     const Scan sc = bfs_mode ? scan_waiting<LPE, kSmall, true>(w, g, R, nw_prev, r, c, r1, c1, map.bfs, p.HW, Wo)
                              : scan_waiting<LPE, kSmall, false>(w, g, R, nw_prev, r, c, r1, c1, nullptr, 0, 0);
     const bool want_pick = active && op == 1 && carry == 0;
@@ -1265,6 +1388,7 @@ __global__ void __launch_bounds__(128, (kMode & 2) ? (kFix ? MDX_FIX_BLOCKS : MD
   }
 
   if (kMode & 2) featurize_env<LPE, kS, kSmall, kFix>(p, w, g, lut, map, widx, t, cell, carry);
+  if constexpr ((kMode & 4) != 0 && LPE == 32 && kS > 0) featurize_alt_env<kS>(p, w, g, lut, map, widx, t, cell, carry);
 }
 
 }  // namespace mdx

@@ -7,15 +7,17 @@ namespace mdx {
 namespace {
 
 int smem_for_mode(const mdx_env* e, int mode) {
-  return (mode & 2) ? e->base.smem_per_warp : e->base.off_alist;
+  return (mode & 6) ? e->base.smem_per_warp : e->base.off_alist;
 }
 
 template <int kMode, int LPE, int kS, bool kSmall, int kFix>
 int launch_variant(mdx_env* e, const KParams& kp, cudaStream_t st) {
   const int spe = smem_for_mode(e, kMode);  // shared memory per environment
-  const int epb = 128 / LPE;                // environments per 128-thread CTA
+  const int threads = (kFix == 1 && (kMode & 2)) ? MDX_FIX_THREADS : 128;
+  const int epb = threads / LPE;            // environments per CTA
   const size_t smem = (size_t)kLutBytes + (size_t)epb * spe;
-  const int slot = kFix ? 95 - kMode
+  const int slot = kMode == 5 ? 80 + (kS == 1 ? 0 : kS == 2 ? 1 : 2) * 2 + (kSmall ? 1 : 0)
+                   : kFix == 2 ? 91 - kMode : kFix ? 95 - kMode
                         : ((kMode * 3 + (LPE == 8 ? 0 : LPE == 16 ? 1 : 2)) * 4 + (kS == 0 ? 0 : kS == 1 ? 1 : kS == 2 ? 2 : 3)) * 2 + (kSmall ? 1 : 0);
   if (smem > 227 * 1024) return fail(MDX_E_INVALID, "per-CTA working set (%zu bytes) exceeds shared memory", smem);
   if (smem > e->smem_configured[slot]) {
@@ -28,7 +30,7 @@ int launch_variant(mdx_env* e, const KParams& kp, cudaStream_t st) {
   KParams q = kp;
   q.smem_per_warp = spe;
   const unsigned grid = (unsigned)((kp.n + epb - 1) / epb);
-  mdx_env_kernel<kMode, LPE, kS, kSmall, kFix><<<grid, 128, smem, st>>>(q);
+  mdx_env_kernel<kMode, LPE, kS, kSmall, kFix><<<grid, threads, smem, st>>>(q);
   CU(cudaGetLastError());
   return MDX_OK;
 }
@@ -36,12 +38,29 @@ int launch_variant(mdx_env* e, const KParams& kp, cudaStream_t st) {
 template <int kMode, int LPE>
 int launch_lpe(mdx_env* e, const KParams& kp, cudaStream_t st, int ks) {
   const bool small = e->P <= 64;
+  if constexpr (kMode == 5) {  // step + IDQ featurisers: whole warps, plane-sliced maps only (the caller falls back to two launches)
+    if constexpr (LPE == 32) {
+      switch (ks) {
+        case 1: return small ? launch_variant<5, 32, 1, true, 0>(e, kp, st) : launch_variant<5, 32, 1, false, 0>(e, kp, st);
+        case 2: return small ? launch_variant<5, 32, 2, true, 0>(e, kp, st) : launch_variant<5, 32, 2, false, 0>(e, kp, st);
+        case 4: return small ? launch_variant<5, 32, 4, true, 0>(e, kp, st) : launch_variant<5, 32, 4, false, 0>(e, kp, st);
+        default: break;
+      }
+    }
+    return MDX_E_UNSUPPORTED_SHAPE;
+  } else {
   if (kMode == 1) return small ? launch_variant<1, LPE, 0, true, 0>(e, kp, st) : launch_variant<1, LPE, 0, false, 0>(e, kp, st);
   switch (ks) {
     case 1: return small ? launch_variant<kMode, LPE, 1, true, 0>(e, kp, st) : launch_variant<kMode, LPE, 1, false, 0>(e, kp, st);
     case 2: return small ? launch_variant<kMode, LPE, 2, true, 0>(e, kp, st) : launch_variant<kMode, LPE, 2, false, 0>(e, kp, st);
-    case 4: return small ? launch_variant<kMode, LPE, 4, true, 0>(e, kp, st) : launch_variant<kMode, LPE, 4, false, 0>(e, kp, st);
+    case 4:
+      if (small) return launch_variant<kMode, LPE, 4, true, 0>(e, kp, st);
+      // working set of > 44 KB per CTA: at most 4 CTAs/SM fit, the register cap of the 7-CTA build would only hurt
+      if (LPE == 32 && kMode != 5 && !e->no_fat && (size_t)kLutBytes + 4 * (size_t)smem_for_mode(e, kMode) > 44 * 1024)
+        return launch_variant<kMode, (LPE == 32 ? 32 : LPE), 4, false, (LPE == 32 ? 2 : 0)>(e, kp, st);
+      return launch_variant<kMode, LPE, 4, false, 0>(e, kp, st);
     default: return small ? launch_variant<kMode, LPE, 0, true, 0>(e, kp, st) : launch_variant<kMode, LPE, 0, false, 0>(e, kp, st);
+  }
   }
 }
 
@@ -59,6 +78,9 @@ int launch_env_kernel(mdx_env* e, const KParams& kp, cudaStream_t st) {
   // packing several envs into a warp lowers the warp count and lengthens each warp's dependent chain, which
   // costs more than the amortised uniform instructions save.  Whole warps are therefore the default;
   // MDX_LPE=8|16 selects the packed variants (kept and tested).
+  if constexpr (kMode == 5) {
+    return launch_lpe<kMode, 32>(e, kp, st, slices(32));
+  } else {
   int lpe = 32;
   if (e->lpe_override) lpe = std::max(e->R <= 8 ? 8 : e->R <= 16 ? 16 : 32, e->lpe_override);
   if (kMode != 1 && !e->force_generic && (HW & 3) == 0)
@@ -66,7 +88,7 @@ int launch_env_kernel(mdx_env* e, const KParams& kp, cudaStream_t st) {
   const int ks = kMode == 1 ? 0 : slices(lpe);
   // the headline MAPPO shape has a fully specialised instantiation
   const KParams& b = e->base;
-  if (kMode != 1 && lpe == 32 && ks == 1 && !e->no_fixed && !b.shaping_bfs && b.R == 5 && b.Pp8 == 56 && b.Pp16 == 64 && b.H_out == 10 && b.W_out == 10 &&
+  if ((kMode & 2) && lpe == 32 && ks == 1 && !e->no_fixed && !b.shaping_bfs && b.R == 5 && b.Pp8 == 56 && b.Pp16 == 64 && b.H_out == 10 && b.W_out == 10 &&
       b.K_o == 4 && b.K_p == 5 && b.sel_k == 5 && b.MR == 100 && b.MP == 100 && b.vec_rows_per_flush == 5 && b.stage_b == 44 &&
       b.off_sched == 0 && b.off_status == 448 && b.off_wlist == 512 && b.off_wkey == 848 && b.off_rinfo == 1072 && b.off_alist == 1392 &&
       b.off_sel == 1504 && b.off_masks == 1568 && b.off_stage == 1728 && b.key_wbits == 6)
@@ -74,6 +96,7 @@ int launch_env_kernel(mdx_env* e, const KParams& kp, cudaStream_t st) {
   if (lpe == 8) return launch_lpe<kMode, 8>(e, kp, st, ks);
   if (lpe == 16) return launch_lpe<kMode, 16>(e, kp, st, ks);
   return launch_lpe<kMode, 32>(e, kp, st, ks);
+  }
 }
 
 }  // namespace

@@ -100,6 +100,78 @@ class VectorizedEnv:
         """One fused launch per MAPPO rollout iteration (MAPPO/trainer.py:172-286 without the nets)."""
         return self.batch.step_featurize(actions, auto_reset=auto_reset, out=out, feat_out=feat_out)
 
+    def host_pipeline(self, feat_out=None, auto_reset=True):
+        """Double-buffered host <-> device stepping for callers whose actions live in HOST memory; see HostPipeline."""
+        return HostPipeline(self, feat_out=feat_out, auto_reset=auto_reset)
+
+
+class HostPipeline:
+    """`rollout_step` for actions that come from pinned HOST memory and rewards/dones that are wanted back on the host,
+    with the copies taken off the critical path: two slots of device/host staging, one copy stream per direction.
+
+        slot = pipe.submit(h_actions)      # H2D copy of step n's actions, fused launch, D2H of (shaped, done): all async
+        shaped, done = pipe.result(slot)   # numpy views of the pinned result buffers, valid until the slot is reused
+
+    While step n runs on the GPU, the copy of step n+1's actions and the read-back of step n-1's results are in flight, so
+    a step costs one kernel.  Feature tensors stay in HBM (`feat_out`, where the policy / critic read them on the launch
+    stream).  Results are the same as calling `rollout_step` step by step (tests/test_gpu_next.py)."""
+
+    def __init__(self, ve, feat_out=None, auto_reset=True):
+        b = ve.batch
+        self.batch, self.auto_reset = b, auto_reset
+        n, R, dev = b.n_envs, b.n_robots, b.device
+        self.n = n
+        self.feat = feat_out if feat_out is not None else b.alloc_features(n)
+        self.main = torch.cuda.current_stream(dev)
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.d_act = [torch.empty((n, R), dtype=torch.uint8, device=dev) for _ in range(2)]
+        # [shaped f32 | done u8] share one allocation per slot: one D2H copy per step
+        self.d_sd = [torch.empty(5 * n, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.d_rew = torch.empty(n, dtype=torch.float64, device=dev)
+        self.h_sd = [torch.empty(5 * n, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_k = [torch.cuda.Event() for _ in range(2)]
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        self.used = [False, False]
+        self.count = 0
+
+    def submit(self, h_actions):
+        """h_actions: uint8 [n, R] action codes in (preferably pinned) host memory.  Returns the slot to pass to result()."""
+        s = self.count & 1
+        self.count += 1
+        n = self.n
+        if self.used[s]:
+            self.ev_out[s].synchronize()          # the host buffers of this slot have been filled (and read by the caller)
+            self.s_in.wait_event(self.ev_k[s])    # the kernel that read d_act[s] two steps ago is done
+        with torch.cuda.stream(self.s_in):
+            self.d_act[s].copy_(h_actions, non_blocking=True)
+            self.ev_in[s].record(self.s_in)
+        self.main.wait_event(self.ev_in[s])
+        if self.used[s]:
+            self.main.wait_event(self.ev_out[s])  # d_sd[s] has been read back
+        with torch.cuda.stream(self.main):
+            out = (self.d_rew, self.d_sd[s][:4 * n].view(torch.float32), self.d_sd[s][4 * n:])
+            self.batch.step_featurize(self.d_act[s], auto_reset=self.auto_reset, out=out, feat_out=self.feat)
+            self.ev_k[s].record(self.main)
+        self.s_out.wait_event(self.ev_k[s])
+        with torch.cuda.stream(self.s_out):
+            self.h_sd[s].copy_(self.d_sd[s], non_blocking=True)
+            self.ev_out[s].record(self.s_out)
+        self.used[s] = True
+        return s
+
+    def result(self, slot):
+        """Blocks until step `slot`'s results are on the host -> (shaped float32 [n], done uint8 [n]) numpy views."""
+        self.ev_out[slot].synchronize()
+        h = self.h_sd[slot].numpy()
+        return h[:4 * self.n].view(np.float32), h[4 * self.n:]
+
+    def drain(self):
+        """Make the launch stream wait for every outstanding copy (call before timing / reusing the buffers elsewhere)."""
+        for s in range(2):
+            if self.used[s]:
+                self.main.wait_event(self.ev_out[s])
+
 
 class _EnvList:
     """`.envs` of the reference is a list of Environment objects; here the per-env views are created on

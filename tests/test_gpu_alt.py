@@ -96,6 +96,39 @@ def test_alt_random_sweep_vs_oracle(maps, R, P, T):
                 assert np.count_nonzero(o6[n]) == np.count_nonzero(want6) and np.count_nonzero(g7[n]) == np.count_nonzero(alt.legacy_global_tensor(e, snap))  # padding stays zero
 
 
+@pytest.mark.parametrize("maps,R,P,T", [(["map1.txt"], 5, 50, 40), (["map.txt"], 6, 20, 30), (["map5.txt"], 32, 200, 45),
+                                        (["map1.txt", "map3.txt", "map5.txt"], 9, 80, 35), (["map5.txt"], 2, 3, 25)])
+@pytest.mark.parametrize("unfused", [False, True])
+def test_idq_fused_iteration_equals_two_launches(maps, R, P, T, unfused, monkeypatch):
+    """mdx_step_idq_featurize (ONE launch: step + per-agent shaping + auto-reset + convert_state x R + 7-channel tensor) against
+    mdx_step_idq followed by mdx_featurize_alt on a twin batch; map.txt (7x7: planes are not whole float4s) and
+    MDX_IDQ_UNFUSED=1 exercise the internal two-launch fallback.  The unfused pair is the one checked against the oracle above."""
+    if unfused:
+        monkeypatch.setenv("MDX_IDQ_UNFUSED", "1")
+    N = 40
+    kw = dict(map_file=maps if len(maps) > 1 else maps[0], n_robots=R, n_packages=P, max_time_steps=T, seed=77)
+    a_, b_ = mdb.VectorizedEnv(mdb.Environment, N, **kw).batch, mdb.VectorizedEnv(mdb.Environment, N, **kw).batch
+    for x in (a_, b_):
+        x.reset()
+        x.prefetch(3)
+    rs = np.random.RandomState(9)
+    ids = torch.tensor([3, 0, 17, 39, 8], dtype=torch.int32)
+    for s in range(2 * T + 7):
+        sub = s % 11 == 5  # now and then only a subset of the envs steps (QMIX-style indices)
+        n = len(ids) if sub else N
+        a = rs.randint(0, 15, size=(n, R)).astype(np.uint8)
+        if s % 3 == 0:
+            a = (a % 5 + 5).astype(np.uint8)
+        kws = dict(ids=ids if sub else None, auto_reset=True, ops_as_int=bool(s & 1))
+        r1, g1, d1, o1, t1 = a_.step_idq_featurize(torch.from_numpy(a), **kws)
+        r2, g2, d2 = b_.step_idq(torch.from_numpy(a), **kws)
+        o2, t2 = b_.featurize_alt(ids=ids if sub else None)
+        assert torch.equal(r1, r2) and torch.equal(g1, g2) and torch.equal(d1, d2), s
+        assert torch.equal(o1, o2) and torch.equal(t1, t2), s
+    assert torch.equal(a_.episode_stats(), b_.episode_stats())
+    assert torch.equal(a_.state_dict(), b_.state_dict())
+
+
 def _tracker_of(env):
     return {p.package_id: {"id": p.package_id, "start_pos": p.start, "target_pos": p.target, "start_time": p.start_time,
                            "deadline": p.deadline, "status": p.status}

@@ -208,9 +208,15 @@ def test_int64_policy_actions_equal_action_codes():
             assert torch.equal(p, q), s
 
 
-@pytest.mark.parametrize("T,N", [(1, 1), (7, 3), (500, 5), (64, 4097), (500, 65536)])
-def test_gae_matches_torch_reference(T, N):
-    """MAPPO/trainer.py:288-301.  Tolerance 1e-6 relative as the stated bar; equality is what holds."""
+@pytest.mark.parametrize("no_tma", [False, True])
+@pytest.mark.parametrize("T,N", [(1, 1), (7, 3), (500, 5), (64, 4097), (500, 65536), (1, 16), (3, 128), (10, 144), (41, 1040), (39, 4096),
+                                 (127, 2064)])
+def test_gae_matches_torch_reference(T, N, no_tma, monkeypatch):
+    """MAPPO/trainer.py:288-301.  Tolerance 1e-6 relative as the stated bar; equality is what holds.  N % 16 == 0 takes the
+    bulk-async-copy (TMA) kernel -- ragged last CTAs (144, 1040, 2064 columns), T shorter than / not a multiple of the stage
+    depth -- everything else, and MDX_GAE_NO_TMA=1, the register kernel."""
+    if no_tma:
+        monkeypatch.setenv("MDX_GAE_NO_TMA", "1")
     g = torch.Generator().manual_seed(T * 131 + N)
     rew = torch.randn(T, N, generator=g) * 3
     val = torch.randn(T, N, generator=g)
@@ -305,3 +311,39 @@ def test_collect_rollouts_matches_trainer_loop():
     wadv, wret = orc.gae_reference(buf.rewards.cpu(), buf.values.cpu(), buf.dones.cpu(), value(buf.global_states[K], buf.global_vector[K]).cpu(), 0.99, 0.95)
     assert torch.equal(b_adv.cpu(), wadv.reshape(K * N, 1).repeat(1, R).reshape(-1)) and torch.equal(b_ret.cpu(), wret.reshape(-1))
     assert torch.equal(b_lp, (buf.vector_obs[:K, :, :, 0] - 1.0).reshape(-1))
+
+
+def test_host_pipeline_equals_synchronous_rollout_steps():
+    """VectorizedEnv.host_pipeline(): host actions in, (shaped, done) out, copies overlapped with the kernel -- every
+    step's results and the final features / episode statistics equal the step-by-step rollout_step() on the same actions,
+    and both equal the oracle."""
+    N, R, P, T_env, K = 64, 5, 50, 20, 50
+    kw = dict(map_file="map1.txt", n_robots=R, n_packages=P, max_time_steps=T_env, seed=123, k_others=R - 1, k_packages=5)
+    va, vb = mdb.VectorizedEnv(mdb.Environment, N, **kw), mdb.VectorizedEnv(mdb.Environment, N, **kw)
+    for v in (va, vb):
+        v.batch.reset()
+        v.batch.prefetch(3)
+    ov = orc.OracleVecEnv(N, mdb.maps.stock_map("map1.txt"), seed=123, max_time_steps=T_env, n_robots=R, n_packages=P)
+    ov.reset()
+    acts = np.random.RandomState(5).randint(0, 15, size=(K, N, R)).astype(np.uint8)
+    h_acts = torch.from_numpy(acts).pin_memory()
+    pipe = va.host_pipeline()
+    got, prev = [], None
+    for t in range(K):
+        slot = pipe.submit(h_acts[t])
+        if prev is not None:
+            sh, dn = pipe.result(prev)
+            got.append((sh.copy(), dn.copy()))
+        prev = slot
+    sh, dn = pipe.result(prev)
+    got.append((sh.copy(), dn.copy()))
+    pipe.drain()
+    torch.cuda.synchronize()
+    for t in range(K):
+        _, wsh, wdn, *wfeat = vb.rollout_step(torch.from_numpy(acts[t]))
+        osh, odn, *ofeat = orc.mappo_rollout_step(ov, acts[t], R - 1, 5)
+        assert np.array_equal(_bits(got[t][0]), _bits(wsh.cpu().numpy())) and np.array_equal(got[t][1], wdn.cpu().numpy()), t
+        assert np.array_equal(_bits(got[t][0]), _bits(osh)) and np.array_equal(got[t][1].astype(bool), odn), t
+    for x, w, o in zip(pipe.feat, wfeat, ofeat):
+        assert torch.equal(x, w) and np.array_equal(_bits(x.cpu().numpy()), _bits(o))
+    assert torch.equal(va.batch.episode_stats(), vb.batch.episode_stats())
