@@ -120,6 +120,39 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
+def _cpu_worker_c(args):
+    """The same rollout iteration through the C restatement (oracle/oracle.c, one call per step for the worker's envs)."""
+    seed, n_envs, n_steps, wl = args
+    import importlib.util
+
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_c import COracleVec  # ctypes binding of oracle/liboracle.so (test infrastructure)
+
+    spec = importlib.util.spec_from_file_location("_mdx_maps", os.path.join(ROOT, "marl-delivery_b200", "maps.py"))
+    maps = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(maps)
+    grid = maps.stock_map(wl["maps"][0])
+    consts = [5.0, 200.0, 20.0, 0.02, 0.0, 0.0, -0.05, -0.05, -0.01]  # MAPPO/helper.py:268-278
+    vec = COracleVec(n_envs, grid, wl["T"], wl["R"], wl["P"], seed, wl["K_o"], wl["K_p"], wl["MR"], wl["MP"], consts)
+    vec.reset()
+    acts = np.random.RandomState(seed).randint(0, 15, size=(n_steps, n_envs, wl["R"])).astype(np.uint8)
+    t0 = time.perf_counter()
+    for s in range(n_steps):
+        vec.rollout_step(acts[s], features=wl["feat"])
+    return time.perf_counter() - t0
+
+
+def cpu_arm_c(n_envs_per_core, n_steps, cores=None):
+    cores = cores or os.cpu_count() or 1
+    jobs = [(BASE_SEED + 1000 * k, n_envs_per_core, n_steps, WL) for k in range(cores)]
+    with mp.get_context("fork").Pool(cores) as pool:
+        times = pool.map(_cpu_worker_c, jobs)
+    wall = max(times)
+    return cores * n_envs_per_core * n_steps / wall, cores, wall
+
+
 def cpu_arm(n_envs_per_core, n_steps, cores=None):
     """-> (env-steps/s over all cores, cores, seconds).  Every core runs an independent shard of the
     same workload (the reference's VectorizedEnv is a sequential loop; shards are how it would use
@@ -441,6 +474,14 @@ def gpu_arm(args):
         line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                 "sample": f"{cores} processes x {args.cpu_envs} envs x {args.cpu_steps} steps of the same "
                                           f"workload (oracle/oracle_env.py), {wall:.1f} s wall"}
+        if len(wl["maps"]) == 1 and kind == "path":
+            # the same work through the C restatement: what a compiled CPU implementation of the path would do
+            try:
+                vc, cc, wc = cpu_arm_c(64, 2000 if feat_on else 20000)
+                line["cpu_baseline_c"] = {"value": vc, "unit": "env-steps/s", "cores": cc, "kind": "port (C restatement, oracle/oracle.c)",
+                                          "sample": f"{cc} processes x 64 envs x {2000 if feat_on else 20000} steps, {wc:.1f} s wall"}
+            except Exception as ex:  # the C oracle is optional test infrastructure
+                line["cpu_baseline_c"] = {"unavailable": str(ex)[:200]}
     print(json.dumps(line))
 
 

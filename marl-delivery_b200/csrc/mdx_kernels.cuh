@@ -41,7 +41,8 @@ namespace mdx {
 #define MDX_FIX_BLOCKS 9   // shape-specialised variant (kFix = 1)
 #endif
 #ifndef MDX_FAT_BLOCKS
-#define MDX_FAT_BLOCKS 4   // big-environment variant (kFix = 2): shared memory already limits it to <= 4 CTAs/SM, so registers are free
+#define MDX_FAT_BLOCKS 5   // big-plane variant (kFix = 2): 96 registers.  Measured: C4 45.1 (4) / 47.9 (5) / 47.2 (6) vs 45.8 M env-steps/s
+                           // for the 7-CTA build; C5 (shared memory allows 4 CTAs/SM) 13.6 / 13.7 / 13.8 vs 13.1 M
 #endif
 #ifndef MDX_FIX_THREADS
 #define MDX_FIX_THREADS 128  // CTA size of the shape-specialised variant (one warp per env)
@@ -1135,9 +1136,10 @@ __device__ __forceinline__ void featurize_alt_env(const KParams& p, const Env& w
 // ------------------------------------------------------------------------------------------------
 // kMode bit 0: step (+ shaped reward, + optional auto-reset);  bit 1: featurise (MAPPO);  bit 2: featurise (IDQ / legacy, whole warps only).
 // LPE lanes per environment: a 128-thread CTA holds 128 / LPE environments.
-// kFix: 2 = like 0, compiled without the register cap of the 7-CTAs/SM variants, for environments whose shared-memory working set
-// allows <= 4 CTAs/SM anyway (C5: 32 robots, 500 packages): the compiler then keeps several LDS.128 -> STG.128 pairs in flight
-// per warp instead of recycling one register quad.
+// kFix: 2 = like 0, compiled with a looser register cap (5 CTAs/SM instead of 7) for the four-slice planes with long package lists
+// (C4, C5: 20x20 maps, > 64 packages), whose time goes into the plane stores: with registers to spare the compiler keeps six
+// LDS.128 -> STG.128 pairs in flight per warp instead of recycling one register quad (ncu: the capped build stalls on the
+// write-after-read of that quad).
 // kFix: shape specialisation.  0 = every shape parameter is read from KParams at run time; 1 = the
 // headline MAPPO shape (C3: map1 10x10, 5 robots, <= 56 packages, K_o = 4, K_p = 5, MR = MP = 100) is baked
 // in as compile-time constants, so loops over robots / planes / rows unroll and the index arithmetic folds.

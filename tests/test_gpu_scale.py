@@ -167,3 +167,29 @@ def test_c3_full_size_properties_and_shard_independence():
                 assert np.array_equal(gs_[k], wg) and np.array_equal(_bits(gvs_[k]), _bits(wgv)), (s, k)
     tot = full.batch.episode_stats() - lo.batch.episode_stats() - hi.batch.episode_stats()
     assert bool((tot == 0).all())  # the int64 counters all-reduce exactly
+
+
+def test_step_only_large_batch_packs_four_envs_per_warp(monkeypatch):
+    """Step-only launches of >= 32 768 environments with <= 8 robots run four environments per warp (8-lane groups); the
+    results must not depend on that choice: a twin batch forced to one warp per environment (MDX_LPE=32) gives the same
+    rewards, shaped rewards, dones, statistics and final state, bit for bit, over whole episodes with auto-reset."""
+    N, R, P, T = 32768, 5, 50, 25
+    kw = dict(map_file="map1.txt", n_robots=R, n_packages=P, max_time_steps=T, seed=4242, k_others=R - 1, k_packages=5)
+    packed = mdb.VectorizedEnv(mdb.Environment, N, **kw).batch
+    monkeypatch.setenv("MDX_LPE", "32")
+    whole = mdb.VectorizedEnv(mdb.Environment, N, **kw).batch
+    monkeypatch.delenv("MDX_LPE")
+    for b in (packed, whole):
+        b.reset()
+        b.prefetch(3)
+    gen = torch.Generator(device="cuda").manual_seed(99)
+    for s in range(2 * T + 5):
+        a = torch.randint(0, 15, (N, R), dtype=torch.uint8, device="cuda", generator=gen)
+        if s % 4 == 0:
+            a = a % 5 + 5
+        r1, s1, d1 = packed.step(a, auto_reset=True)
+        r2, s2, d2 = whole.step(a, auto_reset=True)
+        assert torch.equal(r1, r2) and torch.equal(s1.view(torch.int32), s2.view(torch.int32)) and torch.equal(d1, d2), s
+    assert torch.equal(packed.episode_stats(), whole.episode_stats())
+    assert int(packed.episode_stats()[0]) == 2 * N and int(packed.episode_stats()[7]) == 0
+    assert torch.equal(packed.state_dict(), whole.state_dict())
