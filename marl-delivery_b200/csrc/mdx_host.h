@@ -41,7 +41,8 @@ struct MapHost {
 };
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
-inline uint32_t magic(uint32_t d) { return (uint32_t)((0x100000000ull + d - 1) / d); }
+// multiplier for x / d as __umulhi(x, magic(d)); d == 1 is encoded as 0 (div_magic in the kernels), d >= 2 is exact for x < 2^32 / d
+inline uint32_t magic(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ull + d - 1) / d); }
 
 template <typename F>
 void parallel_for(int n, int n_threads, F&& fn) {

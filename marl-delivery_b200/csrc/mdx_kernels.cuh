@@ -71,6 +71,10 @@ struct Grp {
   __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(mask, v, src, LPE); }  // src is group-relative
 };
 
+// x / d through the host-built multiplier ceil(2^32 / d); d == 1 has no 32-bit multiplier and is encoded as 0
+// (one robot, or one selection slot per robot).
+__device__ __forceinline__ uint32_t div_magic(uint32_t x, uint32_t m) { return m ? __umulhi(x, m) : x; }
+
 struct Env {
   uint16_t *start, *target, *t0, *dl;  // [Pp8] current episode schedule
   uint8_t* status;                     // [Pp16]
@@ -619,12 +623,12 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
     const int nsel = min(Ksel, nw);
     const int rpf = p.vec_rows_per_flush;
     // lanes as (robot, other) pairs for the stable sort of the other robots
-    const int gi = (int)__umulhi((uint32_t)sl, p.mul_r), gj = sl - gi * R;
-    const int G = (int)__umulhi((uint32_t)LPE, p.mul_r);  // robots per pass = LPE / R
+    const int gi = (int)div_magic((uint32_t)sl, p.mul_r), gj = sl - gi * R;
+    const int G = (int)div_magic((uint32_t)LPE, p.mul_r);  // robots per pass = LPE / R
     // winners of the package selection are kept in lanes when a robot's slots fit the group
     const bool lane_sel = kSmall && Ksel <= LPE;
-    const int RP = lane_sel ? (int)__umulhi((uint32_t)LPE, p.mul_ksel) : 1;  // robots per pass = LPE / Ksel
-    const int sel_ii = (int)__umulhi((uint32_t)sl, p.mul_ksel), sel_q = sl - sel_ii * Ksel;
+    const int RP = lane_sel ? (int)div_magic((uint32_t)LPE, p.mul_ksel) : 1;  // robots per pass = LPE / Ksel
+    const int sel_ii = (int)div_magic((uint32_t)sl, p.mul_ksel), sel_q = sl - sel_ii * Ksel;
 #pragma unroll 1
     for (int i0 = 0; i0 < R; i0 += rpf) {
       const int nrows = min(rpf, R - i0);
@@ -633,6 +637,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
       zero_stage<LPE>(w.stage, nrows * D + 4, sl);
       g.sync();
       float* chunk = w.stage + off;
+      float* pk_base = chunk + 6 + K_o * 5;  // first package slot of the first staged row
       // own block (:93-112) and global time (:163)
       if (sl >= i0 && sl < i0 + nrows) {
         float* rowp = chunk + (sl - i0) * D;
@@ -763,7 +768,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
           const uint32_t rc = w.wrc[k];
           const uint32_t tc_ = w.target[j];
           const int tr = (int)__umulhi(tc_, p.mul_wout), tcol = (int)tc_ - tr * Wo;
-          float* o = chunk + sel_ii * D + 6 + K_o * 5 + sel_q * 5;
+          float* o = pk_base + sel_ii * D + sel_q * 5;
           o[0] = __ldg(qr + ((int)(rc >> 8) - ri + Hm1));
           o[1] = __ldg(qc + ((int)(rc & 255u) - ci + Wm1));
           o[2] = __ldg(qr + (tr - ri + Hm1));
@@ -811,7 +816,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
             const uint32_t rc = w.wrc[k];
             const uint32_t tc_ = w.target[j];
             const int tr = (int)__umulhi(tc_, p.mul_wout), tcol = (int)tc_ - tr * Wo;
-            float* o = chunk + (ib - i0 + sel_ii) * D + 6 + K_o * 5 + sel_q * 5;
+            float* o = pk_base + (ib - i0 + sel_ii) * D + sel_q * 5;
             o[0] = __ldg(qr + ((int)(rc >> 8) - ri + Hm1));
             o[1] = __ldg(qc + ((int)(rc & 255u) - ci + Wm1));
             o[2] = __ldg(qr + (tr - ri + Hm1));
@@ -845,7 +850,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
               const uint32_t rc = w.wrc[k];
               const uint32_t tc_ = w.target[j];
               const int tr = (int)__umulhi(tc_, p.mul_wout), tcol = (int)tc_ - tr * Wo;
-              float* o = chunk + (i - i0) * D + 6 + K_o * 5 + pos * 5;
+              float* o = pk_base + (i - i0) * D + pos * 5;
               o[0] = __ldg(qr + ((int)(rc >> 8) - ri + Hm1));
               o[1] = __ldg(qc + ((int)(rc & 255u) - ci + Wm1));
               o[2] = __ldg(qr + (tr - ri + Hm1));
@@ -890,7 +895,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
         const int nslot = nrows * Ksel;
 #pragma unroll 1
         for (int x = sl; x < nslot; x += LPE) {
-          const int ii = (int)__umulhi((uint32_t)x, p.mul_ksel), q = x - ii * Ksel;
+          const int ii = (int)div_magic((uint32_t)x, p.mul_ksel), q = x - ii * Ksel;
           if (q < nsel) {
             const uint32_t rci = w.rrc[i0 + ii];
             const int ri = (int)(rci >> 8), ci = (int)(rci & 255u);
@@ -899,7 +904,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
             const uint32_t rc = w.wrc[k];
             const uint32_t tc_ = w.target[j];
             const int tr = (int)__umulhi(tc_, p.mul_wout), tcol = (int)tc_ - tr * Wo;
-            float* o = chunk + ii * D + 6 + K_o * 5 + q * 5;
+            float* o = pk_base + ii * D + q * 5;
             o[0] = __ldg(qr + ((int)(rc >> 8) - ri + Hm1));
             o[1] = __ldg(qc + ((int)(rc & 255u) - ci + Wm1));
             o[2] = __ldg(qr + (tr - ri + Hm1));
@@ -939,7 +944,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
         const int nslot = nrows * Ksel;
 #pragma unroll 1
         for (int x = sl; x < nslot; x += LPE) {
-          const int ii = (int)__umulhi((uint32_t)x, p.mul_ksel), q = x - ii * Ksel;
+          const int ii = (int)div_magic((uint32_t)x, p.mul_ksel), q = x - ii * Ksel;
           if (q < nsel) {
             const uint32_t rci = w.rrc[i0 + ii];
             const int ri = (int)(rci >> 8), ci = (int)(rci & 255u);
@@ -948,7 +953,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
             const uint32_t rc = w.wrc[k];
             const uint32_t tc_ = w.target[j];
             const int tr = (int)__umulhi(tc_, p.mul_wout), tcol = (int)tc_ - tr * Wo;
-            float* o = chunk + ii * D + 6 + K_o * 5 + q * 5;
+            float* o = pk_base + ii * D + q * 5;
             o[0] = __ldg(qr + ((int)(rc >> 8) - ri + Hm1));
             o[1] = __ldg(qc + ((int)(rc & 255u) - ci + Wm1));
             o[2] = __ldg(qr + (tr - ri + Hm1));

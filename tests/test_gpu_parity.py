@@ -428,3 +428,37 @@ def test_lanes_per_env_variants_match_golden(name, lpe, monkeypatch):
                 assert np.array_equal(g[i], z["gstate"][fi].astype(np.float32)), (step, i)
                 assert np.array_equal(_bits(gv[i]), _bits(z["gvec"][fi])), (step, i)
             fi += 1
+
+
+@pytest.mark.parametrize("name,R,P,T,K_o,K_p,MR,MP", [
+    ("map1.txt", 1, 1, 1, 0, 1, 1, 1),          # smallest everything: one robot, one package, one step per episode
+    ("map1.txt", 1, 0, 5, 0, 3, 2, 2),          # no packages at all: `all delivered` holds vacuously, done at every step
+    ("map5.txt", 3, 80, 30, 2, 8, 5, 30),       # long list, > 5 slots: shared-memory key array path
+    ("map2.txt", 2, 120, 40, 1, 3, 3, 10),      # long list, <= 5 slots: register top-k path, no key array
+    ("map3.txt", 4, 100, 30, 100, 100, 100, 100),  # K = 100 defaults on a long list: rank-count path
+    ("map5.txt", 32, 64, 20, 31, 5, 32, 64),    # full warp of robots, list that just fits the lane-held selection
+    ("map4.txt", 8, 65, 25, 7, 6, 8, 65),       # first size past the 64-package register path
+])
+def test_edge_shapes_against_oracle(name, R, P, T, K_o, K_p, MR, MP):
+    """Shapes at the edges of every selection / staging path of the featuriser, fused auto-reset launch vs the oracle,
+    every step, every tensor, bit for bit."""
+    grid = mdb.maps.stock_map(name)
+    N = 5
+    ve = orc.OracleVecEnv(N, grid, seed=77, max_time_steps=T, n_robots=R, n_packages=P)
+    ve.reset()
+    b = mdb.DeliveryBatch([grid], N, R, P, T, base_seed=77, k_others=K_o, k_packages=K_p, max_robots_in_state=MR,
+                          max_packages_in_state=MP, ring_episodes=8)
+    b.reset()
+    rs = np.random.RandomState(3)
+    for s in range(2 * T + 3):
+        if s % max(1, 3 * T) == 0 or T < 6:
+            b.prefetch(6)
+        a = rs.randint(0, 15, size=(N, R)).astype(np.uint8)
+        if s % 3 == 1:
+            a = (a % 5 + 5).astype(np.uint8)  # everybody tries to pick up
+        wsh, wd, wo, wv, wg, wgv = orc.mappo_rollout_step(ve, a, K_o, K_p, MR, MP)
+        r, sh, d, o, v, g, gv = b.step_featurize(torch.from_numpy(a), auto_reset=True)
+        assert np.array_equal(_bits(sh.cpu().numpy()), _bits(wsh)) and np.array_equal(d.cpu().numpy().astype(bool), wd), s
+        assert np.array_equal(o.cpu().numpy(), wo) and np.array_equal(g.cpu().numpy(), wg), s
+        assert np.array_equal(_bits(v.cpu().numpy()), _bits(wv)) and np.array_equal(_bits(gv.cpu().numpy()), _bits(wgv)), s
+    assert int(b.episode_stats().cpu()[7]) == 0
