@@ -584,7 +584,7 @@ static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int
   kp.actions = d_actions;
   kp.env_ids = d_env_ids;
   kp.n = n;
-  kp.flags = flags;
+  kp.flags = flags & 3u;
   kp.out_reward = d_reward;
   kp.out_shaped = d_shaped;
   kp.out_done = d_done;

@@ -1238,7 +1238,17 @@ __global__ void __launch_bounds__((kFix == 1 && (kMode & 2)) ? MDX_FIX_THREADS :
     }
     total0 = p.total_reward[env];
   }
-  load_episode<LPE>(p, w, env, sl);
+  // first block of the schedule into registers with the other state loads, then the uses
+  const uint4* ep_src = reinterpret_cast<const uint4*>(p.cur + (size_t)env * 4 * p.Pp8);
+  const int n_ep16 = p.Pp8 >> 1;
+  uint4 ep0 = make_uint4(0u, 0u, 0u, 0u);
+  if (sl < n_ep16) ep0 = __ldg(ep_src + sl);
+  {
+    uint4* dst = reinterpret_cast<uint4*>(w.start);
+    if (sl < n_ep16) dst[sl] = ep0;
+#pragma unroll 1
+    for (int i = sl + LPE; i < n_ep16; i += LPE) dst[i] = __ldg(ep_src + i);
+  }
   {
     uint4* dst = reinterpret_cast<uint4*>(w.status);
     if (sl < n_st16) dst[sl] = st0;
