@@ -107,6 +107,7 @@ class DeliveryBatch:
         self.ring_episodes = d.ring_episodes
         self.shaping = tuple(float(x) for x in shaping)
         self._bufs = {}
+        self._ok_out = {}  # id(tuple) -> tuple of caller-owned output tensors that passed _check_out
         self._version = 0  # bumped by every call that changes env state (invalidates EnvView snapshots)
         self._grid_lists = [g.tolist() for g in self.grids]
 
@@ -132,6 +133,40 @@ class DeliveryBatch:
             t = torch.empty(shape, dtype=dtype, device=self.device)
             self._bufs[key] = t
         return t
+
+    def _check_out(self, tensors, specs):
+        """Caller-owned output tensors are written by the kernels without further checks, so a wrong device, dtype,
+        size or a non-contiguous view must be refused here (None = output not wanted).  A tuple that passed once is
+        remembered by identity: steady-state loops that reuse their buffers pay nothing."""
+        key = id(tensors)
+        if self._ok_out.get(key) is tensors:  # (only tuples are remembered: their members cannot be swapped)
+            return
+        if len(tensors) != len(specs):
+            raise ValueError(f"expected {len(specs)} output tensors, got {len(tensors)}")
+        for t, (name, numel, dtype) in zip(tensors, specs):
+            if t is None:
+                continue
+            if not isinstance(t, torch.Tensor) or not t.is_cuda or t.device != self.device:
+                raise ValueError(f"output '{name}' must be a CUDA tensor on {self.device}")
+            if t.dtype != dtype or t.numel() != numel or not t.is_contiguous():
+                raise ValueError(f"output '{name}' must be a contiguous {dtype} tensor of {numel} elements "
+                                 f"(got {t.dtype}, {t.numel()} elements, contiguous={t.is_contiguous()})")
+        if isinstance(tensors, tuple):
+            if len(self._ok_out) > 64:
+                self._ok_out.clear()
+            self._ok_out[key] = tensors
+
+    def _rsd_specs(self, n, second):
+        return (("reward", n, torch.float64), second, ("done", n, torch.uint8))
+
+    def _feat_specs(self, n):
+        R, HW = self.n_robots, self.rows_out * self.cols_out
+        return (("obs", n * R * 6 * HW, torch.float32), ("vec", n * R * self.vec_dim, torch.float32),
+                ("gstate", n * 4 * HW, torch.float32), ("gvec", n * self.gvec_dim, torch.float32))
+
+    def _alt_specs(self, n):
+        R, HW = self.n_robots, self.rows_out * self.cols_out
+        return (("obs6", n * R * 6 * HW, torch.float32), ("gstate7", n * 7 * HW, torch.float32))
 
     def _ids(self, ids):
         """-> (device int32 tensor or None, host list or None, n)"""
@@ -186,6 +221,7 @@ class DeliveryBatch:
             shaped = self._buf("shaped", (n,), torch.float32) if want_shaped else None
             done = self._buf("done", (n,), torch.uint8)
         else:
+            self._check_out(out, self._rsd_specs(n, ("shaped", n, torch.float32)))
             reward, shaped, done = out
         _lib.check(self._L.mdx_step(self._h, _ptr(actions), _ptr(d_ids), n, _ptr(reward), _ptr(shaped), _ptr(done),
                                     (MDX_F_AUTO_RESET if auto_reset else 0) | aflags, self._stream()))
@@ -201,6 +237,7 @@ class DeliveryBatch:
 
     def _feat_out(self, n, out):
         if out is not None:
+            self._check_out(out, self._feat_specs(n))
             return out
         key = ("feat", n)
         if key not in self._bufs:
@@ -224,6 +261,7 @@ class DeliveryBatch:
             shaped = self._buf("shaped", (n,), torch.float32)
             done = self._buf("done", (n,), torch.uint8)
         else:
+            self._check_out(out, self._rsd_specs(n, ("shaped", n, torch.float32)))
             reward, shaped, done = out
         obs, vec, gstate, gvec = self._feat_out(n, feat_out)
         _lib.check(self._L.mdx_step_featurize(self._h, _ptr(actions), _ptr(d_ids), n, _ptr(reward), _ptr(shaped),
@@ -254,6 +292,8 @@ class DeliveryBatch:
         d_ids, _, n = self._ids(ids)
         if out is None:
             out = torch.empty((n, self.n_robots), dtype=torch.uint8, device=self.device)
+        else:
+            self._check_out((out,), (("actions", n * self.n_robots, torch.uint8),))
         _lib.check(self._L.mdx_greedy_actions(self._h, _ptr(d_ids), n, _ptr(out), self._stream()))
         return out
 
@@ -265,6 +305,8 @@ class DeliveryBatch:
         if out is None:
             out = (self._buf("obs6", (n, R, 6, H, W), torch.float32) if obs6 else None,
                    self._buf("gstate7", (n, 7, H, W), torch.float32) if gstate7 else None)
+        else:
+            self._check_out(out, self._alt_specs(n))
         _lib.check(self._L.mdx_featurize_alt(self._h, _ptr(d_ids), n, _ptr(out[0]), _ptr(out[1]), self._stream()))
         return out
 
@@ -276,6 +318,8 @@ class DeliveryBatch:
         if out is None:
             out = (self._buf("reward", (n,), torch.float64), self._buf("agent_rewards", (n, self.n_robots), torch.float64),
                    self._buf("done", (n,), torch.uint8))
+        else:
+            self._check_out(out, self._rsd_specs(n, ("agent_rewards", n * self.n_robots, torch.float64)))
         reward, agent, done = out
         _lib.check(self._L.mdx_step_idq(self._h, _ptr(actions), _ptr(d_ids), n, _ptr(reward), _ptr(agent), _ptr(done),
                                         1 if ops_as_int else 0, (MDX_F_AUTO_RESET if auto_reset else 0) | aflags, self._stream()))
@@ -290,10 +334,14 @@ class DeliveryBatch:
         if out is None:
             out = (self._buf("reward", (n,), torch.float64), self._buf("agent_rewards", (n, self.n_robots), torch.float64),
                    self._buf("done", (n,), torch.uint8))
+        else:
+            self._check_out(out, self._rsd_specs(n, ("agent_rewards", n * self.n_robots, torch.float64)))
         reward, agent, done = out
         R, H, W = self.n_robots, self.rows_out, self.cols_out
         if feat_out is None:
             feat_out = (self._buf("obs6", (n, R, 6, H, W), torch.float32), self._buf("gstate7", (n, 7, H, W), torch.float32))
+        else:
+            self._check_out(feat_out, self._alt_specs(n))
         _lib.check(self._L.mdx_step_idq_featurize(self._h, _ptr(actions), _ptr(d_ids), n, _ptr(reward), _ptr(agent), _ptr(done),
                                                   _ptr(feat_out[0]), _ptr(feat_out[1]), 1 if ops_as_int else 0,
                                                   (MDX_F_AUTO_RESET if auto_reset else 0) | aflags, self._stream()))

@@ -129,6 +129,7 @@ class HostPipeline:
         self.d_sd = [torch.empty(5 * n, dtype=torch.uint8, device=dev) for _ in range(2)]
         self.d_rew = torch.empty(n, dtype=torch.float64, device=dev)
         self.h_sd = [torch.empty(5 * n, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.outs = [(self.d_rew, d[:4 * n].view(torch.float32), d[4 * n:]) for d in self.d_sd]  # (reward, shaped, done) per slot
         self.ev_in = [torch.cuda.Event() for _ in range(2)]
         self.ev_k = [torch.cuda.Event() for _ in range(2)]
         self.ev_out = [torch.cuda.Event() for _ in range(2)]
@@ -150,8 +151,7 @@ class HostPipeline:
         if self.used[s]:
             self.main.wait_event(self.ev_out[s])  # d_sd[s] has been read back
         with torch.cuda.stream(self.main):
-            out = (self.d_rew, self.d_sd[s][:4 * n].view(torch.float32), self.d_sd[s][4 * n:])
-            self.batch.step_featurize(self.d_act[s], auto_reset=self.auto_reset, out=out, feat_out=self.feat)
+            self.batch.step_featurize(self.d_act[s], auto_reset=self.auto_reset, out=self.outs[s], feat_out=self.feat)
             self.ev_k[s].record(self.main)
         self.s_out.wait_event(self.ev_k[s])
         with torch.cuda.stream(self.s_out):
