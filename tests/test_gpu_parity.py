@@ -462,3 +462,25 @@ def test_edge_shapes_against_oracle(name, R, P, T, K_o, K_p, MR, MP):
         assert np.array_equal(o.cpu().numpy(), wo) and np.array_equal(g.cpu().numpy(), wg), s
         assert np.array_equal(_bits(v.cpu().numpy()), _bits(wv)) and np.array_equal(_bits(gv.cpu().numpy()), _bits(wgv)), s
     assert int(b.episode_stats().cpu()[7]) == 0
+
+
+def test_caller_owned_outputs_are_validated():
+    """A wrong dtype / size / layout of a caller-owned output tensor is refused before any kernel writes it."""
+    b = mdb.DeliveryBatch([mdb.maps.stock_map("map1.txt")], 8, 5, 20, 50, base_seed=3, k_others=4, k_packages=5)
+    b.reset()
+    a = torch.zeros((8, 5), dtype=torch.uint8, device="cuda")
+    good = (torch.empty(8, dtype=torch.float64, device="cuda"), torch.empty(8, dtype=torch.float32, device="cuda"),
+            torch.empty(8, dtype=torch.uint8, device="cuda"))
+    b.step(a, out=good)
+    with pytest.raises(ValueError):
+        b.step(a, out=(good[0], torch.empty(8, dtype=torch.float64, device="cuda"), good[2]))  # shaped must be float32
+    with pytest.raises(ValueError):
+        b.step(a, out=(good[0], good[1], torch.empty(7, dtype=torch.uint8, device="cuda")))  # too short
+    with pytest.raises(ValueError):
+        b.step(a, out=(good[0], good[1], torch.empty(8, dtype=torch.uint8)))  # host tensor
+    feat = b.alloc_features(8)
+    with pytest.raises(ValueError):
+        b.featurize(out=(feat[0][:, :, :, :, :5], feat[1], feat[2], feat[3]))  # wrong size and not contiguous
+    with pytest.raises(ValueError):
+        b.featurize(out=(feat[0].transpose(3, 4), feat[1], feat[2], feat[3]))  # right size, not contiguous
+    b.featurize(out=feat)

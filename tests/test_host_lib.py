@@ -159,3 +159,22 @@ def test_stock_maps():
     assert int((mdb.maps.stock_map("map.txt") == 0).sum()) == 25
     txt = "1 1 1\n1 0 1\n1 1 1"  # no trailing newline, like map4/map5
     assert mdb.maps.parse_map_text(txt).tolist() == [[1, 1, 1], [1, 0, 1], [1, 1, 1]]
+
+
+def test_output_tensor_validation_refuses_host_tensors():
+    """DeliveryBatch._check_out guards every kernel that writes caller-owned tensors; without a GPU its refusals can
+    still be exercised on a bare instance."""
+    import torch
+
+    import marl_delivery_b200 as mdb
+
+    b = mdb.DeliveryBatch.__new__(mdb.DeliveryBatch)
+    b.device = torch.device("cuda", 0)
+    b._ok_out = {}
+    specs = (("reward", 4, torch.float64), ("shaped", 4, torch.float32), ("done", 4, torch.uint8))
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        b._check_out((torch.zeros(4, dtype=torch.float64), None, None), specs)
+    with pytest.raises(ValueError, match="expected 3 output tensors"):
+        b._check_out((None, None), specs)
+    b._check_out((None, None, None), specs)  # outputs that are not wanted are fine
+    b.__dict__.clear()  # nothing to close
