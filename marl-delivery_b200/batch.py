@@ -37,6 +37,9 @@ def encode_action(move, pkg_act) -> int:
     return mv + 5 * op
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -124,6 +127,9 @@ class DeliveryBatch:
             pass
 
     def _stream(self):
+        """The caller's current stream on this device (every kernel is enqueued there)."""
+        if _raw_stream is not None:  # the handle without building a torch.cuda.Stream object (a few microseconds per launch)
+            return C.c_void_p(_raw_stream(self.device.index))
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _buf(self, name, shape, dtype):
