@@ -63,7 +63,6 @@ def main():
 
     buffers = None
     for it in range(args.iters):
-        b.prefetch(min(b.ring_episodes - 1, args.steps // 500 + 2))  # keep future episodes ready for the on-device auto-reset
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         out = collect_rollouts(vec_env, policy, critic, args.steps, gamma=0.99, gae_lambda=0.95, buffers=buffers, fresh=buffers is None)

@@ -11,7 +11,8 @@
  *
  * Each function names the reference interface (paths relative to nguyenduchuyiu/marl-delivery) it
  * replaces.  One mdx_env owns the state of `n_envs` environments on ONE device; it is not
- * thread-safe.  The host sampler (mdx_sampler_*) is re-entrant and needs no GPU.
+ * thread-safe.  The host restatement of the reset sampler (mdx_sampler_*, what the device sampler is
+ * pinned against) is re-entrant and needs no GPU.
  *
  * Encodings
  *   cell        : r * W_out + c in the (possibly padded) output plane, 0-based; W_out = max map width
@@ -30,19 +31,20 @@
 extern "C" {
 #endif
 
-#define MDX_VERSION 1
+#define MDX_VERSION 2
 #define MDX_MAX_ROBOTS 32 /* one warp per environment, robots are lanes */
 
 enum {
   MDX_OK = 0,
   MDX_E_INVALID = -1, /* bad argument / unsupported configuration (ValueError in the Python mirror) */
   MDX_E_CUDA = -2,    /* CUDA runtime failure */
-  MDX_E_STARVED = -3, /* on-device auto-reset ran out of pre-sampled episodes */
+  MDX_E_STARVED = -3, /* (v1 only: the pre-sampled episode ring ran dry; cannot happen since v2) */
   MDX_E_NOMEM = -4
 };
 
 /* flags for mdx_step / mdx_step_featurize */
-#define MDX_F_AUTO_RESET 1u /* done envs advance to their next pre-sampled episode inside the kernel   \
+#define MDX_F_AUTO_RESET 1u /* done envs reset inside the kernel: the lane group that owns the env draws its next    \
+                               reset block from the env's MT19937 stream in HBM and applies it                     \
                                (MAPPO/trainer.py:229-234: reset, then featurise the reset state) */
 #define MDX_F_ACTIONS_I64 2u /* d_actions is int64 [n, n_robots]: the policy's raw samples a in [0, 15), decoded   \
                                 in the kernel like MAPPO/trainer.py:195-204 (move a % 5 in sorted LabelEncoder order, \
@@ -84,8 +86,8 @@ typedef struct mdx_config {
   const int64_t* env_seed;       /* [n_envs] RandomState seed per env; NULL = base_seed + i */
   int64_t base_seed;             /* env i uses seed base_seed + i  (MAPPO/env_vectorized.py:7-9) */
   int32_t device;                /* CUDA ordinal */
-  int32_t ring_episodes;         /* depth E of the per-env pre-sampled episode ring, >= 2 */
-  int32_t sampler_threads;       /* host threads for reset sampling, 0 = hardware concurrency */
+  int32_t ring_episodes;         /* ignored since v2 (v1: depth of the host-fed ring of pre-sampled episodes) */
+  int32_t sampler_threads;       /* ignored since v2 (v1: host threads for reset sampling) */
   int32_t flags;                 /* MDX_CFG_* */
 } mdx_config;
 
@@ -95,7 +97,7 @@ typedef struct mdx_dims {
   int32_t vec_dim;            /* 6 + 5*k_others + 5*k_packages + 1 */
   int32_t gvec_dim;           /* 6*max_robots_in_state + 7*max_packages_in_state + 1 */
   int64_t bytes_per_env_step; /* 4*(R*6*H*W + R*D + 4*H*W + Dg) + 4 + 1 + R */
-  int32_t ring_episodes;
+  int32_t ring_episodes;      /* 0 since v2 */
   int32_t reserved;
 } mdx_dims;
 
@@ -132,13 +134,16 @@ int32_t mdx_destroy(mdx_env* env);
 int32_t mdx_get_dims(const mdx_env* env, mdx_dims* out);
 
 /* Environment.reset / VectorizedEnv.reset(indices) (env.py:81-125, QMIX/env_vectorized.py:13-22):
- * every listed env (HOST int32 ids, NULL = all) advances to its next reset block, drawn on the host
- * from the env's own MT19937 stream in the reference's draw order.  Synchronises `stream` once (it
- * has to read how many blocks on-device auto-resets consumed). */
+ * every listed env (HOST int32 ids, NULL = all) advances to its next reset block, drawn ON THE DEVICE
+ * from the env's own numpy-legacy MT19937 stream (624 state words per env in HBM) in the reference's
+ * draw order (env.py:96-123, 150-170): robots from the shrinking row-major free list, then per package
+ * start, target != start, deadline slack, start_time; stable sort by start_time.  Enqueued on `stream`,
+ * no host synchronisation.  An env listed k times is reset k times. */
 int32_t mdx_reset(mdx_env* env, const int32_t* h_env_ids, int32_t n, void* stream);
 
-/* Pre-sample and upload reset blocks so that every env has `episodes_ahead` blocks beyond its current
- * one in the ring (needed before stepping with MDX_F_AUTO_RESET).  Synchronises `stream` once. */
+/* v1 pre-sampled reset blocks on the host into a per-env ring and this call refilled it.  Since v2 an
+ * env draws its next block on the device at the moment it resets (mdx_reset, MDX_F_AUTO_RESET), so there
+ * is nothing to prefetch and an env can never starve: kept as a no-op for v1 callers. */
 int32_t mdx_prefetch(mdx_env* env, int32_t episodes_ahead, void* stream);
 
 /* Environment.step / VectorizedEnv.step(actions, indices) (env.py:173-306,
@@ -148,6 +153,14 @@ int32_t mdx_prefetch(mdx_env* env, int32_t episodes_ahead, void* stream);
  * d_done [n] u8.  Rows follow the order of d_env_ids. */
 int32_t mdx_step(mdx_env* env, const uint8_t* d_actions, const int32_t* d_env_ids, int32_t n,
                  double* d_reward, float* d_shaped, uint8_t* d_done, uint32_t flags, void* stream);
+
+/* n_steps consecutive mdx_step calls over ALL envs in one C call (the trainers' hot loops call vec_env.step once per
+ * step: MAPPO/trainer.py:208, QMIX/trainer.py:435): step s reads d_actions[s] ([n_steps, n_envs, n_robots]) and writes
+ * row s of d_reward / d_shaped / d_done ([n_steps, n_envs], each may be NULL).  For launch-bound batches (a few
+ * thousand envs, kernel ~7 us) this removes the per-step host overhead of the binding; the call only enqueues, so it can
+ * also be captured into a CUDA graph by the caller (VectorizedEnv.rollout_graph does). */
+int32_t mdx_step_n(mdx_env* env, const uint8_t* d_actions, int32_t n_steps, double* d_reward, float* d_shaped,
+                   uint8_t* d_done, uint32_t flags, void* stream);
 
 /* convert_observation / generate_vector_features / convert_global_state for every listed env and
  * every robot (MAPPO/helper.py:6-255), written straight into the caller's tensors:
@@ -173,6 +186,30 @@ int32_t mdx_shaped_reward(mdx_env* env, const uint32_t* d_cur_robots, const int3
 int32_t mdx_get_state(mdx_env* env, int32_t env_id, mdx_state_view* out, void* stream);
 /* State injection for hand-built cases (Group-Project.pdf worked example, helper drop-ins). */
 int32_t mdx_set_state(mdx_env* env, int32_t env_id, const mdx_state_view* in, void* stream);
+
+/* The same for many envs at once, as packed rows (what the dict drop-ins VectorizedEnv.reset / .step and the per-call helper
+ * functions use: ONE launch + ONE copy + ONE synchronisation per call instead of one round trip per field and env).
+ * A row is mdx_state_row_bytes() bytes of little-endian 4-byte words:
+ *   [0] t  [1] episode  [2] map id  [3] 0  [4..5] total_reward (f64)
+ *   [6 .. 6+R)                      robots: cell | carried id << 16
+ *   [S .. S+2*Pp8), S = 6+R rounded up to 2:  schedule u16 [4][Pp8] = start cell, target cell, start_time, deadline by
+ *                                   package id, Pp8 = max(8, P rounded up to 8); padding start_time = 0xFFFF
+ *   [S+2*Pp8 .. +Pp16/4)            status u8 [Pp16], Pp16 = max(16, P rounded up to 16)
+ * padded to a multiple of 4 words.  h_env_ids: HOST ids, NULL = all envs (n = n_envs).
+ * mdx_get_states returns when the rows are in h_rows (it synchronises `stream` once). */
+int64_t mdx_state_row_bytes(const mdx_env* env);
+int32_t mdx_get_states(mdx_env* env, const int32_t* h_env_ids, int32_t n, void* h_rows, void* stream);
+/* Rows are validated on the host like mdx_set_state (time 0..65534, robots on free, pairwise distinct cells as
+ * Environment.add_robot demands (env.py:73-79), known carried ids, packages inside the map), then written with one
+ * asynchronous copy + one kernel.  Episode cursor, map id and generator state are not touched. */
+int32_t mdx_set_states(mdx_env* env, const int32_t* h_env_ids, int32_t n, const void* h_rows, void* stream);
+
+/* Environment.step / VectorizedEnv.step(actions, indices) for callers whose actions and results live in HOST memory
+ * (env.py:173-306 behind the reference's list/dict API): one H2D copy of the action codes [n, n_robots], the step
+ * kernel, a packed snapshot of the stepped envs, ONE copy back and ONE synchronisation.  h_reward [n] f64, h_shaped [n]
+ * f32 (NULL: the shaped reward is not evaluated), h_done [n] u8 and h_rows [n rows] may each be NULL. */
+int32_t mdx_step_host(mdx_env* env, const uint8_t* h_actions, const int32_t* h_env_ids, int32_t n, double* h_reward,
+                      float* h_shaped, uint8_t* h_done, void* h_rows, uint32_t flags, void* stream);
 
 /* d_out8 [8] int64 = {episodes_done, robot_moves, on_time, late, pickups,
  * env_steps, sum_episode_len, starved_envs} summed over this instance's envs (cumulative since
@@ -231,8 +268,10 @@ int32_t mdx_gae(const float* d_rewards, const float* d_values, const uint8_t* d_
                 void* stream);
 
 /* Env-state checkpointing (the reference checkpoints only network weights, MAPPO/helper.py:371-389): the
- * complete state of the instance -- device arrays, episode ring, counters, greedy bookkeeping and every
- * env's MT19937 stream position -- as one host blob.  A loaded instance continues bit-identically. */
+ * complete state of the instance -- device arrays, counters, greedy bookkeeping and every env's MT19937
+ * state -- as one host blob.  A loaded instance continues bit-identically.  The header carries the shape and a
+ * hash of the maps, env -> map assignment, rewards, shaping constants and feature sizes; a blob that does not
+ * match, or is corrupt, is refused BEFORE anything is written (the instance stays as it was). */
 int64_t mdx_checkpoint_bytes(const mdx_env* env);
 int32_t mdx_checkpoint_save(mdx_env* env, void* h_buf, int64_t bytes, void* stream);
 int32_t mdx_checkpoint_load(mdx_env* env, const void* h_buf, int64_t bytes, void* stream);

@@ -80,6 +80,11 @@ SYMBOLS = {
     "mdx_get_state": (C.c_int32, [_VP, C.c_int32, C.POINTER(StateView), _VP]),
     "mdx_set_state": (C.c_int32, [_VP, C.c_int32, C.POINTER(StateView), _VP]),
     "mdx_episode_stats": (C.c_int32, [_VP, _VP, _VP]),
+    "mdx_step_n": (C.c_int32, [_VP, _VP, C.c_int32, _VP, _VP, _VP, C.c_uint32, _VP]),
+    "mdx_state_row_bytes": (C.c_int64, [_VP]),
+    "mdx_get_states": (C.c_int32, [_VP, _VP, C.c_int32, _VP, _VP]),
+    "mdx_set_states": (C.c_int32, [_VP, _VP, C.c_int32, _VP, _VP]),
+    "mdx_step_host": (C.c_int32, [_VP, _VP, _VP, C.c_int32, _VP, _VP, _VP, _VP, C.c_uint32, _VP]),
     "mdx_greedy_actions": (C.c_int32, [_VP, _VP, C.c_int32, _VP, _VP]),
     "mdx_bfs_table": (C.c_int32, [_VP, C.c_int32, C.POINTER(C.c_uint16)]),
     "mdx_featurize_alt": (C.c_int32, [_VP, _VP, C.c_int32, _VP, _VP, _VP]),

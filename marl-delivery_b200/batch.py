@@ -41,7 +41,8 @@ _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 
 def _ptr(t: Optional[torch.Tensor]):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    """Device address as a plain int (ctypes converts it to void*; no c_void_p object per argument)."""
+    return None if t is None else t.data_ptr()
 
 
 class DeliveryBatch:
@@ -51,8 +52,10 @@ class DeliveryBatch:
                  max_time_steps: int = 100, move_cost: float = -0.01, delivery_reward: float = 10.0,
                  delay_reward: float = 1.0, seeds=None, base_seed: int = 2025, env_map=None,
                  k_others: int = 100, k_packages: int = 100, max_robots_in_state: int = 100,
-                 max_packages_in_state: int = 100, shaping=MAPPO_SHAPING, device=None, ring_episodes: int = 4,
-                 sampler_threads: int = 0, blank: bool = False, bfs_shaping: bool = False):
+                 max_packages_in_state: int = 100, shaping=MAPPO_SHAPING, device=None, ring_episodes=None,
+                 sampler_threads=None, blank: bool = False, bfs_shaping: bool = False):
+        """`ring_episodes` / `sampler_threads` are accepted and ignored (v1 pre-sampled reset blocks on the host into a ring;
+        since v2 every env draws its next reset block on the device, from its own MT19937 stream, when it resets)."""
         L = _lib.lib()
         if not torch.cuda.is_available():
             raise _lib.MdxError("no CUDA device: marl-delivery_b200 runs on the GPU only (no CPU fallback)")
@@ -95,8 +98,7 @@ class DeliveryBatch:
             keep.append(sd)
         cfg.base_seed = int(base_seed)
         cfg.device = int(self.device.index)
-        cfg.ring_episodes = int(ring_episodes)
-        cfg.sampler_threads = int(sampler_threads)
+        cfg.ring_episodes, cfg.sampler_threads = 0, 0
         cfg.flags = (_lib.MDX_CFG_BLANK if blank else 0) | (_lib.MDX_CFG_BFS_SHAPING if bfs_shaping else 0)
         handle = C.c_void_p()
         _lib.check(L.mdx_create(C.byref(cfg), C.byref(handle)))
@@ -107,12 +109,22 @@ class DeliveryBatch:
         self.n_envs, self.n_robots, self.n_packages, self.max_time_steps = d.n_envs, d.n_robots, d.n_packages, d.max_time_steps
         self.rows_out, self.cols_out, self.vec_dim, self.gvec_dim = d.rows_out, d.cols_out, d.vec_dim, d.gvec_dim
         self.bytes_per_env_step = int(d.bytes_per_env_step)
-        self.ring_episodes = d.ring_episodes
         self.shaping = tuple(float(x) for x in shaping)
+        self._dev_index = int(self.device.index)
         self._bufs = {}
-        self._ok_out = {}  # id(tuple) -> tuple of caller-owned output tensors that passed _check_out
+        self._ok_out = {}
+        self._ok_ids = {}  # validated device id tensors, keyed by (identity, version)  # id(tuple) -> tuple of caller-owned output tensors that passed _check_out
         self._version = 0  # bumped by every call that changes env state (invalidates EnvView snapshots)
         self._grid_lists = [g.tolist() for g in self.grids]
+        # packed state rows (include/mdx.h: mdx_get_states): one structured numpy record per env
+        R, P = self.n_robots, self.n_packages
+        Pp8, Pp16 = max(8, (P + 7) // 8 * 8), max(16, (P + 15) // 16 * 16)
+        off_sched = 4 * ((6 + R + 1) // 2 * 2)
+        self._row_bytes = int(L.mdx_state_row_bytes(self._h))
+        self._row_dtype = np.dtype({"names": ["t", "episode", "map_id", "total_reward", "robots", "sched", "status"],
+                                    "formats": ["<i4", "<i4", "<i4", "<f8", ("<u4", (R,)), ("<u2", (4, Pp8)), ("u1", (Pp16,))],
+                                    "offsets": [0, 4, 8, 16, 24, off_sched, off_sched + 8 * Pp8], "itemsize": self._row_bytes})
+        self._host = {}  # n -> reusable host arrays of the packed-row entry points
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -129,8 +141,8 @@ class DeliveryBatch:
     def _stream(self):
         """The caller's current stream on this device (every kernel is enqueued there)."""
         if _raw_stream is not None:  # the handle without building a torch.cuda.Stream object (a few microseconds per launch)
-            return C.c_void_p(_raw_stream(self.device.index))
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            return _raw_stream(self._dev_index) or None
+        return torch.cuda.current_stream(self.device).cuda_stream or None
 
     def _buf(self, name, shape, dtype):
         key = (name, tuple(shape), dtype)
@@ -145,8 +157,9 @@ class DeliveryBatch:
         size or a non-contiguous view must be refused here (None = output not wanted).  A tuple that passed once is
         remembered by identity: steady-state loops that reuse their buffers pay nothing."""
         key = id(tensors)
-        if self._ok_out.get(key) is tensors:  # (only tuples are remembered: their members cannot be swapped)
-            return
+        hit = self._ok_out.get(key)
+        if hit is not None and hit[0] is tensors:  # (only tuples are remembered: their members cannot be swapped)
+            return hit[1]
         if len(tensors) != len(specs):
             raise ValueError(f"expected {len(specs)} output tensors, got {len(tensors)}")
         for t, (name, numel, dtype) in zip(tensors, specs):
@@ -157,10 +170,12 @@ class DeliveryBatch:
             if t.dtype != dtype or t.numel() != numel or not t.is_contiguous():
                 raise ValueError(f"output '{name}' must be a contiguous {dtype} tensor of {numel} elements "
                                  f"(got {t.dtype}, {t.numel()} elements, contiguous={t.is_contiguous()})")
+        ptrs = tuple(None if t is None else t.data_ptr() for t in tensors)
         if isinstance(tensors, tuple):
             if len(self._ok_out) > 64:
                 self._ok_out.clear()
-            self._ok_out[key] = tensors
+            self._ok_out[key] = (tensors, ptrs)  # the tuple keeps its tensors (and so their addresses) alive
+        return ptrs
 
     def _rsd_specs(self, n, second):
         return (("reward", n, torch.float64), second, ("done", n, torch.uint8))
@@ -174,17 +189,32 @@ class DeliveryBatch:
         R, HW = self.n_robots, self.rows_out * self.cols_out
         return (("obs6", n * R * 6 * HW, torch.float32), ("gstate7", n * 7 * HW, torch.float32))
 
-    def _ids(self, ids):
-        """-> (device int32 tensor or None, host list or None, n)"""
+    def _ids(self, ids, unique=True):
+        """-> (device int32 tensor or None, host list or None, n).  Ids must be in range and pairwise distinct (two lane
+        groups stepping one env in the same launch would race; the reference would step it twice in sequence).  Host
+        lists are checked here; a device tensor is checked on the device ONCE per (tensor, version) -- one small
+        synchronous read the first time an ids tensor is used, nothing afterwards unless it is modified in place."""
         if ids is None:
             return None, None, self.n_envs
         if isinstance(ids, torch.Tensor):
             d = ids.to(device=self.device, dtype=torch.int32).contiguous()
+            key = (id(ids), ids._version, ids.data_ptr(), int(ids.numel()), unique)
+            if self._ok_ids.get(key) is not ids:
+                n = int(d.numel())
+                if n and (int(d.min()) < 0 or int(d.max()) >= self.n_envs):
+                    raise IndexError("env index out of range")
+                if unique and n > 1 and int(torch.unique(d).numel()) != n:
+                    raise ValueError("an env index is listed twice")
+                if len(self._ok_ids) > 64:
+                    self._ok_ids.clear()
+                self._ok_ids[key] = ids
             return d, None, int(d.numel())
         h = [int(i) for i in ids]
         for i in h:
             if not 0 <= i < self.n_envs:
                 raise IndexError(f"env index {i} out of range")
+        if unique and len(set(h)) != len(h):
+            raise ValueError("an env index is listed twice")
         return torch.tensor(h, dtype=torch.int32, device=self.device), h, len(h)
 
     # ------------------------------------------------------------------ reset / prefetch
@@ -198,14 +228,19 @@ class DeliveryBatch:
         _lib.check(self._L.mdx_reset(self._h, h.ctypes.data_as(C.POINTER(C.c_int32)), int(h.size), self._stream()))
         self._version += 1
 
-    def prefetch(self, episodes_ahead: int):
-        """Pre-sample reset blocks for on-device auto-reset (at most ring_episodes - 1 ahead)."""
+    def prefetch(self, episodes_ahead: int = 0):
+        """No-op kept for v1 callers: reset blocks are no longer pre-sampled on the host -- an env that finishes under
+        `auto_reset` draws its next block on the device right inside the step kernel, so it can never starve."""
         _lib.check(self._L.mdx_prefetch(self._h, int(episodes_ahead), self._stream()))
 
     # ------------------------------------------------------------------ step
     def _check_actions(self, actions, n):
         """-> (device tensor, flag bits).  uint8 action codes are used as they are; an int64 tensor is taken
         to be the policy's raw samples (mb_actions of MAPPO/trainer.py:193) and decoded inside the kernel."""
+        if (actions.__class__ is torch.Tensor and actions.dtype is torch.uint8 and actions.is_cuda and actions.is_contiguous()
+                and actions.dim() == 2 and actions.shape[0] == n and actions.shape[1] == self.n_robots
+                and actions.get_device() == self._dev_index):
+            return actions, 0  # the steady-state case: device-resident action codes of the right shape
         if not isinstance(actions, torch.Tensor):
             actions = torch.as_tensor(np.asarray(actions, dtype=np.uint8))
         flags = 0
@@ -219,20 +254,48 @@ class DeliveryBatch:
         return actions, flags
 
     def step(self, actions, ids=None, auto_reset: bool = False, want_shaped: bool = True, out=None):
-        """-> (reward f64 [n], shaped f32 [n] or None, done u8 [n]); rows follow `ids`."""
-        d_ids, _, n = self._ids(ids)
+        """-> (reward f64 [n], shaped f32 [n] or None, done u8 [n]); rows follow `ids`.
+
+        With `out=None` the returned tensors are buffers OWNED BY THIS INSTANCE and shared between step(), step_idq() and
+        step_featurize(): they are valid until the next call of any of them.  Pass `out=(reward, shaped, done)` (a tuple
+        of caller-owned CUDA tensors; validated once, then remembered by identity) to keep results across steps."""
+        if ids is None:
+            d_ids, n = None, self.n_envs
+        else:
+            d_ids, _, n = self._ids(ids)
         actions, aflags = self._check_actions(actions, n)
         if out is None:
             reward = self._buf("reward", (n,), torch.float64)
             shaped = self._buf("shaped", (n,), torch.float32) if want_shaped else None
             done = self._buf("done", (n,), torch.uint8)
+            p_r, p_s, p_d = reward.data_ptr(), (None if shaped is None else shaped.data_ptr()), done.data_ptr()
         else:
-            self._check_out(out, self._rsd_specs(n, ("shaped", n, torch.float32)))
+            p_r, p_s, p_d = self._check_out(out, self._rsd_specs(n, ("shaped", n, torch.float32)))
             reward, shaped, done = out
-        _lib.check(self._L.mdx_step(self._h, _ptr(actions), _ptr(d_ids), n, _ptr(reward), _ptr(shaped), _ptr(done),
-                                    (MDX_F_AUTO_RESET if auto_reset else 0) | aflags, self._stream()))
+        rc = self._L.mdx_step(self._h, actions.data_ptr(), _ptr(d_ids), n, p_r, p_s, p_d,
+                              (MDX_F_AUTO_RESET if auto_reset else 0) | aflags, self._stream())
+        if rc:
+            _lib.check(rc)
         self._version += 1
         return reward, shaped, done
+
+    def step_n(self, actions, auto_reset: bool = True, out=None):
+        """`n_steps` consecutive step() calls over all envs in ONE C call (include/mdx.h: mdx_step_n): actions uint8
+        [n_steps, n_envs, R] on the GPU -> (reward f64, shaped f32, done u8), each [n_steps, n_envs].  For launch-bound
+        batches the per-step cost is the kernel, not the binding."""
+        if not (isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dtype == torch.uint8 and actions.is_contiguous()
+                and actions.dim() == 3 and tuple(actions.shape[1:]) == (self.n_envs, self.n_robots)):
+            raise ValueError("actions must be a contiguous uint8 CUDA tensor [n_steps, n_envs, n_robots]")
+        S, n = int(actions.shape[0]), self.n_envs
+        if out is None:
+            out = (torch.empty((S, n), dtype=torch.float64, device=self.device), torch.empty((S, n), dtype=torch.float32, device=self.device),
+                   torch.empty((S, n), dtype=torch.uint8, device=self.device))
+        p_r, p_s, p_d = self._check_out(out, (("reward", S * n, torch.float64), ("shaped", S * n, torch.float32), ("done", S * n, torch.uint8)))
+        rc = self._L.mdx_step_n(self._h, actions.data_ptr(), S, p_r, p_s, p_d, MDX_F_AUTO_RESET if auto_reset else 0, self._stream())
+        if rc:
+            _lib.check(rc)
+        self._version += 1
+        return out
 
     def alloc_features(self, n=None, obs=True, vec=True, gstate=True, gvec=True):
         n = self.n_envs if n is None else n
@@ -252,27 +315,38 @@ class DeliveryBatch:
 
     def featurize(self, ids=None, out=None):
         """-> (obs [n,R,6,H,W], vec [n,R,D], gstate [n,4,H,W], gvec [n,Dg]) float32 on the GPU."""
-        d_ids, _, n = self._ids(ids)
+        d_ids, _, n = self._ids(ids, unique=False)  # read-only: repeated ids just produce repeated rows
         obs, vec, gstate, gvec = self._feat_out(n, out)
         _lib.check(self._L.mdx_featurize(self._h, _ptr(d_ids), n, _ptr(obs), _ptr(vec), _ptr(gstate), _ptr(gvec),
                                          self._stream()))
         return obs, vec, gstate, gvec
 
     def step_featurize(self, actions, ids=None, auto_reset: bool = True, out=None, feat_out=None):
-        """One launch per MAPPO rollout iteration (MAPPO/trainer.py:172-286 minus the networks)."""
-        d_ids, _, n = self._ids(ids)
+        """One launch per MAPPO rollout iteration (MAPPO/trainer.py:172-286 minus the networks).  Like step(): with
+        `out=None` / `feat_out=None` the results live in instance-owned buffers that the next call overwrites."""
+        if ids is None:
+            d_ids, n = None, self.n_envs
+        else:
+            d_ids, _, n = self._ids(ids)
         actions, aflags = self._check_actions(actions, n)
         if out is None:
             reward = self._buf("reward", (n,), torch.float64)
             shaped = self._buf("shaped", (n,), torch.float32)
             done = self._buf("done", (n,), torch.uint8)
+            p_r, p_s, p_d = reward.data_ptr(), shaped.data_ptr(), done.data_ptr()
         else:
-            self._check_out(out, self._rsd_specs(n, ("shaped", n, torch.float32)))
+            p_r, p_s, p_d = self._check_out(out, self._rsd_specs(n, ("shaped", n, torch.float32)))
             reward, shaped, done = out
-        obs, vec, gstate, gvec = self._feat_out(n, feat_out)
-        _lib.check(self._L.mdx_step_featurize(self._h, _ptr(actions), _ptr(d_ids), n, _ptr(reward), _ptr(shaped),
-                                              _ptr(done), _ptr(obs), _ptr(vec), _ptr(gstate), _ptr(gvec),
-                                              (MDX_F_AUTO_RESET if auto_reset else 0) | aflags, self._stream()))
+        if feat_out is None:
+            feat_out = self._feat_out(n, None)
+            fp = tuple(None if t is None else t.data_ptr() for t in feat_out)
+        else:
+            fp = self._check_out(feat_out, self._feat_specs(n))
+        obs, vec, gstate, gvec = feat_out
+        rc = self._L.mdx_step_featurize(self._h, actions.data_ptr(), _ptr(d_ids), n, p_r, p_s, p_d, fp[0], fp[1], fp[2], fp[3],
+                                        (MDX_F_AUTO_RESET if auto_reset else 0) | aflags, self._stream())
+        if rc:
+            _lib.check(rc)
         self._version += 1
         return reward, shaped, done, obs, vec, gstate, gvec
 
@@ -306,7 +380,7 @@ class DeliveryBatch:
     def featurize_alt(self, ids=None, obs6=True, gstate7=True, out=None):
         """IDQ / legacy-qmix convert_state (IDQ/networks.py:112-217) for every robot and the legacy 7-channel
         global tensor (qmix/networks.py:350-468) -> (obs6 [n,R,6,H,W], gstate7 [n,7,H,W]) float32 on the GPU."""
-        d_ids, _, n = self._ids(ids)
+        d_ids, _, n = self._ids(ids, unique=False)
         R, H, W = self.n_robots, self.rows_out, self.cols_out
         if out is None:
             out = (self._buf("obs6", (n, R, 6, H, W), torch.float32) if obs6 else None,
@@ -390,19 +464,71 @@ class DeliveryBatch:
         return out
 
     # ------------------------------------------------------------------ introspection
-    def get_state(self, i: int) -> dict:
-        R, P = self.n_robots, self.n_packages
-        arr = {k: np.zeros(R, np.int32) for k in ("robot_row", "robot_col", "robot_carry")}
-        arr.update({k: np.zeros(max(P, 1), np.int32) for k in (
-            "pkg_start_row", "pkg_start_col", "pkg_target_row", "pkg_target_col", "pkg_start_time", "pkg_deadline",
-            "pkg_status")})
-        v = _lib.StateView()
-        for k, a in arr.items():
-            setattr(v, k, a.ctypes.data_as(C.POINTER(C.c_int32)))
-        _lib.check(self._L.mdx_get_state(self._h, int(i), C.byref(v), self._stream()))
-        out = {k: a[:P] if k.startswith("pkg_") else a for k, a in arr.items()}
-        out.update(t=int(v.t), episode=int(v.episode), map_id=int(v.map_id), total_reward=float(v.total_reward))
+    def _rows_to_states(self, rows):
+        """structured rows -> list of the per-env dicts EnvView reads (0-based rows / cols, int32 arrays)."""
+        P, W = self.n_packages, self.cols_out
+        out = []
+        for row in rows:
+            cell = (row["robots"] & 0xffff).astype(np.int32)
+            sched = row["sched"].astype(np.int32)
+            out.append({"t": int(row["t"]), "episode": int(row["episode"]), "map_id": int(row["map_id"]),
+                        "total_reward": float(row["total_reward"]),
+                        "robot_row": cell // W, "robot_col": cell % W, "robot_carry": (row["robots"] >> 16).astype(np.int32),
+                        "pkg_start_row": sched[0, :P] // W, "pkg_start_col": sched[0, :P] % W,
+                        "pkg_target_row": sched[1, :P] // W, "pkg_target_col": sched[1, :P] % W,
+                        "pkg_start_time": sched[2, :P], "pkg_deadline": sched[3, :P],
+                        "pkg_status": row["status"][:P].astype(np.int32)})
         return out
+
+    def get_rows(self, ids=None) -> np.ndarray:
+        """Packed snapshot of the listed envs (all when None) as a structured numpy array (fields t, episode, map_id,
+        total_reward, robots = cell | carry << 16, sched [4, Pp8] = start cell / target cell / start_time / deadline, status):
+        ONE gather launch, ONE D2H copy, ONE synchronisation for any number of envs."""
+        if ids is None:
+            h, n = None, self.n_envs
+        else:
+            h = np.ascontiguousarray(np.asarray(ids, dtype=np.int32).reshape(-1))
+            n = int(h.size)
+        rows = np.empty(n, dtype=self._row_dtype)
+        if n:
+            _lib.check(self._L.mdx_get_states(self._h, None if h is None else h.ctypes.data_as(C.c_void_p), n,
+                                              rows.ctypes.data_as(C.c_void_p), self._stream()))
+        return rows
+
+    def get_states(self, ids=None) -> list:
+        return self._rows_to_states(self.get_rows(ids))
+
+    def get_state(self, i: int) -> dict:
+        if not 0 <= int(i) < self.n_envs:
+            raise ValueError(f"env id {i} out of range")
+        return self._rows_to_states(self.get_rows([int(i)]))[0]
+
+    def time_steps_host(self, sample: int = 256) -> np.ndarray:
+        """Current time step of (a strided sample of) the envs as a host array -- one small synchronous read."""
+        ids = np.unique(np.linspace(0, self.n_envs - 1, min(sample, self.n_envs)).astype(np.int32))
+        return self.get_rows(ids)["t"].copy()
+
+    def step_host(self, codes: np.ndarray, ids=None, auto_reset: bool = False, want_rows: bool = True, want_shaped: bool = False):
+        """Environment.step for HOST callers: uint8 action codes [n, R] in, (reward f64 [n], shaped f32 [n] or None, done
+        bool [n], structured state rows or None) out -- one H2D copy, the step kernel, a packed snapshot, one copy back and
+        one synchronisation, all inside one C call (include/mdx.h: mdx_step_host)."""
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        if ids is None:
+            h, n = None, self.n_envs
+        else:
+            h = np.ascontiguousarray(np.asarray(ids, dtype=np.int32).reshape(-1))
+            n = int(h.size)
+        if codes.shape != (n, self.n_robots):
+            raise ValueError("The number of actions must match the number of robots.")  # env.py:182-183
+        reward = np.empty(n, np.float64)
+        shaped = np.empty(n, np.float32) if want_shaped else None
+        done = np.empty(n, np.uint8)
+        rows = np.empty(n, dtype=self._row_dtype) if want_rows else None
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        _lib.check(self._L.mdx_step_host(self._h, vp(codes), vp(h), n, vp(reward), vp(shaped), vp(done), vp(rows),
+                                         MDX_F_AUTO_RESET if auto_reset else 0, self._stream()))
+        self._version += 1
+        return reward, shaped, done.astype(bool), rows
 
     def set_state(self, i: int, t, total_reward, robots, packages):
         """robots: [(row, col, carry)] 0-based; packages: [(start_row, start_col, target_row, target_col,
@@ -421,9 +547,13 @@ class DeliveryBatch:
         _lib.check(self._L.mdx_set_state(self._h, int(i), C.byref(v), self._stream()))
         self._version += 1
 
-    def episode_stats(self) -> torch.Tensor:
-        """int64[8] (STAT_NAMES) summed over this instance's envs; all-reduce it across ranks."""
-        out = torch.empty(8, dtype=torch.int64, device=self.device)
+    def episode_stats(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """int64[8] (STAT_NAMES) summed over this instance's envs; all-reduce it across ranks.  `out`: a caller-owned
+        int64[8] CUDA tensor to write into (steady-state loops: no allocation)."""
+        if out is None:
+            out = torch.empty(8, dtype=torch.int64, device=self.device)
+        else:
+            self._check_out((out,), (("stats", 8, torch.int64),))
         _lib.check(self._L.mdx_episode_stats(self._h, _ptr(out), self._stream()))
         return out
 

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -20,6 +21,32 @@ using namespace mdx;
 
 namespace mdx {
 thread_local std::string g_err;
+
+int ensure_dynamic_smem(const void* func, size_t bytes, int carveout) {
+  struct Mark {
+    const void* func;
+    int device;
+    size_t bytes;
+  };
+  static std::mutex mu;
+  static std::vector<Mark> marks;
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  Mark* m = nullptr;
+  for (Mark& x : marks)
+    if (x.func == func && x.device == dev) m = &x;
+  if (m == nullptr) {
+    marks.push_back(Mark{func, dev, 0});
+    m = &marks.back();
+  }
+  if (bytes > m->bytes || m->bytes == 0) {
+    CU(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bytes, 48 * 1024)));
+    if (carveout >= 0) CU(cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+    m->bytes = std::max<size_t>(bytes, 48 * 1024);
+  }
+  return MDX_OK;
+}
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -45,75 +72,102 @@ int pick_wpb(const mdx_env* e, int smem_per_warp) {
   return wpb;
 }
 
-// Draw block `sampled[env]` for env and pack it into staging record `rec` (output-plane cells).
-bool sample_into(mdx_env* e, int env, uint16_t* rec, std::vector<int32_t>& rc, std::vector<int32_t>& pk,
-                 EpisodeSampler& scratch) {
-  const MapHost& m = e->maps[(size_t)e->env_map[(size_t)env]];
-  // `scratch` only lends its work vectors; the generator is the env's own stream
-  if (!scratch.draw(e->rng[(size_t)env], m.free_cells, m.rows, e->R, e->P, e->T, rc.data(), pk.data())) return false;
-  const int Pp8 = e->base.Pp8, P = e->P, Wo = e->W_out;
-  std::memset(rec, 0, sizeof(uint16_t) * (size_t)e->rec_u16);
-  auto oc = [&](int cell) { return (uint16_t)((cell / m.cols) * Wo + (cell % m.cols)); };
-  for (int j = 0; j < P; ++j) {
-    rec[0 * Pp8 + j] = oc(pk[(size_t)(0 * P + j)]);
-    rec[1 * Pp8 + j] = oc(pk[(size_t)(1 * P + j)]);
-    rec[2 * Pp8 + j] = (uint16_t)pk[(size_t)(2 * P + j)];
-    rec[3 * Pp8 + j] = (uint16_t)pk[(size_t)(3 * P + j)];
-  }
-  for (int j = P; j < Pp8; ++j) rec[2 * Pp8 + j] = 0xffff;  // padding never spawns
-  for (int i = 0; i < e->R; ++i) rec[4 * Pp8 + i] = oc(rc[(size_t)i]);
-  return true;
-}
-
-// Sample + upload the blocks listed in (ids[k], count[k]) pairs, at most one block per env per wave.
-// `want[env]` = number of blocks the env must have after the call.
-int top_up(mdx_env* e, const std::vector<int32_t>& envs, const std::vector<int32_t>& want, cudaStream_t st) {
-  std::vector<int32_t> todo(envs);
-  while (true) {
-    std::vector<int32_t> wave;
-    for (int32_t env : todo)
-      if (e->sampled[(size_t)env] < want[(size_t)env]) wave.push_back(env);
-    if (wave.empty()) break;
-    const int m = (int)wave.size();
-    std::vector<char> bad((size_t)e->threads + 1, 0);
-    parallel_for(m, e->threads, [&](int tid, int lo, int hi) {
-      EpisodeSampler scratch;
-      std::vector<int32_t> rc((size_t)e->R + 1), pk((size_t)4 * e->P + 1);
-      for (int k = lo; k < hi; ++k) {
-        const int env = wave[(size_t)k];
-        if (!sample_into(e, env, e->h_stage + (size_t)k * e->rec_u16, rc, pk, scratch)) bad[(size_t)tid] = 1;
-        e->h_ids[k] = env;
-        e->h_ids[e->n + k] = e->sampled[(size_t)env] % e->E;
-        e->sampled[(size_t)env] += 1;
-      }
-    });
-    for (char b : bad)
-      if (b)
-        return fail(MDX_E_INVALID,
-                    "reset sampling failed: not enough free cells for the robots/packages, or max_time_steps < 2 "
-                    "with more than min(n_robots, 20) + 1 packages (the reference raises ValueError here)");
-    CU(cudaMemcpyAsync(e->d_stage, e->h_stage, sizeof(uint16_t) * (size_t)m * e->rec_u16, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(e->d_ids, e->h_ids, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(e->d_ids + e->n, e->h_ids + e->n, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, st));
-    const size_t total = (size_t)m * (e->rec_u16 / 8);
-    mdx_upload_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(e->d_sched, e->d_sched_robots, e->d_stage, e->d_ids,
-                                                                       e->d_ids + e->n, m, e->n, e->base.Pp8);
-    CU(cudaGetLastError());
-    // the pinned staging buffers are reused by the next wave
-    CU(cudaStreamSynchronize(st));
-    todo.swap(wave);
-  }
-  // publish the new availability
-  std::memcpy(e->h_i32, e->sampled.data(), sizeof(int32_t) * (size_t)e->n);
-  CU(cudaMemcpyAsync(e->d_ep_avail, e->h_i32, sizeof(int32_t) * (size_t)e->n, cudaMemcpyHostToDevice, st));
-  CU(cudaStreamSynchronize(st));
+// Launches the device reset (draw the next block on the env's own stream, apply it) for `n` envs; d_ids == nullptr: all.
+int launch_reset(mdx_env* e, const int32_t* d_ids, int n, uint32_t advance, cudaStream_t st) {
+  KParams kp = e->base;
+  kp.env_ids = d_ids;
+  kp.n = n;
+  kp.flags = advance;
+  const size_t per_warp = (size_t)8 * e->base.Pp8;
+  int wpb = 8;
+  while (wpb > 1 && wpb * per_warp > 160 * 1024) wpb >>= 1;
+  const size_t smem = wpb * per_warp;
+  int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(mdx_reset_kernel), smem, -1);
+  if (rc != MDX_OK) return rc;
+  mdx_reset_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, smem, st>>>(kp);
+  CU(cudaGetLastError());
   return MDX_OK;
 }
 
-int refresh_ep(mdx_env* e, cudaStream_t st) {
-  CU(cudaMemcpyAsync(e->h_i32, e->d_ep, sizeof(int32_t) * (size_t)e->n, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  std::memcpy(e->ep_host.data(), e->h_i32, sizeof(int32_t) * (size_t)e->n);
+inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// Makes the pinned host buffer and its device mirror at least `bytes` large and safe to overwrite.
+int staging(mdx_env* e, size_t bytes) {
+  if (e->pin_busy == nullptr) CU(cudaEventCreateWithFlags(&e->pin_busy, cudaEventDisableTiming));
+  else CU(cudaEventSynchronize(e->pin_busy));
+  if (bytes <= e->pin_bytes) return MDX_OK;
+  size_t cap = 64 * 1024;
+  while (cap < bytes) cap <<= 1;
+  CU(cudaDeviceSynchronize());
+  cudaFree(e->d_pin);
+  cudaFreeHost(e->h_pin);
+  e->d_pin = nullptr, e->h_pin = nullptr, e->pin_bytes = 0;
+  CU(cudaMalloc(&e->d_pin, cap));
+  CU(cudaMallocHost(&e->h_pin, cap));
+  e->pin_bytes = cap;
+  return MDX_OK;
+}
+
+int check_ids(const mdx_env* e, const int32_t* h_ids, int32_t n, bool unique = false) {
+  if (n < 0) return fail(MDX_E_INVALID, "negative count");
+  if (unique && h_ids != nullptr && n > 1) {  // two lane groups working on one env in the same launch would race
+    std::vector<char> seen((size_t)e->n, 0);
+    for (int k = 0; k < n; ++k) {
+      if (h_ids[k] < 0 || h_ids[k] >= e->n) return fail(MDX_E_INVALID, "env id %d out of range", h_ids[k]);
+      if (seen[(size_t)h_ids[k]]) return fail(MDX_E_INVALID, "env id %d is listed twice", h_ids[k]);
+      seen[(size_t)h_ids[k]] = 1;
+    }
+  }
+  if (h_ids == nullptr) {
+    if (n != e->n) return fail(MDX_E_INVALID, "n must equal n_envs when env ids are not given (got %d, have %d)", n, e->n);
+    return MDX_OK;
+  }
+  for (int k = 0; k < n; ++k)
+    if (h_ids[k] < 0 || h_ids[k] >= e->n) return fail(MDX_E_INVALID, "env id %d out of range", h_ids[k]);
+  return MDX_OK;
+}
+
+RowArgs row_args(const mdx_env* e, uint32_t* d_rows, const int32_t* d_ids, int n) {
+  RowArgs a;
+  a.rows = d_rows;
+  a.ids = d_ids;
+  a.base = 0;
+  a.n = n;
+  a.row_words = e->row_words;
+  a.off_robots = e->off_robots;
+  a.off_sched = e->off_sched;
+  a.off_status = e->off_status;
+  return a;
+}
+
+// What Environment.add_robot / the package constructor would refuse, plus the ranges the u16 state can hold.
+int validate_row(const mdx_env* e, int env, const uint32_t* row) {
+  const KParams& b = e->base;
+  const MapHost& m = e->maps[(size_t)e->env_map[(size_t)env]];
+  const int Wo = e->W_out;
+  const int32_t t = (int32_t)row[0];
+  if (t < 0 || t > 65534) return fail(MDX_E_INVALID, "time step %d out of range [0, 65534]", t);
+  const long long dl_cap = std::min<long long>(65535, ((1LL << (32 - b.key_wbits)) - 2) / b.nranks_max - 1);
+  auto on_map = [&](int cell) { return cell / Wo < m.rows && cell % Wo < m.cols; };
+  for (int i = 0; i < e->R; ++i) {
+    const int cell = (int)(row[e->off_robots + i] & 0xffffu), k = (int)(row[e->off_robots + i] >> 16);
+    if (!on_map(cell)) return fail(MDX_E_INVALID, "robot %d outside the map", i);
+    // Environment.add_robot raises ValueError for an occupied or blocked cell (env.py:73-79)
+    if (m.cells[(size_t)(cell / Wo) * m.cols + cell % Wo] != 0) return fail(MDX_E_INVALID, "Invalid robot position: robot %d stands on an obstacle", i);
+    if (k > e->P) return fail(MDX_E_INVALID, "robot %d carries an unknown package id %d", i, k);
+    for (int j = 0; j < i; ++j)
+      if ((row[e->off_robots + j] & 0xffffu) == (uint32_t)cell) return fail(MDX_E_INVALID, "Invalid robot position: robots %d and %d share a cell", j, i);
+  }
+  const uint16_t* sched = reinterpret_cast<const uint16_t*>(row + e->off_sched);
+  const uint8_t* status = reinterpret_cast<const uint8_t*>(row + e->off_status);
+  for (int j = 0; j < e->P; ++j) {
+    if (!on_map(sched[j]) || !on_map(sched[b.Pp8 + j])) return fail(MDX_E_INVALID, "package %d outside the map", j + 1);
+    if (sched[2 * b.Pp8 + j] > 65534) return fail(MDX_E_INVALID, "package %d: bad start_time", j + 1);
+    if ((long long)sched[3 * b.Pp8 + j] > dl_cap) return fail(MDX_E_INVALID, "package %d: deadline out of range", j + 1);
+    if (status[j] > 3) return fail(MDX_E_INVALID, "package %d: bad status", j + 1);
+  }
+  for (int j = e->P; j < b.Pp8; ++j)
+    if (sched[2 * b.Pp8 + j] != 0xffff) return fail(MDX_E_INVALID, "padding package %d must have start_time 0xFFFF", j + 1);
   return MDX_OK;
 }
 
@@ -136,23 +190,21 @@ int32_t mdx_destroy(mdx_env* e) {
   cudaFree(e->d_blob);
   cudaFree(e->d_t);
   cudaFree(e->d_ep);
-  cudaFree(e->d_ep_avail);
+  cudaFree(e->d_mt);
+  cudaFree(e->d_mtpos);
   cudaFree(e->d_total);
   cudaFree(e->d_robots);
   cudaFree(e->d_status);
-  cudaFree(e->d_sched);
   cudaFree(e->d_cur);
-  cudaFree(e->d_sched_robots);
   cudaFree(e->d_counters);
   cudaFree(e->d_env_map);
-  cudaFree(e->d_stage);
   cudaFree(e->d_ids);
+  cudaFree(e->d_pin);
+  cudaFreeHost(e->h_pin);
+  if (e->pin_busy) cudaEventDestroy(e->pin_busy);
   cudaFree(e->d_bfs);
   cudaFree(e->d_greedy);
   cudaFree(e->d_gfree);
-  cudaFreeHost(e->h_stage);
-  cudaFreeHost(e->h_ids);
-  cudaFreeHost(e->h_i32);
   delete e;
   return MDX_OK;
 }
@@ -168,7 +220,6 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   if (cfg->n_maps <= 0 || !cfg->map_rows || !cfg->map_cols || !cfg->map_cells) return fail(MDX_E_INVALID, "at least one map is required");
   if (cfg->k_others < 0 || cfg->k_packages < 0 || cfg->max_robots_in_state < 0 || cfg->max_packages_in_state < 0)
     return fail(MDX_E_INVALID, "feature sizes must be non-negative");
-  if (cfg->ring_episodes < 2 || cfg->ring_episodes > 64) return fail(MDX_E_INVALID, "ring_episodes must be in [2, 64]");
 
   std::unique_ptr<mdx_env> e(new mdx_env());
   e->cfg = *cfg;
@@ -177,8 +228,7 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   e->R = cfg->n_robots;
   e->P = cfg->n_packages;
   e->T = cfg->max_time_steps;
-  e->E = cfg->ring_episodes;
-  e->threads = cfg->sampler_threads > 0 ? cfg->sampler_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+  e->E = 0;
   if (const char* s = getenv("MDX_WPB")) e->wpb_override = atoi(s);
   if (const char* s = getenv("MDX_GENERIC")) e->force_generic = atoi(s);
   if (const char* s = getenv("MDX_LPE")) e->lpe_override = atoi(s);
@@ -198,9 +248,16 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
     for (int i = 0; i < mh.rows * mh.cols; ++i)
       if (mh.cells[(size_t)i] == 0) mh.free_cells.push_back(i);
     if ((int)mh.free_cells.size() < e->R) return fail(MDX_E_INVALID, "map %d has fewer free cells than robots", m);
+    // where the reference's reset would raise or never return (env.py:106-116): a single free cell cannot hold a start and a
+    // different target; randint(1, T) needs T >= 2 once there are more than min(n_robots, 20) + 1 packages
+    if (e->P > 0 && mh.free_cells.size() < 2)
+      return fail(MDX_E_INVALID, "map %d: packages need at least two free cells (start != target, env.py:107-110)", m);
     Ho = std::max(Ho, mh.rows);
     Wo = std::max(Wo, mh.cols);
   }
+  if (e->P > std::min(e->R, 20) + 1 && e->T < 2 && !(cfg->flags & MDX_CFG_BLANK))
+    return fail(MDX_E_INVALID, "max_time_steps < 2 with more than min(n_robots, 20) + 1 packages: the reference raises ValueError "
+                               "in reset (randint(1, max_time_steps), env.py:116)");
   e->H_out = Ho;
   e->W_out = Wo;
   e->env_map.assign((size_t)e->n, 0);
@@ -237,12 +294,16 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   b.delivery_reward = cfg->delivery_reward;
   b.delay_reward = cfg->delay_reward;
   std::memcpy(b.shaping, &cfg->shaping, sizeof(float) * 9);
-  e->rec_u16 = 4 * b.Pp8 + 32;
+
+  e->off_robots = 6;
+  e->off_sched = round_up(6 + e->R, 2);
+  e->off_status = e->off_sched + 2 * b.Pp8;
+  e->row_words = round_up(e->off_status + b.Pp16 / 4, 4);
 
   // ---- LUTs into one host blob
   const int nqr = 2 * Ho - 1, nqc = 2 * Wo - 1;
   struct MapOff {
-    size_t grid, qr, qc, rank;
+    size_t grid, qr, qc, rank, free_cells;
   };
   std::vector<MapOff> offs((size_t)cfg->n_maps);
   std::vector<unsigned char> blob;
@@ -259,6 +320,12 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
     offs[(size_t)m].qr = reserve(sizeof(float) * (size_t)nqr);
     offs[(size_t)m].qc = reserve(sizeof(float) * (size_t)nqc);
     offs[(size_t)m].rank = reserve(sizeof(uint16_t) * (size_t)nqr * nqc);
+    offs[(size_t)m].free_cells = reserve(sizeof(uint16_t) * mh.free_cells.size());
+    {
+      uint16_t* fc = reinterpret_cast<uint16_t*>(blob.data() + offs[(size_t)m].free_cells);
+      for (size_t k = 0; k < mh.free_cells.size(); ++k)
+        fc[k] = (uint16_t)((mh.free_cells[k] / mh.cols) * Wo + (mh.free_cells[k] % mh.cols));
+    }
     uint32_t* gb = reinterpret_cast<uint32_t*>(blob.data() + offs[(size_t)m].grid);
     for (int r = 0; r < mh.rows; ++r)
       for (int c = 0; c < mh.cols; ++c)
@@ -351,15 +418,13 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   if (b.smem_per_warp > 220 * 1024)
     return fail(MDX_E_INVALID, "per-environment working set (%d bytes) exceeds shared memory", b.smem_per_warp);
 
-  // ---- seeds
-  e->rng.resize((size_t)e->n);
+  // ---- seeds (numpy: RandomState(seed) takes 0 <= seed < 2**32)
+  std::vector<uint32_t> seeds((size_t)e->n);
   for (int i = 0; i < e->n; ++i) {
     const int64_t s = cfg->env_seed ? cfg->env_seed[i] : cfg->base_seed + i;
     if (s < 0 || s > 0xFFFFFFFFll) return fail(MDX_E_INVALID, "Seed must be between 0 and 2**32 - 1");
-    e->rng[(size_t)i].seed((uint32_t)s);
+    seeds[(size_t)i] = (uint32_t)s;
   }
-  e->sampled.assign((size_t)e->n, 0);
-  e->ep_host.assign((size_t)e->n, 0);
 
   // ---- device
   int ndev = 0;
@@ -392,6 +457,9 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
       md[m].qc = reinterpret_cast<const float*>(dbase + offs[(size_t)m].qc);
       md[m].rank = reinterpret_cast<const uint16_t*>(dbase + offs[(size_t)m].rank);
       md[m].bfs = nullptr;
+      md[m].free_cells = reinterpret_cast<const uint16_t*>(dbase + offs[(size_t)m].free_cells);
+      md[m].n_free = (int32_t)e->maps[(size_t)m].free_cells.size();
+      md[m].pad2 = 0;
     }
     CUX(cudaMemcpy(raw->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     raw->d_maps = reinterpret_cast<MapDev*>(dbase + off_maps);
@@ -402,28 +470,20 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   }
   CUX(cudaMalloc(&raw->d_t, sizeof(int32_t) * n));
   CUX(cudaMalloc(&raw->d_ep, sizeof(int32_t) * n));
-  CUX(cudaMalloc(&raw->d_ep_avail, sizeof(int32_t) * n));
+  CUX(cudaMalloc(&raw->d_mt, sizeof(uint32_t) * n * 624));
+  CUX(cudaMalloc(&raw->d_mtpos, sizeof(int32_t) * n));
   CUX(cudaMalloc(&raw->d_total, sizeof(double) * n));
   CUX(cudaMalloc(&raw->d_robots, sizeof(uint32_t) * n * e->R));
   CUX(cudaMalloc(&raw->d_status, n * b.Pp16));
-  CUX(cudaMalloc(&raw->d_sched, sizeof(uint16_t) * (size_t)e->E * n * 4 * b.Pp8));
   CUX(cudaMalloc(&raw->d_cur, sizeof(uint16_t) * n * 4 * b.Pp8));
   CUX(cudaMemset(raw->d_cur, 0, sizeof(uint16_t) * n * 4 * b.Pp8));
-  CUX(cudaMalloc(&raw->d_sched_robots, sizeof(uint16_t) * (size_t)e->E * n * 32));
   CUX(cudaMalloc(&raw->d_counters, sizeof(uint32_t) * n * 8));
   CUX(cudaMalloc(&raw->d_env_map, sizeof(int32_t) * n));
-  CUX(cudaMalloc(&raw->d_stage, sizeof(uint16_t) * n * e->rec_u16));
-  CUX(cudaMalloc(&raw->d_ids, sizeof(int32_t) * 2 * n));
-  CUX(cudaMallocHost(&raw->h_stage, sizeof(uint16_t) * n * e->rec_u16));
-  CUX(cudaMallocHost(&raw->h_ids, sizeof(int32_t) * 2 * n));
-  CUX(cudaMallocHost(&raw->h_i32, sizeof(int32_t) * n));
+  CUX(cudaMalloc(&raw->d_ids, sizeof(int32_t) * n));
   CUX(cudaMemset(raw->d_t, 0, sizeof(int32_t) * n));
   CUX(cudaMemset(raw->d_ep, 0, sizeof(int32_t) * n));
-  CUX(cudaMemset(raw->d_ep_avail, 0, sizeof(int32_t) * n));
   CUX(cudaMemset(raw->d_total, 0, sizeof(double) * n));
   CUX(cudaMemset(raw->d_counters, 0, sizeof(uint32_t) * n * 8));
-  CUX(cudaMemset(raw->d_sched, 0, sizeof(uint16_t) * (size_t)e->E * n * 4 * b.Pp8));
-  CUX(cudaMemset(raw->d_sched_robots, 0, sizeof(uint16_t) * (size_t)e->E * n * 32));
   CUX(cudaMemcpy(raw->d_env_map, e->env_map.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
 #undef CUX
 #define CUX2(call)                                                   \
@@ -437,13 +497,12 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   } while (0)
   b.t = raw->d_t;
   b.ep = raw->d_ep;
-  b.ep_avail = raw->d_ep_avail;
+  b.mt = raw->d_mt;
+  b.mtpos = raw->d_mtpos;
   b.total_reward = raw->d_total;
   b.robots = raw->d_robots;
   b.status = raw->d_status;
-  b.sched = raw->d_sched;
   b.cur = raw->d_cur;
-  b.sched_robots = raw->d_sched_robots;
   b.counters = raw->d_counters;
   b.env_map = cfg->n_maps > 1 ? raw->d_env_map : nullptr;
 
@@ -457,25 +516,22 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
       return rcb;
     }
   }
+  // every env's generator: init_genrand(seed) on the device (d_ids doubles as the seed staging area)
+  CUX2(cudaMemcpy(raw->d_ids, seeds.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice));
+  mdx_seed_kernel<<<(unsigned)((e->n + 127) / 128), 128>>>(raw->d_mt, raw->d_mtpos, reinterpret_cast<const uint32_t*>(raw->d_ids), e->n);
+  CUX2(cudaGetLastError());
   if (cfg->flags & MDX_CFG_BLANK) {
-    // blank envs for state injection; their first mdx_reset draws block 0.  ep = -1 is never read
-    // by a kernel before that reset because slot arithmetic uses the sched of slot 0 (all zero).
+    // blank envs for state injection; their first mdx_reset draws block 0
+    CUX2(cudaDeviceSynchronize());
     *out = e.release();
     return MDX_OK;
   }
   // ---- the constructor's own reset (env.py:41): block 0 for every env
-  std::vector<int32_t> all((size_t)e->n), want((size_t)e->n, 1);
-  for (int i = 0; i < e->n; ++i) all[(size_t)i] = i;
-  int rc = top_up(raw, all, want, 0);
+  int rc = launch_reset(raw, nullptr, e->n, 0u, 0);
   if (rc != MDX_OK) {
     mdx_destroy(e.release());
     return rc;
   }
-  KParams kp = b;
-  kp.env_ids = nullptr;
-  kp.n = e->n;
-  kp.flags = 0;  // initialise in place (episode 0)
-  mdx_reset_kernel<<<(unsigned)((e->n + 7) / 8), 256>>>(kp);
   if (cudaDeviceSynchronize() != cudaSuccess) {
     fail(MDX_E_CUDA, "reset kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
     mdx_destroy(e.release());
@@ -497,7 +553,7 @@ int32_t mdx_get_dims(const mdx_env* e, mdx_dims* out) {
   out->vec_dim = b.D;
   out->gvec_dim = b.Dg;
   out->bytes_per_env_step = 4LL * ((long long)e->R * 6 * b.HW + (long long)e->R * b.D + 4LL * b.HW + b.Dg) + 4 + 1 + e->R;
-  out->ring_episodes = e->E;
+  out->ring_episodes = 0;
   out->reserved = 0;
   return MDX_OK;
 }
@@ -506,22 +562,13 @@ int32_t mdx_reset(mdx_env* e, const int32_t* h_env_ids, int32_t n, void* stream)
   if (!e) return fail(MDX_E_INVALID, "null env");
   DeviceGuard g(e->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  std::vector<int32_t> ids;
-  if (h_env_ids == nullptr) {
-    ids.resize((size_t)e->n);
-    for (int i = 0; i < e->n; ++i) ids[(size_t)i] = i;
-  } else {
-    if (n < 0) return fail(MDX_E_INVALID, "negative count");
-    ids.assign(h_env_ids, h_env_ids + n);
-    for (int32_t id : ids)
-      if (id < 0 || id >= e->n) return fail(MDX_E_INVALID, "env id %d out of range", id);
-  }
-  if (ids.empty()) return MDX_OK;
-  int rc = refresh_ep(e, st);
-  if (rc != MDX_OK) return rc;
-  // an env listed k times is reset k times (the reference would draw k blocks); handle one pass per
-  // repetition so that ring slots are never skipped
-  std::vector<int32_t> remaining(ids);
+  if (h_env_ids == nullptr) return launch_reset(e, nullptr, e->n, 1u, st);
+  if (n < 0) return fail(MDX_E_INVALID, "negative count");
+  for (int k = 0; k < n; ++k)
+    if (h_env_ids[k] < 0 || h_env_ids[k] >= e->n) return fail(MDX_E_INVALID, "env id %d out of range", h_env_ids[k]);
+  // an env listed k times is reset k times (the reference would draw k blocks): one launch per repetition, so that no two
+  // warps of a launch work on the same generator
+  std::vector<int32_t> remaining(h_env_ids, h_env_ids + n);
   while (!remaining.empty()) {
     std::vector<int32_t> pass, later;
     std::vector<char> seen((size_t)e->n, 0);
@@ -532,38 +579,21 @@ int32_t mdx_reset(mdx_env* e, const int32_t* h_env_ids, int32_t n, void* stream)
         pass.push_back(id);
       }
     }
-    std::vector<int32_t> want(e->sampled);
-    for (int32_t id : pass) want[(size_t)id] = std::max(want[(size_t)id], e->ep_host[(size_t)id] + 2);
-    rc = top_up(e, pass, want, st);
+    // pageable source: the copy is staged by the driver before the call returns, so `pass` may die and d_ids is reused in
+    // stream order by the next pass
+    CU(cudaMemcpyAsync(e->d_ids, pass.data(), sizeof(int32_t) * pass.size(), cudaMemcpyHostToDevice, st));
+    int rc = launch_reset(e, e->d_ids, (int)pass.size(), 1u, st);
     if (rc != MDX_OK) return rc;
-    for (size_t k = 0; k < pass.size(); ++k) e->h_ids[k] = pass[k];
-    CU(cudaMemcpyAsync(e->d_ids, e->h_ids, sizeof(int32_t) * pass.size(), cudaMemcpyHostToDevice, st));
-    KParams kp = e->base;
-    kp.env_ids = e->d_ids;
-    kp.n = (int)pass.size();
-    kp.flags = 1;
-    mdx_reset_kernel<<<(unsigned)((pass.size() + 7) / 8), 256, 0, st>>>(kp);
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(st));
-    for (int32_t id : pass) e->ep_host[(size_t)id] += 1;
     remaining.swap(later);
   }
   return MDX_OK;
 }
 
 int32_t mdx_prefetch(mdx_env* e, int32_t ahead, void* stream) {
+  (void)stream;
   if (!e) return fail(MDX_E_INVALID, "null env");
-  if (ahead < 0 || ahead > e->E - 1) return fail(MDX_E_INVALID, "episodes_ahead must be in [0, ring_episodes - 1]");
-  DeviceGuard g(e->device);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = refresh_ep(e, st);
-  if (rc != MDX_OK) return rc;
-  std::vector<int32_t> all((size_t)e->n), want((size_t)e->n);
-  for (int i = 0; i < e->n; ++i) {
-    all[(size_t)i] = i;
-    want[(size_t)i] = std::max(e->sampled[(size_t)i], e->ep_host[(size_t)i] + 1 + ahead);
-  }
-  return top_up(e, all, want, st);
+  if (ahead < 0) return fail(MDX_E_INVALID, "episodes_ahead must be non-negative");
+  return MDX_OK;  // nothing to pre-sample: reset blocks are drawn on the device at the moment an env resets
 }
 
 static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int32_t* d_env_ids, int32_t n, double* d_reward,
@@ -606,6 +636,21 @@ static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int
 int32_t mdx_step(mdx_env* e, const uint8_t* d_actions, const int32_t* d_env_ids, int32_t n, double* d_reward, float* d_shaped,
                  uint8_t* d_done, uint32_t flags, void* stream) {
   return step_common(e, 1, d_actions, d_env_ids, n, d_reward, d_shaped, d_done, nullptr, nullptr, nullptr, nullptr, flags, stream);
+}
+
+int32_t mdx_step_n(mdx_env* e, const uint8_t* d_actions, int32_t n_steps, double* d_reward, float* d_shaped, uint8_t* d_done,
+                   uint32_t flags, void* stream) {
+  if (!e) return fail(MDX_E_INVALID, "null env");
+  if (n_steps < 0) return fail(MDX_E_INVALID, "negative step count");
+  const size_t n = (size_t)e->n;
+  const size_t a_stride = n * e->R * ((flags & MDX_F_ACTIONS_I64) ? 8 : 1);
+  for (int s = 0; s < n_steps; ++s) {
+    int rc = step_common(e, 1, d_actions + (size_t)s * a_stride, nullptr, e->n, d_reward ? d_reward + (size_t)s * n : nullptr,
+                         d_shaped ? d_shaped + (size_t)s * n : nullptr, d_done ? d_done + (size_t)s * n : nullptr, nullptr, nullptr, nullptr,
+                         nullptr, flags, stream);
+    if (rc != MDX_OK) return rc;
+  }
+  return MDX_OK;
 }
 
 int32_t mdx_step_idq(mdx_env* e, const uint8_t* d_actions, const int32_t* d_env_ids, int32_t n, double* d_reward, double* d_agent_rewards,
@@ -673,50 +718,132 @@ static int shape_common(mdx_env* e, const uint32_t* d_cur_robots, const int32_t*
   const int wpb = pick_wpb(e, spw);
   kp.smem_per_warp = spw;
   const size_t smem = (size_t)kLutBytes + (size_t)wpb * spw;
-  CU(cudaFuncSetAttribute(mdx_shape_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+  {
+    int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(mdx_shape_kernel), smem, -1);
+    if (rc != MDX_OK) return rc;
+  }
   mdx_shape_kernel<<<(unsigned)((e->n + wpb - 1) / wpb), wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(kp);
   CU(cudaGetLastError());
+  return MDX_OK;
+}
+
+int64_t mdx_state_row_bytes(const mdx_env* e) { return e ? (int64_t)e->row_words * 4 : 0; }
+
+int32_t mdx_get_states(mdx_env* e, const int32_t* h_env_ids, int32_t n, void* h_rows, void* stream) {
+  if (!e || !h_rows) return fail(MDX_E_INVALID, "null argument");
+  int rc = check_ids(e, h_env_ids, n);
+  if (rc != MDX_OK) return rc;
+  if (n == 0) return MDX_OK;
+  DeviceGuard g(e->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t ids_bytes = h_env_ids ? up16(sizeof(int32_t) * (size_t)n) : 0, rows_bytes = (size_t)n * e->row_words * 4;
+  if ((rc = staging(e, ids_bytes + rows_bytes)) != MDX_OK) return rc;
+  RowArgs a = row_args(e, reinterpret_cast<uint32_t*>(e->d_pin + ids_bytes), nullptr, n);
+  if (h_env_ids != nullptr) {
+    if (n == 1) {
+      a.base = h_env_ids[0];  // one env: its id travels in the kernel parameters
+    } else {
+      std::memcpy(e->h_pin, h_env_ids, sizeof(int32_t) * (size_t)n);
+      CU(cudaMemcpyAsync(e->d_pin, e->h_pin, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+      a.ids = reinterpret_cast<const int32_t*>(e->d_pin);
+    }
+  }
+  mdx_gather_rows_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(e->base, a);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(e->h_pin + ids_bytes, e->d_pin + ids_bytes, rows_bytes, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  std::memcpy(h_rows, e->h_pin + ids_bytes, rows_bytes);
+  return MDX_OK;
+}
+
+int32_t mdx_set_states(mdx_env* e, const int32_t* h_env_ids, int32_t n, const void* h_rows, void* stream) {
+  if (!e || !h_rows) return fail(MDX_E_INVALID, "null argument");
+  int rc = check_ids(e, h_env_ids, n, true);
+  if (rc != MDX_OK) return rc;
+  if (n == 0) return MDX_OK;
+  const uint32_t* rows = static_cast<const uint32_t*>(h_rows);
+  for (int k = 0; k < n; ++k)
+    if ((rc = validate_row(e, h_env_ids ? h_env_ids[k] : k, rows + (size_t)k * e->row_words)) != MDX_OK) return rc;
+  DeviceGuard g(e->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t ids_bytes = h_env_ids ? up16(sizeof(int32_t) * (size_t)n) : 0, rows_bytes = (size_t)n * e->row_words * 4;
+  if ((rc = staging(e, ids_bytes + rows_bytes)) != MDX_OK) return rc;
+  if (h_env_ids) std::memcpy(e->h_pin, h_env_ids, sizeof(int32_t) * (size_t)n);
+  std::memcpy(e->h_pin + ids_bytes, h_rows, rows_bytes);
+  CU(cudaMemcpyAsync(e->d_pin, e->h_pin, ids_bytes + rows_bytes, cudaMemcpyHostToDevice, st));  // ONE copy: ids + rows
+  CU(cudaEventRecord(e->pin_busy, st));
+  RowArgs a = row_args(e, reinterpret_cast<uint32_t*>(e->d_pin + ids_bytes), h_env_ids ? reinterpret_cast<const int32_t*>(e->d_pin) : nullptr, n);
+  mdx_scatter_rows_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(e->base, a);
+  CU(cudaGetLastError());
+  return MDX_OK;
+}
+
+int32_t mdx_step_host(mdx_env* e, const uint8_t* h_actions, const int32_t* h_env_ids, int32_t n, double* h_reward, float* h_shaped,
+                      uint8_t* h_done, void* h_rows, uint32_t flags, void* stream) {
+  if (!e || !h_actions) return fail(MDX_E_INVALID, "null argument");
+  int rc = check_ids(e, h_env_ids, n, true);
+  if (rc != MDX_OK) return rc;
+  if (n == 0) return MDX_OK;
+  if (flags & MDX_F_ACTIONS_I64) return fail(MDX_E_INVALID, "mdx_step_host takes uint8 action codes");
+  DeviceGuard g(e->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t N = (size_t)n;
+  // in:  [ids][actions]      out: [reward f64][shaped f32][done u8][rows]
+  const size_t in_ids = h_env_ids ? up16(4 * N) : 0, in_bytes = in_ids + up16(N * e->R);
+  const size_t o_rew = in_bytes, o_sh = o_rew + up16(8 * N), o_dn = o_sh + up16(4 * N), o_rows = o_dn + up16(N);
+  const size_t total = o_rows + (h_rows ? N * e->row_words * 4 : 0);
+  if ((rc = staging(e, total)) != MDX_OK) return rc;
+  if (h_env_ids) std::memcpy(e->h_pin, h_env_ids, 4 * N);
+  std::memcpy(e->h_pin + in_ids, h_actions, N * e->R);
+  CU(cudaMemcpyAsync(e->d_pin, e->h_pin, in_bytes, cudaMemcpyHostToDevice, st));
+  const int32_t* d_ids = h_env_ids ? reinterpret_cast<const int32_t*>(e->d_pin) : nullptr;
+  rc = mdx_step(e, e->d_pin + in_ids, d_ids, n, reinterpret_cast<double*>(e->d_pin + o_rew),
+                h_shaped ? reinterpret_cast<float*>(e->d_pin + o_sh) : nullptr, e->d_pin + o_dn, flags & MDX_F_AUTO_RESET, stream);
+  if (rc != MDX_OK) return rc;
+  if (h_rows) {
+    RowArgs a = row_args(e, reinterpret_cast<uint32_t*>(e->d_pin + o_rows), d_ids, n);
+    mdx_gather_rows_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(e->base, a);
+    CU(cudaGetLastError());
+  }
+  CU(cudaMemcpyAsync(e->h_pin + o_rew, e->d_pin + o_rew, total - o_rew, cudaMemcpyDeviceToHost, st));  // ONE copy back
+  CU(cudaStreamSynchronize(st));
+  if (h_reward) std::memcpy(h_reward, e->h_pin + o_rew, 8 * N);
+  if (h_shaped) std::memcpy(h_shaped, e->h_pin + o_sh, 4 * N);
+  if (h_done) std::memcpy(h_done, e->h_pin + o_dn, N);
+  if (h_rows) std::memcpy(h_rows, e->h_pin + o_rows, N * e->row_words * 4);
   return MDX_OK;
 }
 
 int32_t mdx_get_state(mdx_env* e, int32_t id, mdx_state_view* out, void* stream) {
   if (!e || !out) return fail(MDX_E_INVALID, "null argument");
   if (id < 0 || id >= e->n) return fail(MDX_E_INVALID, "env id %d out of range", id);
-  DeviceGuard g(e->device);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const KParams& b = e->base;
-  int32_t t = 0, ep = 0;
-  double total = 0;
-  std::vector<uint32_t> rob((size_t)e->R);
-  std::vector<uint8_t> status((size_t)b.Pp16);
-  std::vector<uint16_t> sched((size_t)4 * b.Pp8);
-  CU(cudaStreamSynchronize(st));
-  CU(cudaMemcpy(&t, e->d_t + id, sizeof(t), cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(&ep, e->d_ep + id, sizeof(ep), cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(&total, e->d_total + id, sizeof(total), cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(rob.data(), e->d_robots + (size_t)id * e->R, sizeof(uint32_t) * e->R, cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(status.data(), e->d_status + (size_t)id * b.Pp16, (size_t)b.Pp16, cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(sched.data(), e->d_cur + (size_t)id * 4 * b.Pp8, sizeof(uint16_t) * 4 * b.Pp8, cudaMemcpyDeviceToHost));
-  out->t = t;
-  out->episode = ep;
+  std::vector<uint32_t> row((size_t)e->row_words);
+  int rc = mdx_get_states(e, &id, 1, row.data(), stream);
+  if (rc != MDX_OK) return rc;
+  out->t = (int32_t)row[0];
+  out->episode = (int32_t)row[1];
   out->map_id = e->env_map[(size_t)id];
-  out->total_reward = total;
+  std::memcpy(&out->total_reward, &row[4], sizeof(double));
+  const uint16_t* sched = reinterpret_cast<const uint16_t*>(row.data() + e->off_sched);
+  const uint8_t* status = reinterpret_cast<const uint8_t*>(row.data() + e->off_status);
   const int Wo = e->W_out;
   for (int i = 0; i < e->R; ++i) {
-    const int cell = (int)(rob[(size_t)i] & 0xffffu);
+    const uint32_t rob = row[(size_t)e->off_robots + i];
+    const int cell = (int)(rob & 0xffffu);
     if (out->robot_row) out->robot_row[i] = cell / Wo;
     if (out->robot_col) out->robot_col[i] = cell % Wo;
-    if (out->robot_carry) out->robot_carry[i] = (int)(rob[(size_t)i] >> 16);
+    if (out->robot_carry) out->robot_carry[i] = (int)(rob >> 16);
   }
   for (int j = 0; j < e->P; ++j) {
-    const int s = sched[(size_t)(0 * b.Pp8 + j)], g2 = sched[(size_t)(1 * b.Pp8 + j)];
+    const int s = sched[0 * b.Pp8 + j], g2 = sched[1 * b.Pp8 + j];
     if (out->pkg_start_row) out->pkg_start_row[j] = s / Wo;
     if (out->pkg_start_col) out->pkg_start_col[j] = s % Wo;
     if (out->pkg_target_row) out->pkg_target_row[j] = g2 / Wo;
     if (out->pkg_target_col) out->pkg_target_col[j] = g2 % Wo;
-    if (out->pkg_start_time) out->pkg_start_time[j] = sched[(size_t)(2 * b.Pp8 + j)];
-    if (out->pkg_deadline) out->pkg_deadline[j] = sched[(size_t)(3 * b.Pp8 + j)];
-    if (out->pkg_status) out->pkg_status[j] = status[(size_t)j];
+    if (out->pkg_start_time) out->pkg_start_time[j] = sched[2 * b.Pp8 + j];
+    if (out->pkg_deadline) out->pkg_deadline[j] = sched[3 * b.Pp8 + j];
+    if (out->pkg_status) out->pkg_status[j] = status[j];
   }
   return MDX_OK;
 }
@@ -728,44 +855,35 @@ int32_t mdx_set_state(mdx_env* e, int32_t id, const mdx_state_view* in, void* st
   if (e->P > 0 && (!in->pkg_start_row || !in->pkg_start_col || !in->pkg_target_row || !in->pkg_target_col || !in->pkg_start_time ||
                    !in->pkg_deadline || !in->pkg_status))
     return fail(MDX_E_INVALID, "package arrays are required");
-  DeviceGuard g(e->device);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const KParams& b = e->base;
   const MapHost& m = e->maps[(size_t)e->env_map[(size_t)id]];
   const int Wo = e->W_out;
-  const long long dl_cap = std::min<long long>(65535, ((1LL << (32 - b.key_wbits)) - 2) / b.nranks_max - 1);
-  std::vector<uint32_t> rob((size_t)e->R);
+  std::vector<uint32_t> row((size_t)e->row_words, 0u);
+  row[0] = (uint32_t)in->t;
+  std::memcpy(&row[4], &in->total_reward, sizeof(double));
   for (int i = 0; i < e->R; ++i) {
     const int r = in->robot_row[i], c = in->robot_col[i], k = in->robot_carry[i];
     if (r < 0 || r >= m.rows || c < 0 || c >= m.cols) return fail(MDX_E_INVALID, "robot %d outside the map", i);
     if (k < 0 || k > e->P) return fail(MDX_E_INVALID, "robot %d carries an unknown package id %d", i, k);
-    rob[(size_t)i] = (uint32_t)(r * Wo + c) | ((uint32_t)k << 16);
+    row[(size_t)e->off_robots + i] = (uint32_t)(r * Wo + c) | ((uint32_t)k << 16);
   }
-  std::vector<uint8_t> status((size_t)b.Pp16, 0);
-  std::vector<uint16_t> sched((size_t)4 * b.Pp8, 0);
-  for (int j = b.P; j < b.Pp8; ++j) sched[(size_t)(2 * b.Pp8 + j)] = 0xffff;
+  uint16_t* sched = reinterpret_cast<uint16_t*>(row.data() + e->off_sched);
+  uint8_t* status = reinterpret_cast<uint8_t*>(row.data() + e->off_status);
+  for (int j = b.P; j < b.Pp8; ++j) sched[2 * b.Pp8 + j] = 0xffff;
   for (int j = 0; j < e->P; ++j) {
     const int sr = in->pkg_start_row[j], sc = in->pkg_start_col[j], tr = in->pkg_target_row[j], tc = in->pkg_target_col[j];
     if (sr < 0 || sr >= m.rows || sc < 0 || sc >= m.cols || tr < 0 || tr >= m.rows || tc < 0 || tc >= m.cols)
       return fail(MDX_E_INVALID, "package %d outside the map", j + 1);
     if (in->pkg_start_time[j] < 0 || in->pkg_start_time[j] > 65534) return fail(MDX_E_INVALID, "package %d: bad start_time", j + 1);
-    if (in->pkg_deadline[j] < 0 || in->pkg_deadline[j] > dl_cap) return fail(MDX_E_INVALID, "package %d: deadline out of range", j + 1);
+    if (in->pkg_deadline[j] < 0 || in->pkg_deadline[j] > 65535) return fail(MDX_E_INVALID, "package %d: deadline out of range", j + 1);
     if (in->pkg_status[j] < 0 || in->pkg_status[j] > 3) return fail(MDX_E_INVALID, "package %d: bad status", j + 1);
-    sched[(size_t)(0 * b.Pp8 + j)] = (uint16_t)(sr * Wo + sc);
-    sched[(size_t)(1 * b.Pp8 + j)] = (uint16_t)(tr * Wo + tc);
-    sched[(size_t)(2 * b.Pp8 + j)] = (uint16_t)in->pkg_start_time[j];
-    sched[(size_t)(3 * b.Pp8 + j)] = (uint16_t)in->pkg_deadline[j];
-    status[(size_t)j] = (uint8_t)in->pkg_status[j];
+    sched[0 * b.Pp8 + j] = (uint16_t)(sr * Wo + sc);
+    sched[1 * b.Pp8 + j] = (uint16_t)(tr * Wo + tc);
+    sched[2 * b.Pp8 + j] = (uint16_t)in->pkg_start_time[j];
+    sched[3 * b.Pp8 + j] = (uint16_t)in->pkg_deadline[j];
+    status[j] = (uint8_t)in->pkg_status[j];
   }
-  CU(cudaStreamSynchronize(st));
-  const int32_t t = in->t;
-  const double total = in->total_reward;
-  CU(cudaMemcpy(e->d_t + id, &t, sizeof(t), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(e->d_total + id, &total, sizeof(total), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(e->d_robots + (size_t)id * e->R, rob.data(), sizeof(uint32_t) * e->R, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(e->d_status + (size_t)id * b.Pp16, status.data(), (size_t)b.Pp16, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(e->d_cur + (size_t)id * 4 * b.Pp8, sched.data(), sizeof(uint16_t) * 4 * b.Pp8, cudaMemcpyHostToDevice));
-  return MDX_OK;
+  return mdx_set_states(e, &id, 1, row.data(), stream);  // (validates time, free / distinct robot cells, deadline range)
 }
 
 int32_t mdx_episode_stats(mdx_env* e, int64_t* d_out8, void* stream) {

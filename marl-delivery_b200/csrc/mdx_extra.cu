@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(128) mdx_greedy_kernel(const __grid_constant__
   const int widx = blockIdx.x * (blockDim.x >> 5) + wib;
   if (widx >= p.n) return;
   const int env = p.env_ids ? __ldg(p.env_ids + widx) : widx;
+  if ((unsigned)env >= (unsigned)p.n_envs) return;  // a bad caller-supplied id never becomes an out-of-bounds access (row left unwritten)
   uint32_t* fr = sm_free + (size_t)wib * a.fw;
   MapDev map = p.map0;
   if (p.env_map) map = p.maps[__ldg(p.env_map + env)];
@@ -399,16 +400,41 @@ __global__ void __launch_bounds__(kGaeTmaCols) mdx_gae_tma_kernel(const float* _
 namespace {
 
 struct CkptHeader {
-  uint64_t magic;  // "MDXCKPT1"
-  int32_t n, R, P, T, E, Pp8, Pp16, has_greedy, gfree_words, reserved;
+  uint64_t magic;  // "MDXCKPT2"
+  int32_t n, R, P, T, Pp8, Pp16, H_out, W_out, n_maps, has_greedy, gfree_words, reserved;
+  uint64_t config_hash;  // maps, env -> map assignment, rewards, shaping constants, feature sizes
   int64_t bytes;
 };
-constexpr uint64_t kMagic = 0x3154504b4358444dull;
+constexpr uint64_t kMagic = 0x3254504b4358444dull;
 
 struct Seg {
   void* dev;
   size_t bytes;
 };
+
+// FNV-1a over everything that decides how the stored integers are to be read (cell ids depend on W_out and the maps, rewards on the
+// constants): a blob of an instance configured differently must not load.
+uint64_t config_hash(const mdx_env* e) {
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&](const void* p, size_t nbytes) {
+    const unsigned char* c = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < nbytes; ++i) h = (h ^ c[i]) * 1099511628211ull;
+  };
+  for (const MapHost& m : e->maps) {
+    mix(&m.rows, sizeof(m.rows));
+    mix(&m.cols, sizeof(m.cols));
+    mix(m.cells.data(), m.cells.size());
+  }
+  mix(e->env_map.data(), sizeof(int32_t) * e->env_map.size());
+  const KParams& b = e->base;
+  mix(&b.move_cost, sizeof(double));
+  mix(&b.delivery_reward, sizeof(double));
+  mix(&b.delay_reward, sizeof(double));
+  mix(b.shaping, sizeof(b.shaping));
+  const int32_t sizes[6] = {b.K_o, b.K_p, b.MR, b.MP, b.shaping_bfs, 0};
+  mix(sizes, sizeof(sizes));
+  return h;
+}
 
 std::vector<Seg> device_segments(mdx_env* e) {
   const size_t n = (size_t)e->n;
@@ -416,25 +442,19 @@ std::vector<Seg> device_segments(mdx_env* e) {
   std::vector<Seg> s = {
       {e->d_t, sizeof(int32_t) * n},
       {e->d_ep, sizeof(int32_t) * n},
-      {e->d_ep_avail, sizeof(int32_t) * n},
+      {e->d_mtpos, sizeof(int32_t) * n},  // (index 2: validated on load)
       {e->d_total, sizeof(double) * n},
       {e->d_robots, sizeof(uint32_t) * n * e->R},
       {e->d_status, n * b.Pp16},
-      {e->d_sched, sizeof(uint16_t) * (size_t)e->E * n * 4 * b.Pp8},
       {e->d_cur, sizeof(uint16_t) * n * 4 * b.Pp8},
-      {e->d_sched_robots, sizeof(uint16_t) * (size_t)e->E * n * 32},
       {e->d_counters, sizeof(uint32_t) * n * 8},
+      {e->d_mt, sizeof(uint32_t) * n * 624},
   };
   if (e->d_greedy) {
     s.push_back({e->d_greedy, sizeof(uint32_t) * n * 32});
     s.push_back({e->d_gfree, sizeof(uint32_t) * n * (size_t)e->gfree_words});
   }
   return s;
-}
-
-size_t host_bytes(const mdx_env* e) {
-  const size_t n = (size_t)e->n;
-  return n * (sizeof(uint32_t) * 624 + sizeof(int32_t)) + 2 * n * sizeof(int32_t);  // rng state + pos, sampled, ep_host
 }
 
 int ensure_greedy(mdx_env* e) {
@@ -544,7 +564,7 @@ int32_t mdx_gae(const float* d_rewards, const float* d_values, const uint8_t* d_
 
 int64_t mdx_checkpoint_bytes(const mdx_env* e) {
   if (!e) return 0;
-  size_t total = sizeof(CkptHeader) + host_bytes(e);
+  size_t total = sizeof(CkptHeader);
   for (const Seg& s : device_segments(const_cast<mdx_env*>(e))) total += s.bytes;
   return (int64_t)total;
 }
@@ -559,9 +579,11 @@ int32_t mdx_checkpoint_save(mdx_env* e, void* h_buf, int64_t bytes, void* stream
   unsigned char* p = static_cast<unsigned char*>(h_buf);
   CkptHeader h{};
   h.magic = kMagic;
-  h.n = e->n, h.R = e->R, h.P = e->P, h.T = e->T, h.E = e->E, h.Pp8 = e->base.Pp8, h.Pp16 = e->base.Pp16;
+  h.n = e->n, h.R = e->R, h.P = e->P, h.T = e->T, h.Pp8 = e->base.Pp8, h.Pp16 = e->base.Pp16;
+  h.H_out = e->H_out, h.W_out = e->W_out, h.n_maps = (int32_t)e->maps.size();
   h.has_greedy = e->d_greedy ? 1 : 0;
   h.gfree_words = e->gfree_words;
+  h.config_hash = config_hash(e);
   h.bytes = need;
   std::memcpy(p, &h, sizeof(h));
   p += sizeof(h);
@@ -569,17 +591,6 @@ int32_t mdx_checkpoint_save(mdx_env* e, void* h_buf, int64_t bytes, void* stream
     CU(cudaMemcpy(p, s.dev, s.bytes, cudaMemcpyDeviceToHost));
     p += s.bytes;
   }
-  for (int i = 0; i < e->n; ++i) {
-    std::memcpy(p, e->rng[(size_t)i].mt, sizeof(uint32_t) * 624);
-    p += sizeof(uint32_t) * 624;
-    const int32_t pos = e->rng[(size_t)i].pos;
-    std::memcpy(p, &pos, sizeof(pos));
-    p += sizeof(pos);
-  }
-  std::memcpy(p, e->sampled.data(), sizeof(int32_t) * (size_t)e->n);
-  p += sizeof(int32_t) * (size_t)e->n;
-  // the device episode cursor is authoritative; ep_host is refreshed from it on load
-  std::memcpy(p, e->ep_host.data(), sizeof(int32_t) * (size_t)e->n);
   return MDX_OK;
 }
 
@@ -588,40 +599,50 @@ int32_t mdx_checkpoint_load(mdx_env* e, const void* h_buf, int64_t bytes, void* 
   if (bytes < (int64_t)sizeof(CkptHeader)) return fail(MDX_E_INVALID, "not an mdx checkpoint");
   CkptHeader h;
   std::memcpy(&h, h_buf, sizeof(h));
-  if (h.magic != kMagic) return fail(MDX_E_INVALID, "not an mdx checkpoint");
-  if (h.n != e->n || h.R != e->R || h.P != e->P || h.T != e->T || h.E != e->E || h.Pp8 != e->base.Pp8 || h.Pp16 != e->base.Pp16)
-    return fail(MDX_E_INVALID, "checkpoint shape (n=%d R=%d P=%d T=%d E=%d) does not match this instance (n=%d R=%d P=%d T=%d E=%d)", h.n,
-                h.R, h.P, h.T, h.E, e->n, e->R, e->P, e->T, e->E);
+  if (h.magic != kMagic) return fail(MDX_E_INVALID, "not an mdx checkpoint (or one written by another version of the library)");
+  if (h.n != e->n || h.R != e->R || h.P != e->P || h.T != e->T || h.Pp8 != e->base.Pp8 || h.Pp16 != e->base.Pp16 ||
+      h.H_out != e->H_out || h.W_out != e->W_out || h.n_maps != (int32_t)e->maps.size())
+    return fail(MDX_E_INVALID, "checkpoint shape (n=%d R=%d P=%d T=%d plane %dx%d, %d maps) does not match this instance (n=%d R=%d P=%d T=%d "
+                "plane %dx%d, %d maps)", h.n, h.R, h.P, h.T, h.H_out, h.W_out, h.n_maps, e->n, e->R, e->P, e->T, e->H_out, e->W_out,
+                (int)e->maps.size());
+  if (h.config_hash != config_hash(e))
+    return fail(MDX_E_INVALID, "checkpoint was written by an instance with other maps, env -> map assignment, rewards, shaping or feature sizes");
+  // ---- validate the whole blob before the first byte reaches the device (a refused blob leaves the instance untouched)
+  const size_t n = (size_t)e->n;
+  const size_t gw = (size_t)(h.has_greedy ? h.gfree_words : 0);
+  if (h.has_greedy && h.gfree_words != (2 * std::max(1, e->P) + 31) / 32) return fail(MDX_E_INVALID, "checkpoint greedy state does not match");
+  std::vector<Seg> base = device_segments(e);
+  if (e->d_greedy) base.resize(base.size() - 2);
+  size_t need = sizeof(CkptHeader);
+  for (const Seg& s : base) need += s.bytes;
+  if (h.has_greedy) need += sizeof(uint32_t) * n * 32 + sizeof(uint32_t) * n * gw;
+  if ((int64_t)need != h.bytes || bytes < h.bytes) return fail(MDX_E_INVALID, "truncated or inconsistent checkpoint");
+  {
+    const unsigned char* q = static_cast<const unsigned char*>(h_buf) + sizeof(h) + base[0].bytes + base[1].bytes;
+    for (size_t i = 0; i < n; ++i) {
+      int32_t pos;
+      std::memcpy(&pos, q + sizeof(int32_t) * i, sizeof(pos));
+      if (pos < 0 || pos > 624) return fail(MDX_E_INVALID, "corrupt generator state in checkpoint (env %zu)", i);
+    }
+  }
   if (h.has_greedy) {
     int rc = ensure_greedy(e);
     if (rc != MDX_OK) return rc;
-    if (h.gfree_words != e->gfree_words) return fail(MDX_E_INVALID, "checkpoint greedy state does not match");
   }
   DeviceGuard g(e->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CU(cudaStreamSynchronize(st));
+  const unsigned char* p = static_cast<const unsigned char*>(h_buf) + sizeof(h);
   std::vector<Seg> segs = device_segments(e);
   if (!h.has_greedy && e->d_greedy) segs.resize(segs.size() - 2);
-  size_t need = sizeof(CkptHeader) + host_bytes(e);
-  for (const Seg& s : segs) need += s.bytes;
-  if ((int64_t)need != h.bytes || bytes < h.bytes) return fail(MDX_E_INVALID, "truncated or inconsistent checkpoint");
-  const unsigned char* p = static_cast<const unsigned char*>(h_buf) + sizeof(h);
   for (const Seg& s : segs) {
     CU(cudaMemcpy(s.dev, p, s.bytes, cudaMemcpyHostToDevice));
     p += s.bytes;
   }
-  for (int i = 0; i < e->n; ++i) {
-    std::memcpy(e->rng[(size_t)i].mt, p, sizeof(uint32_t) * 624);
-    p += sizeof(uint32_t) * 624;
-    int32_t pos;
-    std::memcpy(&pos, p, sizeof(pos));
-    p += sizeof(pos);
-    if (pos < 0 || pos > 624) return fail(MDX_E_INVALID, "corrupt generator state in checkpoint");
-    e->rng[(size_t)i].pos = pos;
+  if (!h.has_greedy && e->d_greedy) {  // the blob carries no agent bookkeeping: back to a freshly created agent
+    CU(cudaMemset(e->d_greedy, 0, sizeof(uint32_t) * n * 32));
+    CU(cudaMemset(e->d_gfree, 0xff, sizeof(uint32_t) * n * (size_t)e->gfree_words));
   }
-  std::memcpy(e->sampled.data(), p, sizeof(int32_t) * (size_t)e->n);
-  p += sizeof(int32_t) * (size_t)e->n;
-  std::memcpy(e->ep_host.data(), p, sizeof(int32_t) * (size_t)e->n);
   return MDX_OK;
 }
 

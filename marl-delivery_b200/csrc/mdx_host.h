@@ -74,34 +74,30 @@ struct mdx_env {
   int device = 0;
   int n = 0, R = 0, P = 0, T = 0, E = 0;
   int H_out = 0, W_out = 0;
-  int rec_u16 = 0;  // staging record size in u16: 4*Pp8 + 32
-  int threads = 1;
   std::vector<MapHost> maps;
   std::vector<int32_t> env_map;
-  std::vector<Mt19937> rng;        // one legacy RandomState stream per env
-  std::vector<int32_t> sampled;    // reset blocks drawn so far per env (== device ep_avail)
-  std::vector<int32_t> ep_host;    // last known device episode cursor
   KParams base{};                  // everything but the per-call arguments
   // device memory
   void* d_blob = nullptr;          // maps + LUTs
   MapDev* d_maps = nullptr;
   int32_t* d_t = nullptr;
   int32_t* d_ep = nullptr;
-  int32_t* d_ep_avail = nullptr;
+  uint32_t* d_mt = nullptr;        // [n][624] MT19937 state per env (the device reset sampler's streams)
+  int32_t* d_mtpos = nullptr;      // [n]
   double* d_total = nullptr;
   uint32_t* d_robots = nullptr;
   uint8_t* d_status = nullptr;
-  uint16_t* d_sched = nullptr;
   uint16_t* d_cur = nullptr;
-  uint16_t* d_sched_robots = nullptr;
   uint32_t* d_counters = nullptr;
   int32_t* d_env_map = nullptr;
-  // upload staging (sized for one block per env; larger uploads go in waves)
-  uint16_t* h_stage = nullptr;  // pinned
-  int32_t* h_ids = nullptr;     // pinned: [2][n] ids, slots
-  int32_t* h_i32 = nullptr;     // pinned scratch [n]
-  uint16_t* d_stage = nullptr;
-  int32_t* d_ids = nullptr;     // [2][n]
+  int32_t* d_ids = nullptr;     // [n] env ids of an mdx_reset call
+  // packed-row entry points (mdx_get_states / mdx_set_states / mdx_step_host): one pinned host buffer and its device
+  // mirror, grown on demand; `pin_busy` marks the last asynchronous H2D copy that read the host buffer
+  unsigned char* h_pin = nullptr;
+  unsigned char* d_pin = nullptr;
+  size_t pin_bytes = 0;
+  cudaEvent_t pin_busy = nullptr;
+  int row_words = 0, off_robots = 0, off_sched = 0, off_status = 0;  // row layout in 4-byte words
   // f2: greedy policy + BFS tables (allocated on first use)
   uint16_t* d_bfs = nullptr;       // [n_maps][HW][HW]
   uint32_t* d_greedy = nullptr;    // [n][32]  target id | carried id seen at the previous call << 16
@@ -109,7 +105,6 @@ struct mdx_env {
   int gfree_words = 0;
   int wpb_override = 0;
   int carveout = -1;      // MDX_CARVEOUT=0..100: preferred shared-memory carve-out of the env kernels (-1 = driver default)
-  size_t smem_configured[96] = {};
   int no_fixed = 0;       // MDX_NOFIX=1: never use the shape-specialised instantiation
   int no_fat = 0;         // MDX_NOFAT=1: never use the uncapped-register instantiation for big environments
   int lpe_override = 0;   // MDX_LPE=8|16|32: minimum lanes per environment (experiments / tests)
@@ -118,6 +113,9 @@ struct mdx_env {
 
 
 namespace mdx {
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the kernel FUNCTION on a device, shared by every mdx_env of the
+// process: raise it to `bytes` if the high-water mark recorded for (function, current device) is lower.
+int ensure_dynamic_smem(const void* func, size_t bytes, int carveout);
 // one translation unit per kernel mode (mdx_launch{1,2,3}.cu): 1 step, 2 featurise, 3 fused
 int launch_env_kernel_1(mdx_env* e, const KParams& kp, cudaStream_t st);
 int launch_env_kernel_2(mdx_env* e, const KParams& kp, cudaStream_t st);

@@ -59,6 +59,10 @@ struct MapDev {
   const uint16_t* rank;       // [(2*H_out-1) * (2*W_out-1)] dense rank of the float64 sort key
   const uint16_t* bfs;        // [HW][HW] all-pairs shortest-path length over free cells (output-plane cell ids,
                               // 0xFFFF = unreachable / obstacle); nullptr until the greedy policy or BFS shaping needs it
+  const uint16_t* free_cells; // [n_free] output-plane cell ids of the free cells in the reference's row-major order
+                              // (env.py:155,166): what the device reset sampler indexes with its draws
+  int32_t n_free;
+  int32_t pad2;
 };
 
 struct KParams {
@@ -68,7 +72,7 @@ struct KParams {
   int32_t Pp16;   // P rounded up to 16 (status row)
   int32_t H_out, W_out, HW, W32;
   int32_t K_o, K_p, MR, MP, D, Dg;
-  int32_t E;      // ring depth
+  int32_t E;      // (unused since v2: episodes are drawn on the device when an env resets)
   int32_t key_wbits;     // bits reserved for the waiting-list index inside the 32-bit selection key
   int32_t nranks_max;
   int32_t tq_len;
@@ -91,15 +95,14 @@ struct KParams {
   int32_t shaping_bfs;     // 1: shaped distance terms use the BFS table instead of Manhattan distance (opt-in)
   // state
   int32_t* t;
-  int32_t* ep;
-  const int32_t* ep_avail;
+  int32_t* ep;             // [n_envs] resets applied since construction (= index of the env's current draw block)
+  uint32_t* mt;            // [n_envs][624] MT19937 state of the env's numpy legacy RandomState stream (env.py:40)
+  int32_t* mtpos;          // [n_envs] next output index, 0..624
   double* total_reward;
   uint32_t* robots;        // [n_envs][R]  cell | carry << 16
   uint8_t* status;         // [n_envs][Pp16]
-  uint16_t* sched;         // [E][n_envs][4][Pp8]   ring of pre-sampled episodes: read only when an env resets
-  uint16_t* cur;           // [n_envs][4][Pp8]      schedule of the env's CURRENT episode: what every step reads, at an
-                           //                       address that does not depend on a loaded value (no dependent DRAM trip)
-  uint16_t* sched_robots;  // [E][n_envs][32]
+  uint16_t* cur;           // [n_envs][4][Pp8]      schedule of the env's CURRENT episode: start cell, target cell, start_time,
+                           //                       deadline in package-id order; rewritten by the device sampler on every reset
   uint32_t* counters;      // [n_envs][8]
   const int32_t* env_map;  // [n_envs]
   const MapDev* maps;

@@ -71,6 +71,10 @@ struct Grp {
   __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(mask, v, src, LPE); }  // src is group-relative
 };
 
+}  // namespace mdx
+#include "mdx_sampler.cuh"
+namespace mdx {
+
 // x / d through the host-built multiplier ceil(2^32 / d); d == 1 has no 32-bit multiplier and is encoded as 0
 // (one robot, or one selection slot per robot).
 __device__ __forceinline__ uint32_t div_magic(uint32_t x, uint32_t m) { return m ? __umulhi(x, m) : x; }
@@ -128,22 +132,6 @@ __device__ __forceinline__ void load_episode(const KParams& p, const Env& w, int
   const int n16 = p.Pp8 >> 1;  // 4 rows * Pp8 u16 * 2 B / 16 B
 #pragma unroll 1
   for (int i = sl; i < n16; i += LPE) dst[i] = __ldg(src + i);
-}
-
-// Auto-reset: the next pre-sampled episode moves from ring slot `slot` into shared memory AND into the env's
-// current-episode block (once per episode; every later step reads only that block).
-template <int LPE>
-__device__ __forceinline__ void advance_episode(const KParams& p, const Env& w, int env, int slot, int sl) {
-  const uint4* src = reinterpret_cast<const uint4*>(p.sched + ((size_t)slot * p.n_envs + env) * 4 * p.Pp8);
-  uint4* cur = reinterpret_cast<uint4*>(p.cur + (size_t)env * 4 * p.Pp8);
-  uint4* dst = reinterpret_cast<uint4*>(w.start);
-  const int n16 = p.Pp8 >> 1;
-#pragma unroll 1
-  for (int i = sl; i < n16; i += LPE) {
-    const uint4 v = __ldg(src + i);
-    dst[i] = v;
-    cur[i] = v;
-  }
 }
 
 // numpy float32 add.reduce over the R robot lanes (pairwise_sum: plain loop for n < 8, eight running
@@ -1210,6 +1198,7 @@ __global__ void __launch_bounds__((kFix == 1 && (kMode & 2)) ? MDX_FIX_THREADS :
   const int sl = g.sl;
   const Env w = carve(p, smem_raw + kLutBytes + (size_t)gib * p.smem_per_warp);
   const int env = p.env_ids ? __ldg(p.env_ids + widx) : widx;
+  if ((unsigned)env >= (unsigned)p.n_envs) return;  // a bad caller-supplied id never becomes an out-of-bounds access (row left unwritten)
   const int R = p.R, P = p.P, Wo = p.W_out;
   const bool active = sl < R;
   // single-map instances read the map descriptor from the kernel parameters (no pointer chase)
@@ -1370,24 +1359,19 @@ __global__ void __launch_bounds__((kFix == 1 && (kMode & 2)) ? MDX_FIX_THREADS :
     t = t1;
     g.sync();
     // ---------------- on-device auto-reset (MAPPO/trainer.py:229-234) ----------------
+    // the env's next reset block is drawn right here, by the group that owns it, from the env's MT19937 state in HBM
     if (done && (p.flags & 1u)) {
-      if (ep + 1 < __ldg(p.ep_avail + env)) {
-        ep += 1;
-        const int slot = ep % p.E;
-        advance_episode<LPE>(p, w, env, slot, sl);
-        g.sync();
-        for (int j = sl; j < p.Pp16; j += LPE)
-          w.status[j] = (j < P && w.t0[j] == 0) ? (uint8_t)ST_WAITING : (uint8_t)ST_NONE;
-        if (active) {
-          cell = __ldg(p.sched_robots + ((size_t)slot * p.n_envs + env) * 32 + sl);
-          carry = 0;
-        }
-        t = 0;
-        total = 0.0;
-        g.sync();
-      } else if (sl == 0) {
-        p.counters[(size_t)env * 8 + C_STARVED] = 1u;
+      ep += 1;
+      const int c0 = sample_episode<LPE>(pg, map.free_cells, map.n_free, map.H, w.start, env);
+      for (int j = sl; j < p.Pp16; j += LPE)
+        w.status[j] = (j < P && w.t0[j] == 0) ? (uint8_t)ST_WAITING : (uint8_t)ST_NONE;
+      if (active) {
+        cell = c0;
+        carry = 0;
       }
+      t = 0;
+      total = 0.0;
+      g.sync();
     }
     // ---------------- write the state back ----------------
     if (active) p.robots[(size_t)env * R + sl] = (uint32_t)cell | ((uint32_t)carry << 16);

@@ -1,5 +1,7 @@
 // Variant selection and launch of mdx_env_kernel for ONE kernel mode (MDX_MODE), so that the three modes
 // compile in parallel translation units.
+#include <atomic>
+
 #include "mdx_host.h"
 #include "mdx_kernels.cuh"
 
@@ -16,16 +18,16 @@ int launch_variant(mdx_env* e, const KParams& kp, cudaStream_t st) {
   const int threads = (kFix == 1 && (kMode & 2)) ? MDX_FIX_THREADS : 128;
   const int epb = threads / LPE;            // environments per CTA
   const size_t smem = (size_t)kLutBytes + (size_t)epb * spe;
-  const int slot = kMode == 5 ? 80 + (kS == 1 ? 0 : kS == 2 ? 1 : 2) * 2 + (kSmall ? 1 : 0)
-                   : kFix == 2 ? 91 - kMode : kFix ? 95 - kMode
-                        : ((kMode * 3 + (LPE == 8 ? 0 : LPE == 16 ? 1 : 2)) * 4 + (kS == 0 ? 0 : kS == 1 ? 1 : kS == 2 ? 2 : 3)) * 2 + (kSmall ? 1 : 0);
   if (smem > 227 * 1024) return fail(MDX_E_INVALID, "per-CTA working set (%zu bytes) exceeds shared memory", smem);
-  if (smem > e->smem_configured[slot]) {
-    CU(cudaFuncSetAttribute(mdx_env_kernel<kMode, LPE, kS, kSmall, kFix>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)std::max<size_t>(smem, 48 * 1024)));
-    if (e->carveout >= 0)
-      CU(cudaFuncSetAttribute(mdx_env_kernel<kMode, LPE, kS, kSmall, kFix>, cudaFuncAttributePreferredSharedMemoryCarveout, e->carveout));
-    e->smem_configured[slot] = smem;
+  // The dynamic shared-memory limit is an attribute of this kernel FUNCTION on a device, shared by every mdx_env of the process:
+  // the high-water mark lives in a static of this instantiation (one per function), indexed by device.
+  static std::atomic<size_t> high_water[64];
+  if (smem > high_water[e->device & 63].load(std::memory_order_acquire)) {
+    int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(mdx_env_kernel<kMode, LPE, kS, kSmall, kFix>), smem, e->carveout);
+    if (rc != MDX_OK) return rc;
+    size_t prev = high_water[e->device & 63].load(std::memory_order_relaxed);
+    while (prev < smem && !high_water[e->device & 63].compare_exchange_weak(prev, smem)) {
+    }
   }
   KParams q = kp;
   q.smem_per_warp = spe;

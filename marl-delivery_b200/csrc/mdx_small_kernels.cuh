@@ -1,4 +1,4 @@
-// The non-templated kernels of libmdx (shaped reward on injected states, reset apply, ring upload, counter
+// The non-templated kernels of libmdx (shaped reward on injected states, reset, generator seeding, counter
 // reduction).  Included by mdx_api.cu only.
 #pragma once
 #include "mdx_kernels.cuh"
@@ -53,49 +53,91 @@ __global__ void __launch_bounds__(128) mdx_shape_kernel(const __grid_constant__ 
   if (lane == 0) p.out_shaped[env] = s;
 }
 
-// Apply uploaded reset blocks: env ids[i] advances to its next episode (env.py:81-125 minus the draws,
-// which happened on the host).  One warp per env.
+// Environment.reset (env.py:81-125) for the listed envs: the env's next reset block is drawn on the device from its own
+// MT19937 stream (mdx_sampler.cuh), then applied.  One warp per env; dynamic shared memory = 8 * Pp8 bytes per warp.
+// flags bit 0: count the reset in the episode cursor (0 = the constructor's own reset, env.py:41).
 __global__ void __launch_bounds__(256) mdx_reset_kernel(const __grid_constant__ KParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
-  const int widx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int wib = threadIdx.x >> 5;
+  const int widx = blockIdx.x * (blockDim.x >> 5) + wib;
   if (widx >= p.n) return;
   const int env = p.env_ids ? p.env_ids[widx] : widx;
-  const int ep = p.ep[env] + (int)(p.flags & 1u);  // flags bit 0: advance (0 = re-initialise in place)
-  const int slot = ep % p.E;
-  const uint16_t* blk = p.sched + ((size_t)slot * p.n_envs + env) * 4 * p.Pp8;
-  const uint16_t* t0 = blk + 2 * p.Pp8;
-  {  // the block becomes the env's current-episode schedule
-    const uint4* src = reinterpret_cast<const uint4*>(blk);
-    uint4* cur = reinterpret_cast<uint4*>(p.cur + (size_t)env * 4 * p.Pp8);
-    for (int i = lane; i < (p.Pp8 >> 1); i += 32) cur[i] = src[i];
-  }
+  const MapDev map = p.env_map ? p.maps[p.env_map[env]] : p.map0;
+  uint16_t* s_sched = reinterpret_cast<uint16_t*>(smem_raw + (size_t)wib * 8 * p.Pp8);
+  const int cell = sample_episode<32>(p, map.free_cells, map.n_free, map.H, s_sched, env);
+  const uint16_t* t0 = s_sched + 2 * p.Pp8;
   for (int j = lane; j < p.Pp16; j += 32)
     p.status[(size_t)env * p.Pp16 + j] = (j < p.P && t0[j] == 0) ? (uint8_t)ST_WAITING : (uint8_t)ST_NONE;
-  if (lane < p.R) p.robots[(size_t)env * p.R + lane] = p.sched_robots[((size_t)slot * p.n_envs + env) * 32 + lane];
+  if (lane < p.R) p.robots[(size_t)env * p.R + lane] = (uint32_t)cell;
   if (lane == 0) {
     p.t[env] = 0;
-    p.ep[env] = ep;
+    p.ep[env] += (int)(p.flags & 1u);
     p.total_reward[env] = 0.0;
   }
 }
 
-// Scatter freshly sampled reset blocks from a packed staging buffer into the ring.
-// staging record i: [4*Pp8 u16 schedule][32 u16 robot cells]; dst env = ids[i], slot = slots[i].
-__global__ void mdx_upload_kernel(uint16_t* sched, uint16_t* sched_robots, const uint16_t* staging,
-                                  const int32_t* ids, const int32_t* slots, int n, int n_envs, int Pp8) {
-  const int rec = 4 * Pp8 + 32;
-  const int per = rec / 8;  // uint4 per record (rec is a multiple of 8 u16)
-  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t i = gid / per;
-  const int x = (int)(gid % per);
-  if (i >= (size_t)n) return;
-  const int env = ids[i], slot = slots[i];
-  const uint4 v = reinterpret_cast<const uint4*>(staging + i * rec)[x];
-  const int nsched = (4 * Pp8) / 8;
-  if (x < nsched)
-    reinterpret_cast<uint4*>(sched + ((size_t)slot * n_envs + env) * 4 * Pp8)[x] = v;
-  else
-    reinterpret_cast<uint4*>(sched_robots + ((size_t)slot * n_envs + env) * 32)[x - nsched] = v;
+// init_genrand(seed) for every env (numpy: RandomState(int seed)); one thread per env.
+__global__ void mdx_seed_kernel(uint32_t* mt, int32_t* mtpos, const uint32_t* seeds, int n) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n) return;
+  uint32_t s = seeds[env];
+  uint32_t* m = mt + (size_t)env * 624;
+#pragma unroll 1
+  for (int i = 0; i < 624; ++i) {
+    m[i] = s;
+    s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)(i + 1);
+  }
+  mtpos[env] = 624;
+}
+
+// Packed host <-> device state rows (include/mdx.h: mdx_get_states / mdx_set_states / mdx_step_host).  Row layout, in 4-byte
+// words: [t, episode, map_id, 0, total_reward lo, hi][robots: R words][schedule: 2*Pp8 words][status: Pp16/4 words], padded
+// to a multiple of 4 words.  One warp per listed env; env = ids ? ids[i] : base + i.
+struct RowArgs {
+  uint32_t* rows;       // [n][row_words]
+  const int32_t* ids;   // device ids or nullptr
+  int32_t base, n, row_words, off_robots, off_sched, off_status;
+};
+
+__global__ void mdx_gather_rows_kernel(const __grid_constant__ KParams p, const RowArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= a.n) return;
+  const int env = a.ids ? a.ids[i] : a.base + i;
+  uint32_t* row = a.rows + (size_t)i * a.row_words;
+  if (lane == 0) {
+    row[0] = (uint32_t)p.t[env];
+    row[1] = (uint32_t)p.ep[env];
+    row[2] = p.env_map ? (uint32_t)p.env_map[env] : 0u;
+    row[3] = 0u;
+    const unsigned long long tr = (unsigned long long)__double_as_longlong(p.total_reward[env]);
+    row[4] = (uint32_t)tr;
+    row[5] = (uint32_t)(tr >> 32);
+  }
+  if (lane < p.R) row[a.off_robots + lane] = p.robots[(size_t)env * p.R + lane];
+  const uint32_t* sched = reinterpret_cast<const uint32_t*>(p.cur + (size_t)env * 4 * p.Pp8);
+  for (int k = lane; k < 2 * p.Pp8; k += 32) row[a.off_sched + k] = sched[k];
+  const uint32_t* st = reinterpret_cast<const uint32_t*>(p.status + (size_t)env * p.Pp16);
+  for (int k = lane; k < (p.Pp16 >> 2); k += 32) row[a.off_status + k] = st[k];
+}
+
+// The inverse: rows (validated on the host) -> env state.  The episode cursor, the map id and the generator are not touched.
+__global__ void mdx_scatter_rows_kernel(const __grid_constant__ KParams p, const RowArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= a.n) return;
+  const int env = a.ids ? a.ids[i] : a.base + i;
+  const uint32_t* row = a.rows + (size_t)i * a.row_words;
+  if (lane == 0) {
+    p.t[env] = (int32_t)row[0];
+    p.total_reward[env] = __longlong_as_double((long long)(((unsigned long long)row[5] << 32) | row[4]));
+  }
+  if (lane < p.R) p.robots[(size_t)env * p.R + lane] = row[a.off_robots + lane];
+  uint32_t* sched = reinterpret_cast<uint32_t*>(p.cur + (size_t)env * 4 * p.Pp8);
+  for (int k = lane; k < 2 * p.Pp8; k += 32) sched[k] = row[a.off_sched + k];
+  uint32_t* st = reinterpret_cast<uint32_t*>(p.status + (size_t)env * p.Pp16);
+  for (int k = lane; k < (p.Pp16 >> 2); k += 32) st[k] = row[a.off_status + k];
 }
 
 // sum the per-env counters into 8 int64 (then all-reduced across ranks by NCCL).

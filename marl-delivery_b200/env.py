@@ -9,7 +9,6 @@ Rendering (env.py:347-456) is out of scope.
 from __future__ import annotations
 
 import numpy as np
-import torch
 
 from .batch import STATUS_NAMES, DeliveryBatch, encode_action
 from .maps import load_map
@@ -70,6 +69,11 @@ class EnvView:
             self._snap_ver = self._b._version
         return self._snap
 
+    def _seed(self, snap):
+        """A snapshot that was read together with other envs' (VectorizedEnv.step / reset: one round trip for all)."""
+        self._snap = snap
+        self._snap_ver = self._b._version
+
     @property
     def t(self):
         return self._s()["t"]
@@ -115,11 +119,11 @@ class EnvView:
     def step(self, actions):
         if len(actions) != self.n_robots:
             raise ValueError("The number of actions must match the number of robots.")
-        codes = torch.tensor([[encode_action(m, p) for (m, p) in actions]], dtype=torch.uint8)
-        reward, _, done = self._b.step(codes, ids=self._ids, want_shaped=False)
-        r = float(reward.cpu()[0])
-        d = bool(done.cpu()[0])
-        self._invalidate()
+        codes = np.array([[encode_action(m, p) for (m, p) in actions]], dtype=np.uint8)
+        reward, _, done, rows = self._b.step_host(codes, self._ids)  # one C call: H2D, kernel, snapshot, D2H, one sync
+        r = float(reward[0])
+        d = bool(done[0])
+        self._seed(self._b._rows_to_states(rows)[0])
         infos = {}
         if d:
             infos["total_reward"] = self.total_reward
@@ -153,7 +157,7 @@ class Environment(EnvView):
                  delivery_reward=10., delay_reward=1., seed=2025, device=None):
         grid = load_map(map_file)
         batch = DeliveryBatch([grid], 1, n_robots, n_packages, max_time_steps, move_cost, delivery_reward,
-                              delay_reward, base_seed=seed, device=device, ring_episodes=2)
+                              delay_reward, base_seed=seed, device=device)
         super().__init__(batch, 0, map_file)
         self.move_cost = move_cost
         self.delivery_reward = delivery_reward

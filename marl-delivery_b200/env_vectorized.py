@@ -17,7 +17,7 @@ _ENV_KW = ("map_file", "max_time_steps", "n_robots", "n_packages", "move_cost", 
 
 class VectorizedEnv:
     def __init__(self, env_cls, num_envs, k_others=100, k_packages=100, max_robots_in_state=100,
-                 max_packages_in_state=100, shaping=MAPPO_SHAPING, device=None, ring_episodes=4, first_env_index=0,
+                 max_packages_in_state=100, shaping=MAPPO_SHAPING, device=None, ring_episodes=None, first_env_index=0,
                  bfs_shaping=False,
                  **env_kwargs):
         """`env_cls` is accepted for signature compatibility (the reference passes its Environment
@@ -43,7 +43,7 @@ class VectorizedEnv:
             env_kwargs.get("delivery_reward", 10.), env_kwargs.get("delay_reward", 1.), seeds=seeds,
             env_map=(gidx % len(grids)).astype(np.int32) if len(grids) > 1 else None, k_others=k_others,
             k_packages=k_packages, max_robots_in_state=max_robots_in_state,
-            max_packages_in_state=max_packages_in_state, shaping=shaping, device=device, ring_episodes=ring_episodes,
+            max_packages_in_state=max_packages_in_state, shaping=shaping, device=device,
             bfs_shaping=bfs_shaping)
         self.num_envs = num_envs
         self.envs = _EnvList(self.batch, [files[int(g) % len(files)] for g in gidx] if len(files) > 1 else files * 1)
@@ -52,8 +52,9 @@ class VectorizedEnv:
     def reset(self, indices=None):
         idx = list(range(self.num_envs)) if indices is None else [int(i) for i in indices]
         self.batch.reset(None if indices is None else idx)
-        for i in idx:
-            self.envs[i]._invalidate()
+        snaps = self.batch.get_states(None if indices is None else idx)  # one round trip for all listed envs
+        for i, snap in zip(idx, snaps):
+            self.envs[i]._seed(snap)
             self.envs[i].done = False
         return [self.envs[i].get_state() for i in idx]
 
@@ -68,14 +69,14 @@ class VectorizedEnv:
             if len(acts) != R:
                 raise ValueError("The number of actions must match the number of robots.")
             codes[k] = [encode_action(m, p) for (m, p) in acts]
-        reward, _, done = self.batch.step(torch.from_numpy(codes), ids=None if indices is None and len(idx) == self.num_envs else idx,
-                                          want_shaped=False)
-        rewards = reward.cpu().tolist()
-        dones = [bool(x) for x in done.cpu().tolist()]
+        reward, _, done, rows = self.batch.step_host(codes, None if indices is None and len(idx) == self.num_envs else idx)
+        rewards = reward.tolist()
+        dones = done.tolist()
+        snaps = self.batch._rows_to_states(rows)
         states, infos = [], []
         for k, i in enumerate(idx):
             e = self.envs[i]
-            e._invalidate()
+            e._seed(snaps[k])
             info = {}
             if dones[k]:
                 info["total_reward"] = e.total_reward
@@ -100,9 +101,52 @@ class VectorizedEnv:
         """One fused launch per MAPPO rollout iteration (MAPPO/trainer.py:172-286 without the nets)."""
         return self.batch.step_featurize(actions, auto_reset=auto_reset, out=out, feat_out=feat_out)
 
+    def rollout_graph(self, n_steps, auto_reset=True):
+        """`n_steps` env steps captured in ONE CUDA graph (the hot loops of MAPPO/trainer.py:172 / QMIX/trainer.py:435 call
+        vec_env.step once per step; for a few thousand envs a step is a ~7 us kernel and the host is the bottleneck); see
+        RolloutGraph."""
+        return RolloutGraph(self, n_steps, auto_reset=auto_reset)
+
     def host_pipeline(self, feat_out=None, auto_reset=True):
         """Double-buffered host <-> device stepping for callers whose actions live in HOST memory; see HostPipeline."""
         return HostPipeline(self, feat_out=feat_out, auto_reset=auto_reset)
+
+
+class RolloutGraph:
+    """`n_steps` consecutive `step_tensor(..., auto_reset)` calls over all envs as one CUDA graph.
+
+        g = ve.rollout_graph(64)
+        reward, shaped, done = g.run(actions)     # actions: uint8 [64, N, R] codes (copied into the graph's input buffer)
+
+    `run` replays the graph on the current stream and returns the graph's OUTPUT BUFFERS ([n_steps, N] each, overwritten by
+    the next run).  Results are identical to calling step_tensor step by step (tests/test_gpu_r2.py).  The launches are enqueued by
+    one C call (include/mdx.h: mdx_step_n), so the same speed is also available without a graph through
+    `ve.batch.step_n(actions)`."""
+
+    def __init__(self, ve, n_steps, auto_reset=True):
+        b = ve.batch
+        self.batch, self.n_steps, self.auto_reset = b, int(n_steps), auto_reset
+        dev, N, R = b.device, b.n_envs, b.n_robots
+        self.actions = torch.zeros((self.n_steps, N, R), dtype=torch.uint8, device=dev)
+        self.out = (torch.empty((self.n_steps, N), dtype=torch.float64, device=dev),
+                    torch.empty((self.n_steps, N), dtype=torch.float32, device=dev),
+                    torch.empty((self.n_steps, N), dtype=torch.uint8, device=dev))
+        # one real launch before the capture (loads the kernel), on a snapshot that is put back afterwards
+        blob = b.state_dict()
+        b.step_n(self.actions[:1], auto_reset=auto_reset)
+        torch.cuda.synchronize(dev)
+        b.load_state_dict(blob)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            b.step_n(self.actions, auto_reset=auto_reset, out=self.out)
+        b.load_state_dict(blob)  # (capturing does not run anything, but keep the version counter / views honest)
+
+    def run(self, actions=None):
+        if actions is not None:
+            self.actions.copy_(actions, non_blocking=True)
+        self.graph.replay()
+        self.batch._version += 1
+        return self.out
 
 
 class HostPipeline:

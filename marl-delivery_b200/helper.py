@@ -28,7 +28,7 @@ def _scratch(grid, R, P, T, K_o, K_p, MR, MP, shaping):
         if len(_SCRATCH) > 16:
             _SCRATCH.pop(next(iter(_SCRATCH))).close()
         b = DeliveryBatch([grid], 1, R, P, T, k_others=K_o, k_packages=K_p, max_robots_in_state=MR,
-                          max_packages_in_state=MP, shaping=shaping, ring_episodes=2, base_seed=0, blank=True)
+                          max_packages_in_state=MP, shaping=shaping, base_seed=0, blank=True)
         _SCRATCH[key] = b
     return b
 

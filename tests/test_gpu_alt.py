@@ -68,7 +68,6 @@ def test_alt_random_sweep_vs_oracle(maps, R, P, T):
                            max_time_steps=T, seed=501)
     b = ve.batch
     b.reset()
-    b.prefetch(3)
     envs = [orc.OracleEnv(grids[i % len(grids)], T, R, P, seed=501 + i) for i in range(N)]
     for e in envs:
         e.reset()
@@ -110,7 +109,6 @@ def test_idq_fused_iteration_equals_two_launches(maps, R, P, T, unfused, monkeyp
     a_, b_ = mdb.VectorizedEnv(mdb.Environment, N, **kw).batch, mdb.VectorizedEnv(mdb.Environment, N, **kw).batch
     for x in (a_, b_):
         x.reset()
-        x.prefetch(3)
     rs = np.random.RandomState(9)
     ids = torch.tensor([3, 0, 17, 39, 8], dtype=torch.int32)
     for s in range(2 * T + 7):

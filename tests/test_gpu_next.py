@@ -89,7 +89,6 @@ def test_greedy_vs_oracle_with_auto_reset(maps, R, P, T):
                            max_time_steps=T, seed=77)
     b = ve.batch
     b.reset()
-    b.prefetch(3)
     envs = [orc.OracleEnv(grids[i % len(grids)], T, R, P, seed=77 + i) for i in range(N)]
     agents = []
     for e in envs:
@@ -147,7 +146,6 @@ def test_bfs_shaping_equals_manhattan_without_inner_walls():
     gen = torch.Generator().manual_seed(1)
     for ve in (a_env, b_env):
         ve.batch.reset()
-        ve.batch.prefetch(2)
     for s in range(120):
         a = torch.randint(0, 15, (64, 5), dtype=torch.uint8, generator=gen)
         x = a_env.rollout_step(a)
@@ -191,7 +189,6 @@ def test_int64_policy_actions_equal_action_codes():
     b_env = mdb.VectorizedEnv(mdb.Environment, 128, **kw)
     for ve in (a_env, b_env):
         ve.batch.reset()
-        ve.batch.prefetch(2)
     gen = torch.Generator(device="cuda").manual_seed(2)
     for s in range(90):
         a64 = torch.randint(0, 15, (128, 5), dtype=torch.int64, device="cuda", generator=gen)
@@ -233,7 +230,6 @@ def test_checkpoint_resume_is_bit_identical():
     ve = mdb.VectorizedEnv(mdb.Environment, 96, **kw)
     b = ve.batch
     b.reset()
-    b.prefetch(3)
     gen = torch.Generator().manual_seed(8)
     acts = torch.randint(0, 15, (110, 96, 6), dtype=torch.uint8, generator=gen)
     for s in range(25):
@@ -246,8 +242,6 @@ def test_checkpoint_resume_is_bit_identical():
     def run(batch):
         out = []
         for s in range(25, 110):
-            if s % 29 == 0:
-                batch.prefetch(3)  # draws from the restored MT19937 streams
             if s % 2:
                 res = batch.step_featurize(acts[s])
             else:
@@ -278,7 +272,6 @@ def test_collect_rollouts_matches_trainer_loop():
     ve = mdb.VectorizedEnv(mdb.Environment, N, map_file="map1.txt", n_robots=R, n_packages=P, max_time_steps=T_env, seed=91,
                            k_others=R - 1, k_packages=5)
     ve.batch.reset()
-    ve.batch.prefetch(3)
     gen = torch.Generator(device="cuda").manual_seed(17)
 
     def policy(obs, vec, gstate, gvec):
@@ -322,7 +315,6 @@ def test_host_pipeline_equals_synchronous_rollout_steps():
     va, vb = mdb.VectorizedEnv(mdb.Environment, N, **kw), mdb.VectorizedEnv(mdb.Environment, N, **kw)
     for v in (va, vb):
         v.batch.reset()
-        v.batch.prefetch(3)
     ov = orc.OracleVecEnv(N, mdb.maps.stock_map("map1.txt"), seed=123, max_time_steps=T_env, n_robots=R, n_packages=P)
     ov.reset()
     acts = np.random.RandomState(5).randint(0, 15, size=(K, N, R)).astype(np.uint8)

@@ -90,12 +90,10 @@ def test_golden_trajectory_fused_autoreset(name):
     MAPPO/trainer.py:172-286 sequences it.  Four copies of the env run side by side in one batch."""
     meta, z = load_traj(name)
     N = 4
-    b = _batch_for(meta, z, n_envs=N, ring_episodes=4)
+    b = _batch_for(meta, z, n_envs=N)
     b.reset()
     fi = 0
     for step in range(meta["n_steps"]):
-        if step % 64 == 0:
-            b.prefetch(3)
         a = torch.from_numpy(np.repeat(z["actions"][step][None], N, 0).copy())
         r, sh, d, o, v, g, gv = b.step_featurize(a, auto_reset=True)
         r, sh, d = r.cpu().numpy(), sh.cpu().numpy(), d.cpu().numpy()
@@ -164,7 +162,6 @@ def test_kat_b_vectorised_autoreset():
     ve = mdb.VectorizedEnv(mdb.Environment, 5, map_file="map1.txt", n_robots=5, n_packages=50, max_time_steps=500,
                            seed=42, k_others=4, k_packages=5)
     ve.reset()
-    ve.batch.prefetch(3)
     rs = np.random.RandomState(0)
     total = 0.0
     for s in range(1200):
@@ -242,12 +239,10 @@ def test_random_configs_against_oracle(trial):
     ve = orc.OracleVecEnv(N, grid, seed=seed, max_time_steps=T, n_robots=R, n_packages=P)
     ve.reset()
     b = mdb.DeliveryBatch([grid], N, R, P, T, base_seed=seed, k_others=K_o, k_packages=K_p, max_robots_in_state=MR,
-                          max_packages_in_state=MP, shaping=tuple(float(x) for x in consts), ring_episodes=4)
+                          max_packages_in_state=MP, shaping=tuple(float(x) for x in consts))
     b.reset()
     steps = 2 * T + 5
     for s in range(steps):
-        if s % T == 0:
-            b.prefetch(3)
         a = rs.randint(0, 15, size=(N, R))
         a = np.where(rs.rand(N, R) < 0.04, rs.randint(15, 18, size=(N, R)), a).astype(np.uint8)
         before = [e.snapshot() for e in ve.envs]
@@ -290,7 +285,6 @@ def test_heterogeneous_maps_padded_planes():
                            k_others=9, k_packages=5)
     envs = [orc.OracleEnv(grids[i % 5], T, R, P, seed=77 + i) for i in range(N)]
     ve.reset()
-    ve.batch.prefetch(3)
     for e in envs:
         e.reset()
     rs = np.random.RandomState(3)
@@ -382,13 +376,11 @@ def test_generic_featuriser_path_matches_golden(name, monkeypatch):
     path (any H*W, e.g. maps larger than 22x22), which must produce the same bits."""
     monkeypatch.setenv("MDX_GENERIC", "1")
     meta, z = load_traj(name)
-    b = _batch_for(meta, z, n_envs=2, ring_episodes=4)
+    b = _batch_for(meta, z, n_envs=2)
     monkeypatch.delenv("MDX_GENERIC")
     b.reset()
     fi = 0
     for step in range(min(meta["n_steps"], 260)):
-        if step % 64 == 0:
-            b.prefetch(3)
         a = torch.from_numpy(np.repeat(z["actions"][step][None], 2, 0).copy())
         r, sh, d, o, v, g, gv = b.step_featurize(a, auto_reset=True)
         assert np.all(sh.cpu().numpy() == z["shaped_mappo"][step]), step
@@ -409,13 +401,11 @@ def test_lanes_per_env_variants_match_golden(name, lpe, monkeypatch):
     monkeypatch.setenv("MDX_LPE", str(lpe))
     meta, z = load_traj(name)
     N = 7
-    b = _batch_for(meta, z, n_envs=N, ring_episodes=4)
+    b = _batch_for(meta, z, n_envs=N)
     monkeypatch.delenv("MDX_LPE")
     b.reset()
     fi = 0
     for step in range(min(meta["n_steps"], 200)):
-        if step % 64 == 0:
-            b.prefetch(3)
         a = torch.from_numpy(np.repeat(z["actions"][step][None], N, 0).copy())
         r, sh, d, o, v, g, gv = b.step_featurize(a, auto_reset=True)
         assert np.all(r.cpu().numpy() == z["reward"][step]) and np.all(d.cpu().numpy() == z["done"][step]), step
@@ -447,12 +437,10 @@ def test_edge_shapes_against_oracle(name, R, P, T, K_o, K_p, MR, MP):
     ve = orc.OracleVecEnv(N, grid, seed=77, max_time_steps=T, n_robots=R, n_packages=P)
     ve.reset()
     b = mdb.DeliveryBatch([grid], N, R, P, T, base_seed=77, k_others=K_o, k_packages=K_p, max_robots_in_state=MR,
-                          max_packages_in_state=MP, ring_episodes=8)
+                          max_packages_in_state=MP)
     b.reset()
     rs = np.random.RandomState(3)
     for s in range(2 * T + 3):
-        if s % max(1, 3 * T) == 0 or T < 6:
-            b.prefetch(6)
         a = rs.randint(0, 15, size=(N, R)).astype(np.uint8)
         if s % 3 == 1:
             a = (a % 5 + 5).astype(np.uint8)  # everybody tries to pick up

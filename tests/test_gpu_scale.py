@@ -34,7 +34,6 @@ def test_c2_c3_4096_envs_whole_episode_vs_c_oracle():
     ve = mdb.VectorizedEnv(mdb.Environment, N, map_file="map1.txt", n_robots=R, n_packages=P, max_time_steps=T, seed=42,
                            k_others=4, k_packages=5)
     ve.batch.reset()
-    ve.batch.prefetch(2)
     gen = torch.Generator().manual_seed(7)
     n_done = 0
     for s in range(520):
@@ -64,7 +63,6 @@ def test_c5_stress_32_robots_500_packages_vs_c_oracle():
                            k_others=31, k_packages=5)
     assert ve.batch.vec_dim == 187
     ve.batch.reset()
-    ve.batch.prefetch(2)
     gen = torch.Generator().manual_seed(11)
     for s in range(1030):
         a = torch.randint(0, 15, (N, R), dtype=torch.uint8, generator=gen)
@@ -89,7 +87,6 @@ def test_c4_heterogeneous_2048_envs_vs_c_oracle():
     for e in envs:
         e.reset()
     ve.batch.reset()
-    ve.batch.prefetch(2)
     consts = np.array(orc.MAPPO_SHAPING, np.float32)
     gen = torch.Generator().manual_seed(3)
     for s in range(130):
@@ -124,7 +121,6 @@ def test_c3_full_size_properties_and_shard_independence():
     lo, hi = mk(N // 2, 0), mk(N // 2, N // 2)
     for ve in (full, lo, hi):
         ve.batch.reset()
-        ve.batch.prefetch(1)
     grid = mdb.maps.stock_map("map1.txt")
     pick = np.sort(np.random.RandomState(0).choice(N, 128, replace=False))
     spot = [COracleEnv(grid, T, R, P, 42 + int(i)) for i in pick]
@@ -181,7 +177,6 @@ def test_step_only_large_batch_packs_four_envs_per_warp(monkeypatch):
     monkeypatch.delenv("MDX_LPE")
     for b in (packed, whole):
         b.reset()
-        b.prefetch(3)
     gen = torch.Generator(device="cuda").manual_seed(99)
     for s in range(2 * T + 5):
         a = torch.randint(0, 15, (N, R), dtype=torch.uint8, device="cuda", generator=gen)

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     for name in declared:
         assert getattr(L, name) is not None
-    assert L.mdx_version() == 1
+    assert L.mdx_version() == 2
 
 
 def test_no_cpu_fallback():
