@@ -58,6 +58,10 @@ enum {
                                  per-map all-pairs BFS table instead of MAPPO/helper.py:284-285's Manhattan distance   \
                                  (BASELINE.json north star vs SURVEY.md Q9).  Identical on maps without inner walls. */
 
+#define MDX_CFG_LAX_ROBOTS 4 /* state injection accepts robots on obstacles or sharing a cell (hand-built state dicts passed to the  \
+                                per-call converter drop-ins, which the reference's converters accept too); such an instance must only \
+                                be featurised / shaped, never stepped */
+
 /* Shaping constants of compute_shaped_rewards, in this order (MAPPO/helper.py:271-279,
  * QMIX/helper.py:270-278). */
 typedef struct mdx_shaping {
@@ -210,6 +214,13 @@ int32_t mdx_set_states(mdx_env* env, const int32_t* h_env_ids, int32_t n, const 
  * f32 (NULL: the shaped reward is not evaluated), h_done [n] u8 and h_rows [n rows] may each be NULL. */
 int32_t mdx_step_host(mdx_env* env, const uint8_t* h_actions, const int32_t* h_env_ids, int32_t n, double* h_reward,
                       float* h_shaped, uint8_t* h_done, void* h_rows, uint32_t flags, void* stream);
+
+/* mdx_featurize for HOST callers (the per-call helper drop-ins convert_observation / generate_vector_features /
+ * convert_global_state return numpy, MAPPO/helper.py:6-255): the listed envs' feature tensors straight into host arrays
+ * (any may be NULL), one launch + one synchronisation; small results are written by the kernel directly into pinned host
+ * memory, larger ones take one copy back. */
+int32_t mdx_featurize_host(mdx_env* env, const int32_t* h_env_ids, int32_t n, float* h_obs, float* h_vec, float* h_gstate,
+                           float* h_gvec, void* stream);
 
 /* d_out8 [8] int64 = {episodes_done, robot_moves, on_time, late, pickups,
  * env_steps, sum_episode_len, starved_envs} summed over this instance's envs (cumulative since

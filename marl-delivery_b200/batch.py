@@ -53,7 +53,7 @@ class DeliveryBatch:
                  delay_reward: float = 1.0, seeds=None, base_seed: int = 2025, env_map=None,
                  k_others: int = 100, k_packages: int = 100, max_robots_in_state: int = 100,
                  max_packages_in_state: int = 100, shaping=MAPPO_SHAPING, device=None, ring_episodes=None,
-                 sampler_threads=None, blank: bool = False, bfs_shaping: bool = False):
+                 sampler_threads=None, blank: bool = False, bfs_shaping: bool = False, lax_robots: bool = False):
         """`ring_episodes` / `sampler_threads` are accepted and ignored (v1 pre-sampled reset blocks on the host into a ring;
         since v2 every env draws its next reset block on the device, from its own MT19937 stream, when it resets)."""
         L = _lib.lib()
@@ -99,7 +99,8 @@ class DeliveryBatch:
         cfg.base_seed = int(base_seed)
         cfg.device = int(self.device.index)
         cfg.ring_episodes, cfg.sampler_threads = 0, 0
-        cfg.flags = (_lib.MDX_CFG_BLANK if blank else 0) | (_lib.MDX_CFG_BFS_SHAPING if bfs_shaping else 0)
+        cfg.flags = ((_lib.MDX_CFG_BLANK if blank else 0) | (_lib.MDX_CFG_BFS_SHAPING if bfs_shaping else 0)
+                     | (_lib.MDX_CFG_LAX_ROBOTS if lax_robots else 0))
         handle = C.c_void_p()
         _lib.check(L.mdx_create(C.byref(cfg), C.byref(handle)))
         self._h = handle
@@ -465,20 +466,24 @@ class DeliveryBatch:
 
     # ------------------------------------------------------------------ introspection
     def _rows_to_states(self, rows):
-        """structured rows -> list of the per-env dicts EnvView reads (0-based rows / cols, int32 arrays)."""
+        """structured rows -> list of the per-env dicts EnvView reads (0-based rows / cols, int32 arrays).  All arithmetic is
+        done once over the whole batch of rows; the per-env dicts hold views."""
         P, W = self.n_packages, self.cols_out
-        out = []
-        for row in rows:
-            cell = (row["robots"] & 0xffff).astype(np.int32)
-            sched = row["sched"].astype(np.int32)
-            out.append({"t": int(row["t"]), "episode": int(row["episode"]), "map_id": int(row["map_id"]),
-                        "total_reward": float(row["total_reward"]),
-                        "robot_row": cell // W, "robot_col": cell % W, "robot_carry": (row["robots"] >> 16).astype(np.int32),
-                        "pkg_start_row": sched[0, :P] // W, "pkg_start_col": sched[0, :P] % W,
-                        "pkg_target_row": sched[1, :P] // W, "pkg_target_col": sched[1, :P] % W,
-                        "pkg_start_time": sched[2, :P], "pkg_deadline": sched[3, :P],
-                        "pkg_status": row["status"][:P].astype(np.int32)})
-        return out
+        n = len(rows)
+        if n == 0:
+            return []
+        rob = rows["robots"]
+        cell = (rob & 0xffff).astype(np.int32)
+        rr, rc, rk = cell // W, cell % W, (rob >> 16).astype(np.int32)
+        sched = rows["sched"][:, :, :P].astype(np.int32)
+        pos = sched[:, :2]
+        prow, pcol = pos // W, pos % W
+        status = rows["status"][:, :P].astype(np.int32)
+        t, ep, mp, tot = rows["t"].tolist(), rows["episode"].tolist(), rows["map_id"].tolist(), rows["total_reward"].tolist()
+        return [{"t": t[i], "episode": ep[i], "map_id": mp[i], "total_reward": tot[i],
+                 "robot_row": rr[i], "robot_col": rc[i], "robot_carry": rk[i],
+                 "pkg_start_row": prow[i, 0], "pkg_start_col": pcol[i, 0], "pkg_target_row": prow[i, 1], "pkg_target_col": pcol[i, 1],
+                 "pkg_start_time": sched[i, 2], "pkg_deadline": sched[i, 3], "pkg_status": status[i]} for i in range(n)]
 
     def get_rows(self, ids=None) -> np.ndarray:
         """Packed snapshot of the listed envs (all when None) as a structured numpy array (fields t, episode, map_id,
@@ -491,8 +496,7 @@ class DeliveryBatch:
             n = int(h.size)
         rows = np.empty(n, dtype=self._row_dtype)
         if n:
-            _lib.check(self._L.mdx_get_states(self._h, None if h is None else h.ctypes.data_as(C.c_void_p), n,
-                                              rows.ctypes.data_as(C.c_void_p), self._stream()))
+            _lib.check(self._L.mdx_get_states(self._h, None if h is None else h.ctypes.data, n, rows.ctypes.data, self._stream()))
         return rows
 
     def get_states(self, ids=None) -> list:
@@ -502,6 +506,33 @@ class DeliveryBatch:
         if not 0 <= int(i) < self.n_envs:
             raise ValueError(f"env id {i} out of range")
         return self._rows_to_states(self.get_rows([int(i)]))[0]
+
+    def featurize_host(self, ids=None, obs=True, vec=True, gstate=True, gvec=True):
+        """featurize() for HOST callers -> numpy arrays (None for the ones not asked for): one launch + one synchronisation
+        inside one C call (include/mdx.h: mdx_featurize_host); small results are written by the kernel straight into pinned
+        host memory."""
+        if ids is None:
+            h, n = None, self.n_envs
+        else:
+            h = np.ascontiguousarray(np.asarray(ids, dtype=np.int32).reshape(-1))
+            n = int(h.size)
+        R, H, W = self.n_robots, self.rows_out, self.cols_out
+        o = np.empty((n, R, 6, H, W), np.float32) if obs else None
+        v = np.empty((n, R, self.vec_dim), np.float32) if vec else None
+        g = np.empty((n, 4, H, W), np.float32) if gstate else None
+        gv = np.empty((n, self.gvec_dim), np.float32) if gvec else None
+        vp = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+        _lib.check(self._L.mdx_featurize_host(self._h, vp(h), n, vp(o), vp(v), vp(g), vp(gv), self._stream()))
+        return o, v, g, gv
+
+    def set_rows(self, ids, rows: np.ndarray):
+        """Packed state rows (the structured dtype of get_rows) -> the listed envs; validated in C like set_state."""
+        h = np.ascontiguousarray(np.asarray(ids, dtype=np.int32).reshape(-1))
+        rows = np.ascontiguousarray(rows)
+        if rows.dtype != self._row_dtype or rows.shape != (h.size,):
+            raise ValueError("rows must be a structured array of get_rows()'s dtype, one row per id")
+        _lib.check(self._L.mdx_set_states(self._h, h.ctypes.data, int(h.size), rows.ctypes.data, self._stream()))
+        self._version += 1
 
     def time_steps_host(self, sample: int = 256) -> np.ndarray:
         """Current time step of (a strided sample of) the envs as a host array -- one small synchronous read."""
@@ -524,7 +555,7 @@ class DeliveryBatch:
         shaped = np.empty(n, np.float32) if want_shaped else None
         done = np.empty(n, np.uint8)
         rows = np.empty(n, dtype=self._row_dtype) if want_rows else None
-        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        vp = lambda a: None if a is None else a.ctypes.data  # noqa: E731
         _lib.check(self._L.mdx_step_host(self._h, vp(codes), vp(h), n, vp(reward), vp(shaped), vp(done), vp(rows),
                                          MDX_F_AUTO_RESET if auto_reset else 0, self._stream()))
         self._version += 1

@@ -103,7 +103,7 @@ int staging(mdx_env* e, size_t bytes) {
   cudaFreeHost(e->h_pin);
   e->d_pin = nullptr, e->h_pin = nullptr, e->pin_bytes = 0;
   CU(cudaMalloc(&e->d_pin, cap));
-  CU(cudaMallocHost(&e->h_pin, cap));
+  CU(cudaHostAlloc(&e->h_pin, cap, cudaHostAllocMapped | cudaHostAllocPortable));  // device-addressable (unified addressing)
   e->pin_bytes = cap;
   return MDX_OK;
 }
@@ -153,8 +153,9 @@ int validate_row(const mdx_env* e, int env, const uint32_t* row) {
     const int cell = (int)(row[e->off_robots + i] & 0xffffu), k = (int)(row[e->off_robots + i] >> 16);
     if (!on_map(cell)) return fail(MDX_E_INVALID, "robot %d outside the map", i);
     // Environment.add_robot raises ValueError for an occupied or blocked cell (env.py:73-79)
-    if (m.cells[(size_t)(cell / Wo) * m.cols + cell % Wo] != 0) return fail(MDX_E_INVALID, "Invalid robot position: robot %d stands on an obstacle", i);
     if (k > e->P) return fail(MDX_E_INVALID, "robot %d carries an unknown package id %d", i, k);
+    if (e->cfg.flags & MDX_CFG_LAX_ROBOTS) continue;
+    if (m.cells[(size_t)(cell / Wo) * m.cols + cell % Wo] != 0) return fail(MDX_E_INVALID, "Invalid robot position: robot %d stands on an obstacle", i);
     for (int j = 0; j < i; ++j)
       if ((row[e->off_robots + j] & 0xffffu) == (uint32_t)cell) return fail(MDX_E_INVALID, "Invalid robot position: robots %d and %d share a cell", j, i);
   }
@@ -602,6 +603,7 @@ static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int
                        float* d_g7 = nullptr) {
   if (!e) return fail(MDX_E_INVALID, "null env");
   if ((mode & 1) && !d_actions) return fail(MDX_E_INVALID, "actions are required");
+  if ((mode & 1) && (e->cfg.flags & MDX_CFG_LAX_ROBOTS)) return fail(MDX_E_INVALID, "an MDX_CFG_LAX_ROBOTS instance cannot be stepped");
   if (d_env_ids == nullptr && n != e->n) return fail(MDX_E_INVALID, "n must equal n_envs when env ids are not given (got %d, have %d)", n, e->n);
   if (n < 0 || n > e->n) return fail(MDX_E_INVALID, "bad env count %d", n);
   if (n == 0) return MDX_OK;
@@ -729,6 +731,11 @@ static int shape_common(mdx_env* e, const uint32_t* d_cur_robots, const int32_t*
 
 int64_t mdx_state_row_bytes(const mdx_env* e) { return e ? (int64_t)e->row_words * 4 : 0; }
 
+// Small transfers skip the copy engine altogether: the pinned staging buffer is host memory the device can address directly
+// (unified addressing), so the kernels read their inputs from it and write their results into it over PCIe, and the call is one or
+// two launches plus one synchronisation.  Larger ones go through the device mirror with one copy each way.
+constexpr size_t kZeroCopyBytes = 32 * 1024;
+
 int32_t mdx_get_states(mdx_env* e, const int32_t* h_env_ids, int32_t n, void* h_rows, void* stream) {
   if (!e || !h_rows) return fail(MDX_E_INVALID, "null argument");
   int rc = check_ids(e, h_env_ids, n);
@@ -738,19 +745,21 @@ int32_t mdx_get_states(mdx_env* e, const int32_t* h_env_ids, int32_t n, void* h_
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t ids_bytes = h_env_ids ? up16(sizeof(int32_t) * (size_t)n) : 0, rows_bytes = (size_t)n * e->row_words * 4;
   if ((rc = staging(e, ids_bytes + rows_bytes)) != MDX_OK) return rc;
-  RowArgs a = row_args(e, reinterpret_cast<uint32_t*>(e->d_pin + ids_bytes), nullptr, n);
+  const bool zc = ids_bytes + rows_bytes <= kZeroCopyBytes;
+  unsigned char* dv = zc ? e->h_pin : e->d_pin;  // what the kernels address
+  RowArgs a = row_args(e, reinterpret_cast<uint32_t*>(dv + ids_bytes), nullptr, n);
   if (h_env_ids != nullptr) {
     if (n == 1) {
       a.base = h_env_ids[0];  // one env: its id travels in the kernel parameters
     } else {
       std::memcpy(e->h_pin, h_env_ids, sizeof(int32_t) * (size_t)n);
-      CU(cudaMemcpyAsync(e->d_pin, e->h_pin, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
-      a.ids = reinterpret_cast<const int32_t*>(e->d_pin);
+      if (!zc) CU(cudaMemcpyAsync(e->d_pin, e->h_pin, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+      a.ids = reinterpret_cast<const int32_t*>(dv);
     }
   }
   mdx_gather_rows_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(e->base, a);
   CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(e->h_pin + ids_bytes, e->d_pin + ids_bytes, rows_bytes, cudaMemcpyDeviceToHost, st));
+  if (!zc) CU(cudaMemcpyAsync(e->h_pin + ids_bytes, e->d_pin + ids_bytes, rows_bytes, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   std::memcpy(h_rows, e->h_pin + ids_bytes, rows_bytes);
   return MDX_OK;
@@ -768,13 +777,49 @@ int32_t mdx_set_states(mdx_env* e, const int32_t* h_env_ids, int32_t n, const vo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t ids_bytes = h_env_ids ? up16(sizeof(int32_t) * (size_t)n) : 0, rows_bytes = (size_t)n * e->row_words * 4;
   if ((rc = staging(e, ids_bytes + rows_bytes)) != MDX_OK) return rc;
+  const bool zc = ids_bytes + rows_bytes <= kZeroCopyBytes;
+  unsigned char* dv = zc ? e->h_pin : e->d_pin;
   if (h_env_ids) std::memcpy(e->h_pin, h_env_ids, sizeof(int32_t) * (size_t)n);
   std::memcpy(e->h_pin + ids_bytes, h_rows, rows_bytes);
-  CU(cudaMemcpyAsync(e->d_pin, e->h_pin, ids_bytes + rows_bytes, cudaMemcpyHostToDevice, st));  // ONE copy: ids + rows
-  CU(cudaEventRecord(e->pin_busy, st));
-  RowArgs a = row_args(e, reinterpret_cast<uint32_t*>(e->d_pin + ids_bytes), h_env_ids ? reinterpret_cast<const int32_t*>(e->d_pin) : nullptr, n);
+  if (!zc) CU(cudaMemcpyAsync(e->d_pin, e->h_pin, ids_bytes + rows_bytes, cudaMemcpyHostToDevice, st));  // ONE copy: ids + rows
+  RowArgs a = row_args(e, reinterpret_cast<uint32_t*>(dv + ids_bytes), h_env_ids ? reinterpret_cast<const int32_t*>(dv) : nullptr, n);
   mdx_scatter_rows_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(e->base, a);
   CU(cudaGetLastError());
+  CU(cudaEventRecord(e->pin_busy, st));  // the host buffer is read until here (by the copy, or by the kernel itself)
+  return MDX_OK;
+}
+
+int32_t mdx_featurize_host(mdx_env* e, const int32_t* h_env_ids, int32_t n, float* h_obs, float* h_vec, float* h_gstate, float* h_gvec,
+                           void* stream) {
+  if (!e) return fail(MDX_E_INVALID, "null env");
+  int rc = check_ids(e, h_env_ids, n);
+  if (rc != MDX_OK) return rc;
+  if (n == 0) return MDX_OK;
+  DeviceGuard g(e->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const KParams& b = e->base;
+  const size_t N = (size_t)n;
+  const size_t ids_bytes = h_env_ids ? up16(4 * N) : 0;
+  const size_t b_obs = h_obs ? up16(4 * N * e->R * 6 * b.HW) : 0, b_vec = h_vec ? up16(4 * N * e->R * b.D) : 0;
+  const size_t b_gs = h_gstate ? up16(4 * N * 4 * b.HW) : 0, b_gv = h_gvec ? up16(4 * N * b.Dg) : 0;
+  const size_t o_obs = ids_bytes, o_vec = o_obs + b_obs, o_gs = o_vec + b_vec, o_gv = o_gs + b_gs, total = o_gv + b_gv;
+  if ((rc = staging(e, total)) != MDX_OK) return rc;
+  const bool zc = total <= kZeroCopyBytes;
+  unsigned char* dv = zc ? e->h_pin : e->d_pin;
+  if (h_env_ids) {
+    std::memcpy(e->h_pin, h_env_ids, 4 * N);
+    if (!zc) CU(cudaMemcpyAsync(e->d_pin, e->h_pin, 4 * N, cudaMemcpyHostToDevice, st));
+  }
+  rc = mdx_featurize(e, h_env_ids ? reinterpret_cast<const int32_t*>(dv) : nullptr, n, h_obs ? reinterpret_cast<float*>(dv + o_obs) : nullptr,
+                     h_vec ? reinterpret_cast<float*>(dv + o_vec) : nullptr, h_gstate ? reinterpret_cast<float*>(dv + o_gs) : nullptr,
+                     h_gvec ? reinterpret_cast<float*>(dv + o_gv) : nullptr, stream);
+  if (rc != MDX_OK) return rc;
+  if (!zc) CU(cudaMemcpyAsync(e->h_pin + o_obs, e->d_pin + o_obs, total - o_obs, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (h_obs) std::memcpy(h_obs, e->h_pin + o_obs, 4 * N * e->R * 6 * b.HW);
+  if (h_vec) std::memcpy(h_vec, e->h_pin + o_vec, 4 * N * e->R * b.D);
+  if (h_gstate) std::memcpy(h_gstate, e->h_pin + o_gs, 4 * N * 4 * b.HW);
+  if (h_gvec) std::memcpy(h_gvec, e->h_pin + o_gv, 4 * N * b.Dg);
   return MDX_OK;
 }
 
@@ -793,19 +838,21 @@ int32_t mdx_step_host(mdx_env* e, const uint8_t* h_actions, const int32_t* h_env
   const size_t o_rew = in_bytes, o_sh = o_rew + up16(8 * N), o_dn = o_sh + up16(4 * N), o_rows = o_dn + up16(N);
   const size_t total = o_rows + (h_rows ? N * e->row_words * 4 : 0);
   if ((rc = staging(e, total)) != MDX_OK) return rc;
+  const bool zc = total <= kZeroCopyBytes;
+  unsigned char* dv = zc ? e->h_pin : e->d_pin;  // what the kernels address
   if (h_env_ids) std::memcpy(e->h_pin, h_env_ids, 4 * N);
   std::memcpy(e->h_pin + in_ids, h_actions, N * e->R);
-  CU(cudaMemcpyAsync(e->d_pin, e->h_pin, in_bytes, cudaMemcpyHostToDevice, st));
-  const int32_t* d_ids = h_env_ids ? reinterpret_cast<const int32_t*>(e->d_pin) : nullptr;
-  rc = mdx_step(e, e->d_pin + in_ids, d_ids, n, reinterpret_cast<double*>(e->d_pin + o_rew),
-                h_shaped ? reinterpret_cast<float*>(e->d_pin + o_sh) : nullptr, e->d_pin + o_dn, flags & MDX_F_AUTO_RESET, stream);
+  if (!zc) CU(cudaMemcpyAsync(e->d_pin, e->h_pin, in_bytes, cudaMemcpyHostToDevice, st));
+  const int32_t* d_ids = h_env_ids ? reinterpret_cast<const int32_t*>(dv) : nullptr;
+  rc = mdx_step(e, dv + in_ids, d_ids, n, reinterpret_cast<double*>(dv + o_rew), h_shaped ? reinterpret_cast<float*>(dv + o_sh) : nullptr,
+                dv + o_dn, flags & MDX_F_AUTO_RESET, stream);
   if (rc != MDX_OK) return rc;
   if (h_rows) {
-    RowArgs a = row_args(e, reinterpret_cast<uint32_t*>(e->d_pin + o_rows), d_ids, n);
+    RowArgs a = row_args(e, reinterpret_cast<uint32_t*>(dv + o_rows), d_ids, n);
     mdx_gather_rows_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(e->base, a);
     CU(cudaGetLastError());
   }
-  CU(cudaMemcpyAsync(e->h_pin + o_rew, e->d_pin + o_rew, total - o_rew, cudaMemcpyDeviceToHost, st));  // ONE copy back
+  if (!zc) CU(cudaMemcpyAsync(e->h_pin + o_rew, e->d_pin + o_rew, total - o_rew, cudaMemcpyDeviceToHost, st));  // ONE copy back
   CU(cudaStreamSynchronize(st));
   if (h_reward) std::memcpy(h_reward, e->h_pin + o_rew, 8 * N);
   if (h_shaped) std::memcpy(h_shaped, e->h_pin + o_sh, 4 * N);

@@ -120,6 +120,9 @@ __global__ void mdx_gather_rows_kernel(const __grid_constant__ KParams p, const 
   for (int k = lane; k < 2 * p.Pp8; k += 32) row[a.off_sched + k] = sched[k];
   const uint32_t* st = reinterpret_cast<const uint32_t*>(p.status + (size_t)env * p.Pp16);
   for (int k = lane; k < (p.Pp16 >> 2); k += 32) row[a.off_status + k] = st[k];
+  // padding words are zero, so that equal states give byte-identical rows
+  for (int k = a.off_robots + p.R + lane; k < a.off_sched; k += 32) row[k] = 0u;
+  for (int k = a.off_status + (p.Pp16 >> 2) + lane; k < a.row_words; k += 32) row[k] = 0u;
 }
 
 // The inverse: rows (validated on the host) -> env state.  The episode cursor, the map id and the generator are not touched.

@@ -100,11 +100,11 @@ class EnvView:
         s = self._s()
         t = s["t"]
         pk = [(j + 1, int(s["pkg_start_row"][j]) + 1, int(s["pkg_start_col"][j]) + 1, int(s["pkg_target_row"][j]) + 1,
-               int(s["pkg_target_col"][j]) + 1, int(s["pkg_start_time"][j]), int(s["pkg_deadline"][j]))
-              for j in range(self.n_packages) if int(s["pkg_start_time"][j]) == t]
+               int(s["pkg_target_col"][j]) + 1, t, int(s["pkg_deadline"][j]))
+              for j in np.flatnonzero(s["pkg_start_time"] == t).tolist()]
         out = StateDict({"time_step": t, "map": self.grid,
-                         "robots": [(int(r) + 1, int(c) + 1, int(k)) for r, c, k in
-                                    zip(s["robot_row"], s["robot_col"], s["robot_carry"])],
+                         "robots": [(r + 1, c + 1, k) for r, c, k in
+                                    zip(s["robot_row"].tolist(), s["robot_col"].tolist(), s["robot_carry"].tolist())],
                          "packages": pk})
         out._view = self
         return out

@@ -28,7 +28,7 @@ def _scratch(grid, R, P, T, K_o, K_p, MR, MP, shaping):
         if len(_SCRATCH) > 16:
             _SCRATCH.pop(next(iter(_SCRATCH))).close()
         b = DeliveryBatch([grid], 1, R, P, T, k_others=K_o, k_packages=K_p, max_robots_in_state=MR,
-                          max_packages_in_state=MP, shaping=shaping, base_seed=0, blank=True)
+                          max_packages_in_state=MP, shaping=shaping, base_seed=0, blank=True, lax_robots=True)
         _SCRATCH[key] = b
     return b
 
@@ -41,20 +41,27 @@ def _pad_packages(n):
 
 
 def _inject(b: DeliveryBatch, state, tracker):
-    robots = [(int(r) - 1, int(c) - 1, int(k)) for (r, c, k) in state["robots"]]
-    P = b.n_packages
-    pk = [(0, 0, 0, 0, 0, 0, 0)] * P
-    pk = list(pk)
+    """(state dict, tracker dict) -> env 0 of the scratch batch as ONE packed row (one host -> device transfer)."""
+    W, P = b.cols_out, b.n_packages
+    row = np.zeros(1, dtype=b._row_dtype)
+    row["t"] = int(state["time_step"])
+    row["robots"][0] = [((int(r) - 1) * W + int(c) - 1) | (int(k) << 16) for (r, c, k) in state["robots"]]
+    sched, status = row["sched"][0], row["status"][0]
+    sched[2, P:] = 0xffff
     prev = 0
     for pid, p in tracker.items():
         pid = int(pid)
         if pid <= prev:
             raise ValueError("tracker dict must be keyed by ascending package id")
         prev = pid
-        pk[pid - 1] = (p["start_pos"][0], p["start_pos"][1], p["target_pos"][0], p["target_pos"][1],
-                       int(p["start_time"]), int(p["deadline"]), _STATUS_CODE[p["status"]])
+        j = pid - 1
+        (sr, sc), (tr, tc) = p["start_pos"], p["target_pos"]
+        if min(sr, sc, tr, tc) < 0 or max(sr, tr) >= b.rows_out or max(sc, tc) >= W:
+            raise ValueError(f"package {pid} outside the map")
+        sched[0, j], sched[1, j], sched[2, j], sched[3, j] = sr * W + sc, tr * W + tc, int(p["start_time"]), int(p["deadline"])
+        status[j] = _STATUS_CODE[p["status"]]
     # a carried id the tracker does not know stays 'None' -> "not in dict" branch of the reference
-    b.set_state(0, int(state["time_step"]), 0.0, robots, pk)
+    b.set_rows([0], row)
 
 
 def _prepare(state, tracker, T, K_o, K_p, MR, MP, shaping=MAPPO_SHAPING, min_pkg=0):
@@ -74,8 +81,8 @@ def convert_observation(env_state_dict, persistent_packages_for_env, current_rob
         obs = np.zeros((6, H, W), np.float32)
         obs[0] = np.asarray(env_state_dict["map"], dtype=np.float32)
         return obs
-    o, _, _, _ = b.featurize()
-    return o[0, current_robot_idx].cpu().numpy()
+    o, _, _, _ = b.featurize_host(vec=False, gstate=False, gvec=False)
+    return o[0, current_robot_idx]
 
 
 def generate_vector_features(env_state_dict, persistent_packages_for_env, current_robot_idx, max_time_steps,
@@ -85,8 +92,8 @@ def generate_vector_features(env_state_dict, persistent_packages_for_env, curren
     if not (0 <= current_robot_idx < len(env_state_dict["robots"])):
         return np.zeros(6 + 5 * K_o + 5 * K_p + 1, dtype=np.float32)
     b, _ = _prepare(env_state_dict, persistent_packages_for_env, max_time_steps, K_o, K_p, 1, 1)
-    _, v, _, _ = b.featurize()
-    return v[0, current_robot_idx].cpu().numpy()
+    _, v, _, _ = b.featurize_host(obs=False, gstate=False, gvec=False)
+    return v[0, current_robot_idx]
 
 
 def convert_global_state(env_state_dict, persistent_packages_for_env, max_time_steps, max_robots_in_state=100,
@@ -94,8 +101,8 @@ def convert_global_state(env_state_dict, persistent_packages_for_env, max_time_s
     """MAPPO/helper.py:167-255 -> ((4, n_rows, n_cols) float32, (6*MR + 7*MP + 1,) float32)."""
     b, _ = _prepare(env_state_dict, persistent_packages_for_env, max_time_steps, 0, 0, int(max_robots_in_state),
                     int(max_packages_in_state))
-    _, _, g, gv = b.featurize()
-    return g[0].cpu().numpy(), gv[0].cpu().numpy()
+    _, _, g, gv = b.featurize_host(obs=False, vec=False)
+    return g[0], gv[0]
 
 
 def compute_shaped_rewards(global_reward, prev_env_state_dict, current_env_state_dict, actions_taken_for_all_agents,

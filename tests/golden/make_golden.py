@@ -151,9 +151,13 @@ def gen_reset_blocks():
 
 
 def run_traj(name, map_name, R, P, T, seed, n_steps, act_seed, policy, K_o, K_p, MR=100, MP=100,
-             feat_every=1, big_vec_every=0, invalid_frac=0.0):
+             feat_every=1, big_vec_every=0, invalid_frac=0.0, stale=False):
     """One env driven like one slot of MAPPO/trainer.py:collect_rollouts (auto-reset on done, the
-    features recorded for a step are those of the state the NEXT action is taken from)."""
+    features recorded for a step are those of the state the NEXT action is taken from).
+
+    stale=True keeps the tracker exactly as MAPPO/trainer.py:229-234 does -- it is NOT cleared when the env resets (SURVEY.md
+    Q7), so 'waiting' entries of earlier episodes survive, shadow new packages with the same id and change the dict order;
+    the tracker's ids (in dict order) and statuses are recorded per step as well."""
     path = os.path.join(REF, map_name)
     e = ref_env.Environment(path, T, R, P, seed=seed)
     H, W = e.n_rows, e.n_cols
@@ -205,6 +209,9 @@ def run_traj(name, map_name, R, P, T, seed, n_steps, act_seed, policy, K_o, K_p,
     feat0 = feats(state, trk.persistent_packages_list[0])
     fi = bi = 0
     n_tracker_mismatch = 0
+    trk_ids = np.zeros((n_steps, P), np.int32)     # dict order after the step's tracker update, 0-padded
+    trk_status = np.zeros((n_steps, P), np.uint8)
+    n_shadowed = 0
     for s in range(n_steps):
         a = rs.randint(0, 15, size=R)
         if greedy is not None:
@@ -255,7 +262,8 @@ def run_traj(name, map_name, R, P, T, seed, n_steps, act_seed, policy, K_o, K_p,
         rec["shaped_qmix"][s] = qmix_helper.compute_shaped_rewards(r, state, nxt, acts, pp_prev, R)
         if done:
             nxt = e.reset()
-            trk.clear(0)  # env-truth semantics (QMIX/IDQ/legacy clear; default of the build)
+            if not stale:
+                trk.clear(0)  # env-truth semantics (QMIX/IDQ/legacy clear; default of the build)
             trk.update(0, nxt)
             reset_pkgs.append(np.array([[p.start[0] * W + p.start[1], p.target[0] * W + p.target[1],
                                          p.start_time, p.deadline] for p in e.packages], np.int32))
@@ -268,6 +276,11 @@ def run_traj(name, map_name, R, P, T, seed, n_steps, act_seed, policy, K_o, K_p,
         pp = trk.persistent_packages_list[0]
         if pp != truth_tracker(e) or list(pp) != list(truth_tracker(e)):
             n_tracker_mismatch += 1
+        for k, (pid, pv) in enumerate(pp.items()):
+            trk_ids[s, k] = pid
+            trk_status[s, k] = STATUS[pv["status"]]
+            if (pv["start_pos"], pv["deadline"]) != (e.packages[pid - 1].start, e.packages[pid - 1].deadline):
+                n_shadowed += 1
         state = nxt
         if s % feat_every == 0:
             obs[fi], vec[fi], gst[fi], gvec[fi] = feats(state, pp)
@@ -276,8 +289,9 @@ def run_traj(name, map_name, R, P, T, seed, n_steps, act_seed, policy, K_o, K_p,
             vec_big[bi] = np.stack([mappo_helper.generate_vector_features(state, pp, i, T) for i in range(R)])
             gvec_q[bi] = qmix_helper.convert_global_state(state, pp, T, 10, 20)[1]
             bi += 1
-    assert n_tracker_mismatch == 0, n_tracker_mismatch
-    meta = dict(name=name, map=map_name, R=R, P=P, T=T, seed=seed, n_steps=n_steps, act_seed=act_seed,
+    assert stale or n_tracker_mismatch == 0, n_tracker_mismatch
+    assert not stale or (n_tracker_mismatch > 0 and n_shadowed > 0), "the stale fixture must exercise the artefact"
+    meta = dict(stale=bool(stale), n_tracker_mismatch=n_tracker_mismatch, n_shadowed=n_shadowed, name=name, map=map_name, R=R, P=P, T=T, seed=seed, n_steps=n_steps, act_seed=act_seed,
                 policy=policy, K_o=K_o, K_p=K_p, MR=MR, MP=MP, feat_every=feat_every,
                 big_vec_every=big_vec_every, H=H, W=W, n_resets=len(reset_pkgs),
                 n_delivered_total=int((rec["reward"] > 0.5).sum()))
@@ -286,7 +300,8 @@ def run_traj(name, map_name, R, P, T, seed, n_steps, act_seed, policy, K_o, K_p,
         reset_pkgs=np.stack(reset_pkgs), reset_robots=np.stack(reset_robots),
         obs0=feat0[0], vec0=feat0[1], gstate0=feat0[2], gvec0=feat0[3],
         obs=obs, vec=vec, gstate=gst, gvec=gvec, vec_big=vec_big, gvec_qmix=gvec_q,
-        feat_steps=np.array(feat_steps, np.int32), big_steps=np.array(big_steps, np.int32), **rec)
+        feat_steps=np.array(feat_steps, np.int32), big_steps=np.array(big_steps, np.int32), trk_ids=trk_ids,
+        trk_status=trk_status, **rec)
     sz = os.path.getsize(os.path.join(HERE, f"traj_{name}.npz"))
     print(f"traj_{name}.npz  {sz/1024:.0f} KiB  resets={len(reset_pkgs)-1} "
           f"sum_r={rec['reward'].sum():.4f} deliveries~{meta['n_delivered_total']} "
@@ -312,8 +327,9 @@ def gen_kat_a():
                 kat_a_delivered=np.int32(delivered))
 
 
-def gen_kat_b():
-    """KAT-B: 5 vectorised envs, 1200 steps with auto-reset (cleared tracker)."""
+def gen_kat_b(stale=False):
+    """KAT-B: 5 vectorised envs, 1200 steps with auto-reset; cleared tracker (sum 1627.37), or -- stale=True -- the tracker
+    handling of MAPPO/trainer.py:229-234 itself, which never clears it (sum 1243.89)."""
     ve = MappoVec(ref_env.Environment, 5, map_file=os.path.join(REF, "map1.txt"), n_robots=5, n_packages=50,
                   max_time_steps=500, seed=42)
     states = ve.reset()
@@ -336,14 +352,16 @@ def gen_kat_b():
             dones[s, i] = d[i]
             if d[i]:
                 nxt[i] = ve.envs[i].reset()
-                trk.clear(i)
+                if not stale:
+                    trk.clear(i)
             trk.update(i, nxt[i])
             v = mappo_helper.generate_vector_features(nxt[i], trk.persistent_packages_list[i], 0, 500, 4, 5)
             g = mappo_helper.convert_global_state(nxt[i], trk.persistent_packages_list[i], 500)[1]
             gsum[s, i] = float(v.astype(np.float64).sum() + g.astype(np.float64).sum())
         states = nxt
-    print("KAT-B shaped sum", shaped.astype(np.float64).sum())
-    return dict(kat_b_shaped=shaped, kat_b_reward=envr, kat_b_done=dones, kat_b_featsum=gsum)
+    print("KAT-B shaped sum", shaped.astype(np.float64).sum(), "(stale tracker)" if stale else "(cleared tracker)")
+    pre = "kat_b_stale_" if stale else "kat_b_"
+    return {pre + "shaped": shaped, pre + "reward": envr, pre + "done": dones, pre + "featsum": gsum}
 
 
 def gen_readme_random():
@@ -549,12 +567,23 @@ def main():
     run_traj("map3_small", "map3.txt", 7, 20, 100, 6, 250, 8, "mixed", 3, 3, MR=10, MP=20, feat_every=1)
 
 
+def gen_stale():
+    """SURVEY.md Q7 / VERDICT r1 row J1: what MAPPO/trainer.py really feeds the featurisers after the first auto-reset."""
+    np.savez_compressed(os.path.join(HERE, "kats_stale.npz"), **gen_kat_b(stale=True))
+    run_traj("map1_stale", "map1.txt", 5, 30, 40, 61, 420, 11, "homing", 4, 5, feat_every=1, big_vec_every=7, stale=True)
+    run_traj("map7_stale", "map.txt", 4, 12, 25, 62, 300, 12, "mixed", 3, 5, MR=10, MP=20, feat_every=1, big_vec_every=5, stale=True)
+    run_traj("map5_stale", "map5.txt", 10, 100, 60, 63, 250, 13, "homing", 9, 5, feat_every=2, invalid_frac=0.02, stale=True)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "greedy":
         gen_greedy()
+    elif len(sys.argv) > 1 and sys.argv[1] == "stale":
+        gen_stale()
     elif len(sys.argv) > 1 and sys.argv[1] == "alt":
         gen_alt()
     else:
         main()
         gen_greedy()
         gen_alt()
+        gen_stale()
