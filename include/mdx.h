@@ -62,6 +62,17 @@ enum {
                                 per-call converter drop-ins, which the reference's converters accept too); such an instance must only \
                                 be featurised / shaped, never stepped */
 
+#define MDX_CFG_STALE_TRACKER 8 /* OPT-IN: reproduce what MAPPO/trainer.py REALLY feeds compute_shaped_rewards and the three        \
+                                   converters.  The trainer keeps one package dict per env (`persistent_packages_list`, :91-130)   \
+                                   and never clears it when the env auto-resets (:229-234; the QMIX / IDQ / legacy trainers do):   \
+                                   'waiting' entries of earlier episodes survive, shadow the new episode's packages with the same \
+                                   id and change the dict (= iteration) order.  With this flag every env carries that dict on the   \
+                                   device, in insertion order; mdx_step* maintain it exactly like the trainer's loop (a done env    \
+                                   that is auto-reset shows it only the RESET state), mdx_reset applies the update for the reset     \
+                                   state without clearing, and the shaped reward / featurisers read IT instead of the env truth.    \
+                                   The dict starts empty: call mdx_reset before the first step, as the trainer does.  Default (flag \
+                                   off) = env truth = a tracker cleared on reset. */
+
 /* Shaping constants of compute_shaped_rewards, in this order (MAPPO/helper.py:271-279,
  * QMIX/helper.py:270-278). */
 typedef struct mdx_shaping {
@@ -215,12 +226,26 @@ int32_t mdx_set_states(mdx_env* env, const int32_t* h_env_ids, int32_t n, const 
 int32_t mdx_step_host(mdx_env* env, const uint8_t* h_actions, const int32_t* h_env_ids, int32_t n, double* h_reward,
                       float* h_shaped, uint8_t* h_done, void* h_rows, uint32_t flags, void* stream);
 
+/* mdx_shaped_reward for HOST callers (the per-call compute_shaped_rewards drop-in): all arguments and the result are host
+ * arrays of the shapes mdx_shaped_reward documents, for ALL envs of the instance; one launch + one synchronisation. */
+int32_t mdx_shaped_reward_host(mdx_env* env, const uint32_t* h_cur_robots, const int32_t* h_cur_t, const uint8_t* h_actions,
+                               const double* h_global_reward, float* h_out, void* stream);
+
 /* mdx_featurize for HOST callers (the per-call helper drop-ins convert_observation / generate_vector_features /
  * convert_global_state return numpy, MAPPO/helper.py:6-255): the listed envs' feature tensors straight into host arrays
  * (any may be NULL), one launch + one synchronisation; small results are written by the kernel directly into pinned host
  * memory, larger ones take one copy back. */
 int32_t mdx_featurize_host(mdx_env* env, const int32_t* h_env_ids, int32_t n, float* h_obs, float* h_vec, float* h_gstate,
                            float* h_gvec, void* stream);
+
+/* MDX_CFG_STALE_TRACKER instances only.  mdx_tracker_clear empties the dict of the listed envs (HOST ids, NULL = all): what the
+ * QMIX / IDQ trainers do on reset (QMIX/trainer.py:523-526).  mdx_tracker_get / mdx_tracker_set copy one env's dict to / from the
+ * host in dict order (synchronous; tests, and the per-call converter drop-ins, which receive arbitrary dicts): h_rows5 is u16
+ * [5][Pp8] = package id, start cell, target cell, start_time, deadline; h_status u8 [Pp16] = 1 waiting / 2 in_transit;
+ * Pp8 = max(8, P rounded up to 8), Pp16 = max(16, P rounded up to 16); ids must be distinct and in 1..P. */
+int32_t mdx_tracker_clear(mdx_env* env, const int32_t* h_env_ids, int32_t n, void* stream);
+int32_t mdx_tracker_get(mdx_env* env, int32_t env_id, int32_t* h_n, uint16_t* h_rows5, uint8_t* h_status, void* stream);
+int32_t mdx_tracker_set(mdx_env* env, int32_t env_id, int32_t n, const uint16_t* h_rows5, const uint8_t* h_status, void* stream);
 
 /* d_out8 [8] int64 = {episodes_done, robot_moves, on_time, late, pickups,
  * env_steps, sum_episode_len, starved_envs} summed over this instance's envs (cumulative since

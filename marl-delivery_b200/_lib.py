@@ -14,6 +14,7 @@ MDX_F_ACTIONS_I64 = 2
 MDX_CFG_BLANK = 1
 MDX_CFG_BFS_SHAPING = 2
 MDX_CFG_LAX_ROBOTS = 4
+MDX_CFG_STALE_TRACKER = 8
 MDX_MAX_ROBOTS = 32
 
 
@@ -81,7 +82,11 @@ SYMBOLS = {
     "mdx_get_state": (C.c_int32, [_VP, C.c_int32, C.POINTER(StateView), _VP]),
     "mdx_set_state": (C.c_int32, [_VP, C.c_int32, C.POINTER(StateView), _VP]),
     "mdx_episode_stats": (C.c_int32, [_VP, _VP, _VP]),
+    "mdx_shaped_reward_host": (C.c_int32, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "mdx_featurize_host": (C.c_int32, [_VP, _VP, C.c_int32, _VP, _VP, _VP, _VP, _VP]),
+    "mdx_tracker_clear": (C.c_int32, [_VP, _VP, C.c_int32, _VP]),
+    "mdx_tracker_get": (C.c_int32, [_VP, C.c_int32, _VP, _VP, _VP, _VP]),
+    "mdx_tracker_set": (C.c_int32, [_VP, C.c_int32, C.c_int32, _VP, _VP, _VP]),
     "mdx_step_n": (C.c_int32, [_VP, _VP, C.c_int32, _VP, _VP, _VP, C.c_uint32, _VP]),
     "mdx_state_row_bytes": (C.c_int64, [_VP]),
     "mdx_get_states": (C.c_int32, [_VP, _VP, C.c_int32, _VP, _VP]),

@@ -53,7 +53,8 @@ class DeliveryBatch:
                  delay_reward: float = 1.0, seeds=None, base_seed: int = 2025, env_map=None,
                  k_others: int = 100, k_packages: int = 100, max_robots_in_state: int = 100,
                  max_packages_in_state: int = 100, shaping=MAPPO_SHAPING, device=None, ring_episodes=None,
-                 sampler_threads=None, blank: bool = False, bfs_shaping: bool = False, lax_robots: bool = False):
+                 sampler_threads=None, blank: bool = False, bfs_shaping: bool = False, lax_robots: bool = False,
+                 stale_tracker: bool = False):
         """`ring_episodes` / `sampler_threads` are accepted and ignored (v1 pre-sampled reset blocks on the host into a ring;
         since v2 every env draws its next reset block on the device, from its own MT19937 stream, when it resets)."""
         L = _lib.lib()
@@ -100,7 +101,8 @@ class DeliveryBatch:
         cfg.device = int(self.device.index)
         cfg.ring_episodes, cfg.sampler_threads = 0, 0
         cfg.flags = ((_lib.MDX_CFG_BLANK if blank else 0) | (_lib.MDX_CFG_BFS_SHAPING if bfs_shaping else 0)
-                     | (_lib.MDX_CFG_LAX_ROBOTS if lax_robots else 0))
+                     | (_lib.MDX_CFG_LAX_ROBOTS if lax_robots else 0) | (_lib.MDX_CFG_STALE_TRACKER if stale_tracker else 0))
+        self.stale_tracker = bool(stale_tracker)
         handle = C.c_void_p()
         _lib.check(L.mdx_create(C.byref(cfg), C.byref(handle)))
         self._h = handle
@@ -366,6 +368,19 @@ class DeliveryBatch:
                                              self._stream()))
         return out
 
+    def shaped_reward_host(self, cur_robots: np.ndarray, cur_t: np.ndarray, codes: np.ndarray, global_reward: np.ndarray) -> np.ndarray:
+        """shaped_reward() for HOST callers: cur_robots uint32 [n, R] = cell | carry << 16, cur_t int32 [n], codes uint8 [n, R],
+        global_reward float64 [n] -> float32 [n]; one launch + one synchronisation inside one C call."""
+        n, R = self.n_envs, self.n_robots
+        cur_robots = np.ascontiguousarray(cur_robots, dtype=np.uint32).reshape(n, R)
+        cur_t = np.ascontiguousarray(cur_t, dtype=np.int32).reshape(n)
+        codes = np.ascontiguousarray(codes, dtype=np.uint8).reshape(n, R)
+        gr = np.ascontiguousarray(global_reward, dtype=np.float64).reshape(n)
+        out = np.empty(n, np.float32)
+        _lib.check(self._L.mdx_shaped_reward_host(self._h, cur_robots.ctypes.data, cur_t.ctypes.data, codes.ctypes.data, gr.ctypes.data,
+                                                  out.ctypes.data, self._stream()))
+        return out
+
     # ------------------------------------------------------------------ callers either side of the path
     def greedy_actions(self, ids=None, out=None) -> torch.Tensor:
         """GreedyAgents.get_actions (greedyagent.py:119-174) for the listed envs -> uint8 [n, R] action codes on
@@ -560,6 +575,38 @@ class DeliveryBatch:
                                          MDX_F_AUTO_RESET if auto_reset else 0, self._stream()))
         self._version += 1
         return reward, shaped, done.astype(bool), rows
+
+    # ------------------------------------------------------------------ the MAPPO trainer's tracker (stale_tracker=True)
+    def tracker_clear(self, ids=None):
+        """Empty the package dict of the listed envs (all when None): what QMIX/trainer.py:523-526 does on reset."""
+        if ids is None:
+            _lib.check(self._L.mdx_tracker_clear(self._h, None, 0, self._stream()))
+        else:
+            h = np.ascontiguousarray(np.asarray(ids, dtype=np.int32).reshape(-1))
+            _lib.check(self._L.mdx_tracker_clear(self._h, h.ctypes.data, int(h.size), self._stream()))
+
+    def get_tracker(self, i: int) -> list:
+        """The dict of env i in dict (insertion) order: [(package id, start cell, target cell, start_time, deadline, status)]."""
+        P = self.n_packages
+        Pp8, Pp16 = max(8, (P + 7) // 8 * 8), max(16, (P + 15) // 16 * 16)
+        n = C.c_int32(0)
+        rows = np.zeros((5, Pp8), np.uint16)
+        st = np.zeros(Pp16, np.uint8)
+        _lib.check(self._L.mdx_tracker_get(self._h, int(i), C.byref(n), rows.ctypes.data, st.ctypes.data, self._stream()))
+        return [(int(rows[0, k]), int(rows[1, k]), int(rows[2, k]), int(rows[3, k]), int(rows[4, k]), int(st[k])) for k in range(n.value)]
+
+    def set_tracker(self, i: int, entries):
+        """entries: [(package id, start cell, target cell, start_time, deadline, status 1|2)] in dict order."""
+        P = self.n_packages
+        Pp8, Pp16 = max(8, (P + 7) // 8 * 8), max(16, (P + 15) // 16 * 16)
+        if len(entries) > P:
+            raise ValueError("a tracker holds at most n_packages entries")
+        rows = np.zeros((5, Pp8), np.uint16)
+        st = np.zeros(Pp16, np.uint8)
+        for k, e in enumerate(entries):
+            rows[:, k] = e[:5]
+            st[k] = e[5]
+        _lib.check(self._L.mdx_tracker_set(self._h, int(i), len(entries), rows.ctypes.data, st.ctypes.data, self._stream()))
 
     def set_state(self, i: int, t, total_reward, robots, packages):
         """robots: [(row, col, carry)] 0-based; packages: [(start_row, start_col, target_row, target_col,

@@ -8,7 +8,7 @@ FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=fa
 mkdir -p obj
 : > build.log
 pids=()
-for src in mdx_api.cu mdx_launch1.cu mdx_launch2.cu mdx_launch3.cu mdx_launch5.cu mdx_extra.cu sampler.cpp; do
+for src in mdx_api.cu mdx_launch1.cu mdx_launch2.cu mdx_launch3.cu mdx_launch5.cu mdx_launch1t.cu mdx_launch2t.cu mdx_launch3t.cu mdx_extra.cu sampler.cpp; do
   [ -f "$src" ] || continue
   ( $NVCC $FLAGS -c -o "obj/${src%.*}.o" "$src" > "obj/${src%.*}.log" 2>&1 ) &
   pids+=($!)

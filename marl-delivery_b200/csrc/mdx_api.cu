@@ -200,6 +200,9 @@ int32_t mdx_destroy(mdx_env* e) {
   cudaFree(e->d_counters);
   cudaFree(e->d_env_map);
   cudaFree(e->d_ids);
+  cudaFree(e->d_trk);
+  cudaFree(e->d_trk_status);
+  cudaFree(e->d_trk_n);
   cudaFree(e->d_pin);
   cudaFreeHost(e->h_pin);
   if (e->pin_busy) cudaEventDestroy(e->pin_busy);
@@ -222,8 +225,11 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   if (cfg->k_others < 0 || cfg->k_packages < 0 || cfg->max_robots_in_state < 0 || cfg->max_packages_in_state < 0)
     return fail(MDX_E_INVALID, "feature sizes must be non-negative");
 
+  if ((cfg->flags & MDX_CFG_STALE_TRACKER) && (cfg->flags & MDX_CFG_BFS_SHAPING))
+    return fail(MDX_E_INVALID, "MDX_CFG_STALE_TRACKER and MDX_CFG_BFS_SHAPING cannot be combined");
   std::unique_ptr<mdx_env> e(new mdx_env());
   e->cfg = *cfg;
+  e->stale = (cfg->flags & MDX_CFG_STALE_TRACKER) != 0;
   e->device = cfg->device;
   e->n = cfg->n_envs;
   e->R = cfg->n_robots;
@@ -393,7 +399,10 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
     // (the fused IDQ featuriser keeps its H*W urgency plane in the stage)
     const int stage_floats = std::max(std::max(rpf * b.D + 8, b.stage_b + 7 * std::min(e->P, b.MP) + 12), b.HW + 4);
     off = round_up(off + 4 * stage_floats, 16);
+    const int o_trk = off;
+    if (e->stale) off = round_up(off + 10 * b.Pp8 + b.Pp16 + 2 * b.Pp8, 16);
     if (commit) {
+      b.off_trk = o_trk;
       b.off_sched = o_sched, b.off_status = o_status, b.off_wlist = o_wlist, b.off_wkey = o_wkey, b.off_rinfo = o_rinfo;
       b.off_alist = o_alist, b.off_sel = o_sel, b.off_masks = o_masks, b.off_stage = o_stage;
       b.vec_rows_per_flush = rpf;
@@ -481,6 +490,14 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   CUX(cudaMalloc(&raw->d_counters, sizeof(uint32_t) * n * 8));
   CUX(cudaMalloc(&raw->d_env_map, sizeof(int32_t) * n));
   CUX(cudaMalloc(&raw->d_ids, sizeof(int32_t) * n));
+  if (e->stale) {
+    CUX(cudaMalloc(&raw->d_trk, sizeof(uint16_t) * n * 5 * b.Pp8));
+    CUX(cudaMalloc(&raw->d_trk_status, n * b.Pp16));
+    CUX(cudaMalloc(&raw->d_trk_n, sizeof(int32_t) * n));
+    CUX(cudaMemset(raw->d_trk, 0, sizeof(uint16_t) * n * 5 * b.Pp8));
+    CUX(cudaMemset(raw->d_trk_status, 0, n * b.Pp16));
+    CUX(cudaMemset(raw->d_trk_n, 0, sizeof(int32_t) * n));
+  }
   CUX(cudaMemset(raw->d_t, 0, sizeof(int32_t) * n));
   CUX(cudaMemset(raw->d_ep, 0, sizeof(int32_t) * n));
   CUX(cudaMemset(raw->d_total, 0, sizeof(double) * n));
@@ -505,6 +522,9 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   b.status = raw->d_status;
   b.cur = raw->d_cur;
   b.counters = raw->d_counters;
+  b.trk = raw->d_trk;
+  b.trk_status = raw->d_trk_status;
+  b.trk_n = raw->d_trk_n;
   b.env_map = cfg->n_maps > 1 ? raw->d_env_map : nullptr;
 
   CUX2(cudaMemset(raw->d_robots, 0, sizeof(uint32_t) * n * e->R));
@@ -559,11 +579,27 @@ int32_t mdx_get_dims(const mdx_env* e, mdx_dims* out) {
   return MDX_OK;
 }
 
+static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int32_t* d_env_ids, int32_t n, double* d_reward,
+                       float* d_shaped, uint8_t* d_done, float* d_obs, float* d_vec, float* d_gstate, float* d_gvec,
+                       uint32_t flags, void* stream, double* d_agent = nullptr, int ops_as_int = 0, float* d_obs6 = nullptr,
+                       float* d_g7 = nullptr, uint32_t internal_flags = 0);
+
+// MDX_CFG_STALE_TRACKER: the trainer's dict sees the reset state (MAPPO/trainer.py:232-233) -- internal flag 4 of the
+// featurise-mode kernel with no outputs; internal flag 8 empties the dict instead.
+static int tracker_pass(mdx_env* e, const int32_t* d_ids, int n, uint32_t internal_flags, void* stream) {
+  return step_common(e, 2, nullptr, d_ids, n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, stream, nullptr, 0, nullptr,
+                     nullptr, internal_flags);
+}
+
 int32_t mdx_reset(mdx_env* e, const int32_t* h_env_ids, int32_t n, void* stream) {
   if (!e) return fail(MDX_E_INVALID, "null env");
   DeviceGuard g(e->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (h_env_ids == nullptr) return launch_reset(e, nullptr, e->n, 1u, st);
+  if (h_env_ids == nullptr) {
+    int rc = launch_reset(e, nullptr, e->n, 1u, st);
+    if (rc == MDX_OK && e->stale) rc = tracker_pass(e, nullptr, e->n, 4u, stream);
+    return rc;
+  }
   if (n < 0) return fail(MDX_E_INVALID, "negative count");
   for (int k = 0; k < n; ++k)
     if (h_env_ids[k] < 0 || h_env_ids[k] >= e->n) return fail(MDX_E_INVALID, "env id %d out of range", h_env_ids[k]);
@@ -584,6 +620,7 @@ int32_t mdx_reset(mdx_env* e, const int32_t* h_env_ids, int32_t n, void* stream)
     // stream order by the next pass
     CU(cudaMemcpyAsync(e->d_ids, pass.data(), sizeof(int32_t) * pass.size(), cudaMemcpyHostToDevice, st));
     int rc = launch_reset(e, e->d_ids, (int)pass.size(), 1u, st);
+    if (rc == MDX_OK && e->stale) rc = tracker_pass(e, e->d_ids, (int)pass.size(), 4u, stream);
     if (rc != MDX_OK) return rc;
     remaining.swap(later);
   }
@@ -599,9 +636,11 @@ int32_t mdx_prefetch(mdx_env* e, int32_t ahead, void* stream) {
 
 static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int32_t* d_env_ids, int32_t n, double* d_reward,
                        float* d_shaped, uint8_t* d_done, float* d_obs, float* d_vec, float* d_gstate, float* d_gvec,
-                       uint32_t flags, void* stream, double* d_agent = nullptr, int ops_as_int = 0, float* d_obs6 = nullptr,
-                       float* d_g7 = nullptr) {
+                       uint32_t flags, void* stream, double* d_agent, int ops_as_int, float* d_obs6, float* d_g7, uint32_t internal_flags) {
   if (!e) return fail(MDX_E_INVALID, "null env");
+  if (e->stale && (d_agent || mode == 5))
+    return fail(MDX_E_INVALID, "the IDQ entry points read the env truth (IDQ/trainer.py:236 clears its tracker); not available on an "
+                               "MDX_CFG_STALE_TRACKER instance");
   if ((mode & 1) && !d_actions) return fail(MDX_E_INVALID, "actions are required");
   if ((mode & 1) && (e->cfg.flags & MDX_CFG_LAX_ROBOTS)) return fail(MDX_E_INVALID, "an MDX_CFG_LAX_ROBOTS instance cannot be stepped");
   if (d_env_ids == nullptr && n != e->n) return fail(MDX_E_INVALID, "n must equal n_envs when env ids are not given (got %d, have %d)", n, e->n);
@@ -616,7 +655,7 @@ static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int
   kp.actions = d_actions;
   kp.env_ids = d_env_ids;
   kp.n = n;
-  kp.flags = flags & 3u;
+  kp.flags = (flags & 3u) | internal_flags;
   kp.out_reward = d_reward;
   kp.out_shaped = d_shaped;
   kp.out_done = d_done;
@@ -629,6 +668,7 @@ static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int
   kp.alt_obs6 = d_obs6;
   kp.alt_g7 = d_g7;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (e->stale) return mode == 1 ? launch_env_kernel_trk_1(e, kp, st) : mode == 2 ? launch_env_kernel_trk_2(e, kp, st) : launch_env_kernel_trk_3(e, kp, st);
   if (mode == 5) return launch_env_kernel_5(e, kp, st);
   if (mode == 1) return launch_env_kernel_1(e, kp, st);
   if (mode == 2) return launch_env_kernel_2(e, kp, st);
@@ -716,15 +756,19 @@ static int shape_common(mdx_env* e, const uint32_t* d_cur_robots, const int32_t*
   kp.global_reward = d_global_reward;
   kp.out_shaped = d_out;
   kp.n = e->n;
-  const int spw = e->base.off_alist;
+  if (e->stale && d_agent) return fail(MDX_E_INVALID, "IDQ reward_shaping reads the env truth; not available on an MDX_CFG_STALE_TRACKER instance");
+  const int spw = e->stale ? e->base.smem_per_warp : e->base.off_alist;
   const int wpb = pick_wpb(e, spw);
   kp.smem_per_warp = spw;
   const size_t smem = (size_t)kLutBytes + (size_t)wpb * spw;
+  const void* fn = e->stale ? reinterpret_cast<const void*>(mdx_shape_kernel<true>) : reinterpret_cast<const void*>(mdx_shape_kernel<false>);
   {
-    int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(mdx_shape_kernel), smem, -1);
+    int rc = ensure_dynamic_smem(fn, smem, -1);
     if (rc != MDX_OK) return rc;
   }
-  mdx_shape_kernel<<<(unsigned)((e->n + wpb - 1) / wpb), wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(kp);
+  const unsigned grid = (unsigned)((e->n + wpb - 1) / wpb);
+  if (e->stale) mdx_shape_kernel<true><<<grid, wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(kp);
+  else mdx_shape_kernel<false><<<grid, wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(kp);
   CU(cudaGetLastError());
   return MDX_OK;
 }
@@ -786,6 +830,32 @@ int32_t mdx_set_states(mdx_env* e, const int32_t* h_env_ids, int32_t n, const vo
   mdx_scatter_rows_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(e->base, a);
   CU(cudaGetLastError());
   CU(cudaEventRecord(e->pin_busy, st));  // the host buffer is read until here (by the copy, or by the kernel itself)
+  return MDX_OK;
+}
+
+int32_t mdx_shaped_reward_host(mdx_env* e, const uint32_t* h_cur_robots, const int32_t* h_cur_t, const uint8_t* h_actions,
+                               const double* h_global_reward, float* h_out, void* stream) {
+  if (!e || !h_cur_robots || !h_cur_t || !h_actions || !h_global_reward || !h_out) return fail(MDX_E_INVALID, "null argument");
+  DeviceGuard g(e->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t N = (size_t)e->n;
+  const size_t o_rob = 0, o_t = o_rob + up16(4 * N * e->R), o_act = o_t + up16(4 * N), o_gr = o_act + up16(N * e->R), o_out = o_gr + up16(8 * N);
+  const size_t total = o_out + up16(4 * N);
+  int rc = staging(e, total);
+  if (rc != MDX_OK) return rc;
+  const bool zc = total <= kZeroCopyBytes;
+  unsigned char* dv = zc ? e->h_pin : e->d_pin;
+  std::memcpy(e->h_pin + o_rob, h_cur_robots, 4 * N * e->R);
+  std::memcpy(e->h_pin + o_t, h_cur_t, 4 * N);
+  std::memcpy(e->h_pin + o_act, h_actions, N * e->R);
+  std::memcpy(e->h_pin + o_gr, h_global_reward, 8 * N);
+  if (!zc) CU(cudaMemcpyAsync(e->d_pin, e->h_pin, o_out, cudaMemcpyHostToDevice, st));
+  rc = mdx_shaped_reward(e, reinterpret_cast<const uint32_t*>(dv + o_rob), reinterpret_cast<const int32_t*>(dv + o_t), dv + o_act,
+                         reinterpret_cast<const double*>(dv + o_gr), reinterpret_cast<float*>(dv + o_out), stream);
+  if (rc != MDX_OK) return rc;
+  if (!zc) CU(cudaMemcpyAsync(e->h_pin + o_out, e->d_pin + o_out, 4 * N, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  std::memcpy(h_out, e->h_pin + o_out, 4 * N);
   return MDX_OK;
 }
 
@@ -931,6 +1001,60 @@ int32_t mdx_set_state(mdx_env* e, int32_t id, const mdx_state_view* in, void* st
     status[j] = (uint8_t)in->pkg_status[j];
   }
   return mdx_set_states(e, &id, 1, row.data(), stream);  // (validates time, free / distinct robot cells, deadline range)
+}
+
+int32_t mdx_tracker_clear(mdx_env* e, const int32_t* h_env_ids, int32_t n, void* stream) {
+  if (!e) return fail(MDX_E_INVALID, "null env");
+  if (!e->stale) return fail(MDX_E_INVALID, "not an MDX_CFG_STALE_TRACKER instance");
+  DeviceGuard g(e->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (h_env_ids == nullptr) {
+    CU(cudaMemsetAsync(e->d_trk_n, 0, sizeof(int32_t) * (size_t)e->n, st));
+    return MDX_OK;
+  }
+  int rc = check_ids(e, h_env_ids, n, true);
+  if (rc != MDX_OK || n == 0) return rc;
+  CU(cudaMemcpyAsync(e->d_ids, h_env_ids, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));  // pageable source: staged before return
+  return tracker_pass(e, e->d_ids, n, 8u, stream);
+}
+
+int32_t mdx_tracker_get(mdx_env* e, int32_t id, int32_t* h_n, uint16_t* h_rows5, uint8_t* h_status, void* stream) {
+  if (!e || !h_n || !h_rows5 || !h_status) return fail(MDX_E_INVALID, "null argument");
+  if (!e->stale) return fail(MDX_E_INVALID, "not an MDX_CFG_STALE_TRACKER instance");
+  if (id < 0 || id >= e->n) return fail(MDX_E_INVALID, "env id %d out of range", id);
+  DeviceGuard g(e->device);
+  const KParams& b = e->base;
+  CU(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  CU(cudaMemcpy(h_n, e->d_trk_n + id, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(h_rows5, e->d_trk + (size_t)id * 5 * b.Pp8, sizeof(uint16_t) * 5 * b.Pp8, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(h_status, e->d_trk_status + (size_t)id * b.Pp16, (size_t)b.Pp16, cudaMemcpyDeviceToHost));
+  return MDX_OK;
+}
+
+int32_t mdx_tracker_set(mdx_env* e, int32_t id, int32_t n, const uint16_t* h_rows5, const uint8_t* h_status, void* stream) {
+  if (!e || !h_rows5 || !h_status) return fail(MDX_E_INVALID, "null argument");
+  if (!e->stale) return fail(MDX_E_INVALID, "not an MDX_CFG_STALE_TRACKER instance");
+  if (id < 0 || id >= e->n) return fail(MDX_E_INVALID, "env id %d out of range", id);
+  if (n < 0 || n > e->P) return fail(MDX_E_INVALID, "a tracker holds at most n_packages entries");
+  const KParams& b = e->base;
+  const MapHost& m = e->maps[(size_t)e->env_map[(size_t)id]];
+  const int Wo = e->W_out;
+  const long long dl_cap = std::min<long long>(65535, ((1LL << (32 - b.key_wbits)) - 2) / b.nranks_max - 1);
+  std::vector<char> seen((size_t)e->P + 1, 0);
+  for (int k = 0; k < n; ++k) {
+    const int pid = h_rows5[k], s = h_rows5[b.Pp8 + k], t = h_rows5[2 * b.Pp8 + k];
+    if (pid < 1 || pid > e->P || seen[(size_t)pid]) return fail(MDX_E_INVALID, "tracker entry %d: package ids must be distinct and in 1..n_packages", k);
+    seen[(size_t)pid] = 1;
+    if (s / Wo >= m.rows || s % Wo >= m.cols || t / Wo >= m.rows || t % Wo >= m.cols) return fail(MDX_E_INVALID, "tracker entry %d outside the map", k);
+    if ((long long)h_rows5[4 * b.Pp8 + k] > dl_cap) return fail(MDX_E_INVALID, "tracker entry %d: deadline out of range", k);
+    if (h_status[k] != ST_WAITING && h_status[k] != ST_IN_TRANSIT) return fail(MDX_E_INVALID, "tracker entry %d: status must be waiting or in_transit", k);
+  }
+  DeviceGuard g(e->device);
+  CU(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  CU(cudaMemcpy(e->d_trk_n + id, &n, sizeof(int32_t), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(e->d_trk + (size_t)id * 5 * b.Pp8, h_rows5, sizeof(uint16_t) * 5 * b.Pp8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(e->d_trk_status + (size_t)id * b.Pp16, h_status, (size_t)b.Pp16, cudaMemcpyHostToDevice));
+  return MDX_OK;
 }
 
 int32_t mdx_episode_stats(mdx_env* e, int64_t* d_out8, void* stream) {

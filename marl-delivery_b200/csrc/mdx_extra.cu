@@ -431,7 +431,7 @@ uint64_t config_hash(const mdx_env* e) {
   mix(&b.delivery_reward, sizeof(double));
   mix(&b.delay_reward, sizeof(double));
   mix(b.shaping, sizeof(b.shaping));
-  const int32_t sizes[6] = {b.K_o, b.K_p, b.MR, b.MP, b.shaping_bfs, 0};
+  const int32_t sizes[6] = {b.K_o, b.K_p, b.MR, b.MP, b.shaping_bfs, e->stale ? 1 : 0};
   mix(sizes, sizeof(sizes));
   return h;
 }
@@ -450,6 +450,11 @@ std::vector<Seg> device_segments(mdx_env* e) {
       {e->d_counters, sizeof(uint32_t) * n * 8},
       {e->d_mt, sizeof(uint32_t) * n * 624},
   };
+  if (e->stale) {  // the trainer's package dicts are part of the state (MDX_CFG_STALE_TRACKER)
+    s.push_back({e->d_trk, sizeof(uint16_t) * n * 5 * b.Pp8});
+    s.push_back({e->d_trk_status, n * b.Pp16});
+    s.push_back({e->d_trk_n, sizeof(int32_t) * n});
+  }
   if (e->d_greedy) {
     s.push_back({e->d_greedy, sizeof(uint32_t) * n * 32});
     s.push_back({e->d_gfree, sizeof(uint32_t) * n * (size_t)e->gfree_words});

@@ -89,6 +89,10 @@ struct mdx_env {
   uint8_t* d_status = nullptr;
   uint16_t* d_cur = nullptr;
   uint32_t* d_counters = nullptr;
+  bool stale = false;              // MDX_CFG_STALE_TRACKER
+  uint16_t* d_trk = nullptr;       // [n][5][Pp8]
+  uint8_t* d_trk_status = nullptr; // [n][Pp16]
+  int32_t* d_trk_n = nullptr;      // [n]
   int32_t* d_env_map = nullptr;
   int32_t* d_ids = nullptr;     // [n] env ids of an mdx_reset call
   // packed-row entry points (mdx_get_states / mdx_set_states / mdx_step_host): one pinned host buffer and its device
@@ -120,6 +124,9 @@ int ensure_dynamic_smem(const void* func, size_t bytes, int carveout);
 int launch_env_kernel_1(mdx_env* e, const KParams& kp, cudaStream_t st);
 int launch_env_kernel_2(mdx_env* e, const KParams& kp, cudaStream_t st);
 int launch_env_kernel_3(mdx_env* e, const KParams& kp, cudaStream_t st);
+int launch_env_kernel_trk_1(mdx_env* e, const KParams& kp, cudaStream_t st);  // MDX_CFG_STALE_TRACKER instances
+int launch_env_kernel_trk_2(mdx_env* e, const KParams& kp, cudaStream_t st);
+int launch_env_kernel_trk_3(mdx_env* e, const KParams& kp, cudaStream_t st);
 int launch_env_kernel_5(mdx_env* e, const KParams& kp, cudaStream_t st);  // step + IDQ featurisers; MDX_E_UNSUPPORTED_SHAPE: use two launches
 constexpr int MDX_E_UNSUPPORTED_SHAPE = -100;  // internal: never crosses the C ABI
 // builds the all-pairs BFS tables and publishes them in the map descriptors (idempotent)

@@ -86,6 +86,8 @@ struct KParams {
   // smem carve-up (bytes from the warp's base)
   // step-only launches need [0, off_alist); the featuriser adds alist, sel, planes and the stage
   int32_t off_sched, off_status, off_wlist, off_wkey, off_rinfo, off_alist, off_sel, off_masks, off_stage;
+  int32_t off_trk;        // stale-tracker instances: tracker table (ids, start, target, start_time, deadline: u16 [5][Pp8]; status u8
+                          // [Pp16]; id -> slot map u16 [Pp8]) behind the stage
   int32_t smem_per_warp;
   int32_t sel_k;      // min(K_p, P): selection slots per robot
   int32_t stage_b;    // float offset of the gvec package segment inside the stage
@@ -104,6 +106,10 @@ struct KParams {
   uint16_t* cur;           // [n_envs][4][Pp8]      schedule of the env's CURRENT episode: start cell, target cell, start_time,
                            //                       deadline in package-id order; rewritten by the device sampler on every reset
   uint32_t* counters;      // [n_envs][8]
+  // MDX_CFG_STALE_TRACKER: the MAPPO trainer's package dict per env, in dict (insertion) order (MAPPO/trainer.py:91-130)
+  uint16_t* trk;           // [n_envs][5][Pp8]  package id (1-based), start cell, target cell, start_time, deadline
+  uint8_t* trk_status;     // [n_envs][Pp16]    ST_WAITING / ST_IN_TRANSIT
+  int32_t* trk_n;          // [n_envs]          entries in the dict
   const int32_t* env_map;  // [n_envs]
   const MapDev* maps;
   MapDev map0;             // copy of maps[0] (used directly when every env shares one map)

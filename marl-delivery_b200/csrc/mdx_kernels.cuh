@@ -88,7 +88,17 @@ struct Env {
   uint32_t* planes;                    // [10][W32] grid, robots, waiting starts, active targets, 2 x (self, others, own target)
   uint16_t *rcell, *rcarry, *rtgt, *rdl, *rrc;  // [32] per robot
   float* stage;                        // 16-byte aligned staging for vec / gvec rows
+  uint16_t *pid, *slot;                // tracker view only (kTrk): package id of every list slot; slot of every id (0xFFFF = absent)
 };
+
+constexpr uint32_t kNoSlot = 0xFFFFu;
+
+// The featurisers and the shaped reward read packages through an Env "view".  Default (env truth): slot j IS package id j + 1.
+// kTrk (MDX_CFG_STALE_TRACKER): the view is the trainer's dict in insertion order, ids are data.
+template <bool kTrk>
+__device__ __forceinline__ uint32_t slot_of(const Env& w, int id) { return kTrk ? (uint32_t)w.slot[id - 1] : (uint32_t)(id - 1); }
+template <bool kTrk>
+__device__ __forceinline__ int id_of(const Env& w, int slot) { return kTrk ? (int)w.pid[slot] : slot + 1; }
 
 __device__ __forceinline__ Env carve(const KParams& p, unsigned char* base) {
   Env w;
@@ -113,7 +123,23 @@ __device__ __forceinline__ Env carve(const KParams& p, unsigned char* base) {
   w.rdl = ri + 96;
   w.rrc = ri + 128;
   w.stage = reinterpret_cast<float*>(base + p.off_stage);
+  w.pid = nullptr;
+  w.slot = nullptr;
   return w;
+}
+
+// The tracker view of the same working set: package arrays point at the tracker table, lists / planes / stage are shared.
+__device__ __forceinline__ Env carve_tracker(const KParams& p, unsigned char* base, const Env& w) {
+  Env f = w;
+  uint16_t* s = reinterpret_cast<uint16_t*>(base + p.off_trk);
+  f.pid = s;
+  f.start = s + p.Pp8;
+  f.target = s + 2 * p.Pp8;
+  f.t0 = s + 3 * p.Pp8;
+  f.dl = s + 4 * p.Pp8;
+  f.status = base + p.off_trk + 10 * p.Pp8;
+  f.slot = reinterpret_cast<uint16_t*>(base + p.off_trk + 10 * p.Pp8 + p.Pp16);
+  return f;
 }
 
 // max(0, deadline - t) / T  and  t / T  (MAPPO/helper.py:107,155,163): table of correctly rounded
@@ -201,13 +227,13 @@ __device__ __forceinline__ void zero_stage(float* stage, int n_floats, int sl) {
 // Compact list of packages that are 'waiting' with start_time <= t, in id order: package index and
 // packed start position.  Returns the count.
 template <int LPE>
-__device__ __forceinline__ int build_waiting(const KParams& p, const Env& w, const Grp<LPE>& g, int t) {
+__device__ __forceinline__ int build_waiting(const KParams& p, const Env& w, const Grp<LPE>& g, int t, int Pn) {
   int nw = 0;
   const unsigned lt = (1u << g.sl) - 1u;
 #pragma unroll 1
-  for (int base = 0; base < p.P; base += LPE) {
+  for (int base = 0; base < Pn; base += LPE) {
     const int j = base + g.sl;
-    const bool wait = j < p.P && w.status[j] == ST_WAITING && (int)w.t0[j] <= t;
+    const bool wait = j < Pn && w.status[j] == ST_WAITING && (int)w.t0[j] <= t;
     const unsigned m = g.ballot(wait);
     if (wait) {
       const int k = nw + __popc(m & lt);
@@ -286,20 +312,22 @@ __device__ __forceinline__ Scan scan_waiting(const Env& w, const Grp<LPE>& g, in
 
 // Shaped team reward of one transition (MAPPO/helper.py:257-369).  Per lane (robot): old / new
 // position and carried id, decoded action, the scan above; w.status still holds the PREVIOUS statuses.
-template <int LPE, bool kBfs>
+template <int LPE, bool kBfs, bool kTrk = false>
 __device__ __forceinline__ float shaped_team_reward(const KParams& p, const Env& w, const Grp<LPE>& g, int t_cur, int r0,
                                                     int c0, int k0, int r1, int c1, int k1, int mv, int op, int nw,
                                                     const Scan& sc, double env_reward, const uint16_t* bfs) {
   float acc = 0.0f;
   if (g.sl < p.R) {
-    const uint8_t st0 = k0 ? w.status[k0 - 1] : (uint8_t)ST_NONE;
-    const bool tracked = k0 != 0 && (st0 == ST_WAITING || st0 == ST_IN_TRANSIT);
+    // "prev_pkg in persistent_packages_at_prev_state": env truth -> the package is waiting or in transit; tracker view -> the id has a slot
+    const uint32_t s0 = k0 ? slot_of<kTrk>(w, k0) : kNoSlot;
+    const uint8_t st0 = s0 != kNoSlot ? w.status[s0] : (uint8_t)ST_NONE;
+    const bool tracked = s0 != kNoSlot && (st0 == ST_WAITING || st0 == ST_IN_TRANSIT);
     int gr = -1, gc = 0, dl0 = 0;
-    if (k0) {
-      const uint32_t tg = w.target[k0 - 1];
+    if (s0 != kNoSlot) {
+      const uint32_t tg = w.target[s0];
       gr = (int)__umulhi(tg, p.mul_wout);
       gc = (int)tg - gr * p.W_out;
-      dl0 = w.dl[k0 - 1];
+      dl0 = w.dl[s0];
     }
     const bool at_target = k0 != 0 && r1 == gr && c1 == gc;
     // 1. successful pickup / delivery (:295-305)
@@ -408,12 +436,13 @@ __device__ __forceinline__ void decode_action(int a, int& mv, int& op) {
 //          = 0: generic flat loops over per-robot bit planes (any H*W).
 //   kSmall:     P <= 64, so a lane owns at most 64/LPE waiting-list entries and keeps their selection
 //               keys in registers.
-template <int LPE, int kS, bool kSmall, int kFix>
+//   kTrk:       `w` is the tracker view (dict order, Pn entries, ids are data); otherwise the env truth (Pn = P, slot j = id j + 1).
+template <int LPE, int kS, bool kSmall, int kFix, bool kTrk = false>
 __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, const Grp<LPE>& g, const float4* lut,
-                                              const MapDev& map, int row, int t, int cell, int carry) {
+                                              const MapDev& map, int row, int t, int cell, int carry, int Pn) {
   constexpr int EPL = 64 / LPE;
   const int sl = g.sl;
-  const int R = p.R, P = p.P, W32 = p.W32, HW = p.HW, Wo = p.W_out;
+  const int R = p.R, P = Pn, W32 = p.W32, HW = p.HW, Wo = p.W_out;
   const int Hm1 = p.H_out - 1, Wm1 = p.W_out - 1, NC = 2 * p.W_out - 1;
   const unsigned lt = (1u << sl) - 1u;
   const bool active = sl < R;
@@ -426,10 +455,11 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
   bool carrying_it = false;
   int own_tgt = 0xFFFF, own_rem = 0, tr_own = 0, tc_own = 0;
   if (active) {
-    if (carry != 0 && w.status[carry - 1] == ST_IN_TRANSIT) {
+    const uint32_t sc_ = carry != 0 ? slot_of<kTrk>(w, carry) : kNoSlot;
+    if (sc_ != kNoSlot && w.status[sc_] == ST_IN_TRANSIT) {
       carrying_it = true;
-      own_tgt = w.target[carry - 1];
-      own_rem = max(0, (int)w.dl[carry - 1] - t);
+      own_tgt = w.target[sc_];
+      own_rem = max(0, (int)w.dl[sc_] - t);
       tr_own = (int)__umulhi((uint32_t)own_tgt, p.mul_wout);
       tc_own = own_tgt - tr_own * Wo;
     }
@@ -472,12 +502,29 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
       w.wrc[k] = (uint16_t)((sr << 8) | (sc - sr * Wo));
       w.wdl[k] = (uint16_t)max(0, (int)w.dl[j] - t);
     }
-    if (act) {
+    if (!kTrk && act) {
       const int k = na + __popc(am & lt);
       if (k < p.MP) w.alist[k] = (uint16_t)j;
     }
     nw += __popc(wm);
     na += __popc(am);
+  }
+  if (kTrk) {
+    // convert_global_state lists the active packages sorted by ID (MAPPO/helper.py:229), not in dict order: walk the ids
+    g.sync();
+    na = 0;
+#pragma unroll 1
+    for (int base = 0; base < p.P; base += LPE) {
+      const int id0 = base + sl;
+      const uint32_t s_ = id0 < p.P ? (uint32_t)w.slot[id0] : kNoSlot;
+      const bool act = s_ != kNoSlot && ((w.status[s_] == ST_WAITING && (int)w.t0[s_] <= t) || w.status[s_] == ST_IN_TRANSIT);
+      const unsigned am = g.ballot(act);
+      if (act) {
+        const int k = na + __popc(am & lt);
+        if (k < p.MP) w.alist[k] = (uint16_t)s_;
+      }
+      na += __popc(am);
+    }
   }
   g.sync();
 
@@ -999,7 +1046,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
       float cn = -1.0f;
       if (!wait) {
         for (int ridx = 0; ridx < R; ++ridx)
-          if ((int)w.rcarry[ridx] == j + 1) {
+          if ((int)w.rcarry[ridx] == id_of<kTrk>(w, j)) {
             cn = __ldg(p.cq + ridx);  // ridx / (MR - 1), or 0 when MR <= 1
             break;
           }
@@ -1136,6 +1183,68 @@ __device__ __forceinline__ void featurize_alt_env(const KParams& p, const Env& w
 // kFix: shape specialisation.  0 = every shape parameter is read from KParams at run time; 1 = the
 // headline MAPPO shape (C3: map1 10x10, 5 robots, <= 56 packages, K_o = 4, K_p = 5, MR = MP = 100) is baked
 // in as compile-time constants, so loops over robots / planes / rows unroll and the index arithmetic folds.
+// MAPPO/trainer.py:95-130 `_update_persistent_packages_for_env(env_idx, state)` on the tracker table in shared memory; `state` is
+// the env's current one: time t_now, robot i carries `carry` (lane i), packages of the env truth `w`.  Returns the new dict size.
+//   1. every package the state lists as newly spawned (start_time == t_now, env.py:134-137) joins the END of the dict unless its
+//      id is already a key -- a stale entry of an earlier episode shadows it;
+//   2. ids some robot carries become 'in_transit'; 'in_transit' ids nobody carries any more are deleted (the others keep their order).
+template <int LPE>
+__device__ __forceinline__ int tracker_update(const KParams& p, const Env& w, const Env& f, const Grp<LPE>& g, int t_now, int carry, int n) {
+  const unsigned lt = (1u << g.sl) - 1u;
+#pragma unroll 1
+  for (int base = 0; base < p.P; base += LPE) {
+    const int j = base + g.sl;
+    const bool add = j < p.P && (int)w.t0[j] == t_now && f.slot[j] == kNoSlot;
+    const unsigned m = g.ballot(add);
+    if (add) {
+      const int k = n + __popc(m & lt);
+      f.pid[k] = (uint16_t)(j + 1);
+      f.start[k] = w.start[j];
+      f.target[k] = w.target[j];
+      f.t0[k] = w.t0[j];
+      f.dl[k] = w.dl[j];
+      f.status[k] = ST_WAITING;
+      f.slot[j] = (uint16_t)k;
+    }
+    n += __popc(m);
+  }
+  g.sync();
+  int out = 0;
+#pragma unroll 1
+  for (int base = 0; base < n; base += LPE) {
+    const int k = base + g.sl;
+    const bool valid = k < n;
+    uint32_t id = 0u, a = 0u, b = 0u, c = 0u, d = 0u;
+    uint8_t st = ST_NONE;
+    if (valid) {
+      id = f.pid[k], a = f.start[k], b = f.target[k], c = f.t0[k], d = f.dl[k];
+      st = f.status[k];
+    }
+    bool carried = false;
+#pragma unroll 1
+    for (int i = 0; i < p.R; ++i) {
+      const uint32_t cid = (uint32_t)g.shfl(carry, i);  // (every lane of the group executes every shuffle: no short-circuit)
+      carried = carried | (cid == id);                  // id 0 (invalid lane) matches "carries nothing": masked below
+    }
+    carried = carried && valid;
+    if (carried) st = ST_IN_TRANSIT;
+    const bool keep = valid && (carried || st != ST_IN_TRANSIT);
+    const unsigned m = g.ballot(keep);
+    g.sync();  // every lane holds its entry in registers: the slots below `base` may be overwritten
+    if (keep) {
+      const int q = out + __popc(m & lt);
+      f.pid[q] = (uint16_t)id, f.start[q] = (uint16_t)a, f.target[q] = (uint16_t)b, f.t0[q] = (uint16_t)c, f.dl[q] = (uint16_t)d;
+      f.status[q] = st;
+      f.slot[id - 1] = (uint16_t)q;
+    } else if (valid) {
+      f.slot[id - 1] = (uint16_t)kNoSlot;
+    }
+    out += __popc(m);
+    g.sync();
+  }
+  return out;
+}
+
 template <int kFix>
 __device__ __forceinline__ void specialise(KParams& p) {
   if (kFix == 1) {
@@ -1175,7 +1284,10 @@ __device__ __forceinline__ void specialise(KParams& p) {
   }
 }
 
-template <int kMode, int LPE, int kS, bool kSmall, int kFix>
+// kTrk: MDX_CFG_STALE_TRACKER instances -- shaped reward and featurisers read the trainer's own (never cleared) package dict, which
+// the kernel also maintains; flags bit 2 (internal): apply the tracker update for the CURRENT state first (after mdx_reset);
+// flags bit 3 (internal): empty the dict first (mdx_tracker_clear).
+template <int kMode, int LPE, int kS, bool kSmall, int kFix, bool kTrk = false>
 __global__ void __launch_bounds__((kFix == 1 && (kMode & 2)) ? MDX_FIX_THREADS : 128,
                                    (kMode & 2) ? (kFix == 1 ? MDX_FIX_BLOCKS : kFix == 2 ? MDX_FAT_BLOCKS : MDX_FEAT_BLOCKS)
                                                : ((kMode & 4) && kS > 2) ? 6 : 8) mdx_env_kernel(const __grid_constant__ KParams pg) {
@@ -1246,7 +1358,34 @@ __global__ void __launch_bounds__((kFix == 1 && (kMode & 2)) ? MDX_FIX_THREADS :
   }
   int cell = active ? (int)(rob & 0xffffu) : (0x10000 + sl);
   int carry = active ? (int)(rob >> 16) : 0;
+  Env wf = w;  // what the shaped reward and the featurisers read
+  int ntrk = 0;
+  if constexpr (kTrk) {
+    unsigned char* base = smem_raw + kLutBytes + (size_t)gib * p.smem_per_warp;
+    wf = carve_tracker(p, base, w);
+    ntrk = (p.flags & 8u) ? 0 : p.trk_n[env];
+    const uint4* src = reinterpret_cast<const uint4*>(p.trk + (size_t)env * 5 * p.Pp8);
+    uint4* dst = reinterpret_cast<uint4*>(wf.pid);
+#pragma unroll 1
+    for (int i = sl; i < (5 * p.Pp8) >> 3; i += LPE) dst[i] = src[i];
+    const uint4* ssrc = reinterpret_cast<const uint4*>(p.trk_status + (size_t)env * p.Pp16);
+    uint4* sdst = reinterpret_cast<uint4*>(wf.status);
+#pragma unroll 1
+    for (int i = sl; i < (p.Pp16 >> 4); i += LPE) sdst[i] = ssrc[i];
+#pragma unroll 1
+    for (int j = sl; j < p.Pp8; j += LPE) wf.slot[j] = (uint16_t)kNoSlot;
+    g.sync();
+#pragma unroll 1
+    for (int k = sl; k < ntrk; k += LPE) wf.slot[wf.pid[k] - 1] = (uint16_t)k;
+  }
   g.sync();
+  [[maybe_unused]] bool trk_dirty = false;
+  if constexpr (kTrk) {
+    if (p.flags & 12u) {
+      if (p.flags & 4u) ntrk = tracker_update<LPE>(p, w, wf, g, t, carry, ntrk);
+      trk_dirty = true;
+    }
+  }
 
   if (kMode & 1) {
     // ---------------- decode ----------------
@@ -1290,7 +1429,7 @@ __global__ void __launch_bounds__((kFix == 1 && (kMode & 2)) ? MDX_FIX_THREADS :
     // ---------------- package ops in robot order (env.py:260-292) ----------------
     // robots stand on distinct cells, so pickups never contend across robots: each takes the
     // lowest-id waiting package on its own cell
-    const int nw_prev = build_waiting<LPE>(p, w, g, t);
+    const int nw_prev = build_waiting<LPE>(p, w, g, t, P);
     const bool bfs_mode = kFix != 1 && p.shaping_bfs != 0;
     const Scan sc = bfs_mode ? scan_waiting<LPE, kSmall, true>(w, g, R, nw_prev, r, c, r1, c1, map.bfs, p.HW, Wo)
                              : scan_waiting<LPE, kSmall, false>(w, g, R, nw_prev, r, c, r1, c1, nullptr, 0, 0);
@@ -1312,9 +1451,20 @@ __global__ void __launch_bounds__((kFix == 1 && (kMode & 2)) ? MDX_FIX_THREADS :
     }
     // shaped reward reads the PREVIOUS statuses, so evaluate it before they change
     float shaped = 0.0f;
+    if constexpr (kTrk) {
+      // persistent_packages_at_prev_state is the trainer's dict, not the env truth: second waiting list + scan on the tracker view
+      // (`picked` above already consumed the truth list)
+      if (p.out_shaped != nullptr) {
+        g.sync();
+        const int nw_t = build_waiting<LPE>(p, wf, g, t, ntrk);
+        const Scan sct = scan_waiting<LPE, kSmall, false>(wf, g, R, nw_t, r, c, r1, c1, nullptr, 0, 0);
+        shaped = shaped_team_reward<LPE, false, true>(p, wf, g, t + 1, r, c, carry, r1, c1, carry1, mv, op, nw_t, sct, rew, nullptr);
+      }
+    } else {
     if (p.out_shaped != nullptr)
       shaped = bfs_mode ? shaped_team_reward<LPE, true>(p, w, g, t + 1, r, c, carry, r1, c1, carry1, mv, op, nw_prev, sc, rew, map.bfs)
                         : shaped_team_reward<LPE, false>(p, w, g, t + 1, r, c, carry, r1, c1, carry1, mv, op, nw_prev, sc, rew, nullptr);
+    }
     if (p.out_agent != nullptr && active)
       p.out_agent[(size_t)widx * R + sl] = idq_agent_reward(w, nw_prev, moved, op, r, c, carry, carry1, cell1 == tgt0, t + 1, dl0, p.idq_ops_int);
     g.sync();
@@ -1373,6 +1523,15 @@ __global__ void __launch_bounds__((kFix == 1 && (kMode & 2)) ? MDX_FIX_THREADS :
       total = 0.0;
       g.sync();
     }
+    // ---------------- the trainer's tracker (MAPPO/trainer.py:229-280) ----------------
+    // a done env is reset first and the dict sees only the RESET state (it is never cleared); a done env that is
+    // not auto-reset waits for the caller's mdx_reset, which applies the update; otherwise the dict sees the next state
+    if constexpr (kTrk) {
+      if (!done || (p.flags & 1u)) {
+        ntrk = tracker_update<LPE>(p, w, wf, g, t, carry, ntrk);
+        trk_dirty = true;
+      }
+    }
     // ---------------- write the state back ----------------
     if (active) p.robots[(size_t)env * R + sl] = (uint32_t)cell | ((uint32_t)carry << 16);
     {
@@ -1388,7 +1547,21 @@ __global__ void __launch_bounds__((kFix == 1 && (kMode & 2)) ? MDX_FIX_THREADS :
     }
   }
 
-  if (kMode & 2) featurize_env<LPE, kS, kSmall, kFix>(p, w, g, lut, map, widx, t, cell, carry);
+  if constexpr (kTrk) {
+    if (trk_dirty) {
+      g.sync();
+      uint4* dst = reinterpret_cast<uint4*>(p.trk + (size_t)env * 5 * p.Pp8);
+      const uint4* src = reinterpret_cast<const uint4*>(wf.pid);
+#pragma unroll 1
+      for (int i = sl; i < (5 * p.Pp8) >> 3; i += LPE) dst[i] = src[i];
+      uint4* sdst = reinterpret_cast<uint4*>(p.trk_status + (size_t)env * p.Pp16);
+      const uint4* ssrc = reinterpret_cast<const uint4*>(wf.status);
+#pragma unroll 1
+      for (int i = sl; i < (p.Pp16 >> 4); i += LPE) sdst[i] = ssrc[i];
+      if (sl == 0) p.trk_n[env] = ntrk;
+    }
+  }
+  if (kMode & 2) featurize_env<LPE, kS, kSmall, kFix, kTrk>(p, kTrk ? wf : w, g, lut, map, widx, t, cell, carry, kTrk ? ntrk : P);
   if constexpr ((kMode & 4) != 0 && LPE == 32 && kS > 0) featurize_alt_env<kS>(p, w, g, lut, map, widx, t, cell, carry);
 }
 

@@ -8,8 +8,13 @@
 namespace mdx {
 namespace {
 
+#ifndef MDX_TRK
+#define MDX_TRK 0
+#endif
+constexpr bool kTrkTU = MDX_TRK != 0;  // this translation unit holds the stale-tracker variants (whole warps, run-time shapes)
+
 int smem_for_mode(const mdx_env* e, int mode) {
-  return (mode & 6) ? e->base.smem_per_warp : e->base.off_alist;
+  return ((mode & 6) || kTrkTU) ? e->base.smem_per_warp : e->base.off_alist;
 }
 
 template <int kMode, int LPE, int kS, bool kSmall, int kFix>
@@ -23,7 +28,7 @@ int launch_variant(mdx_env* e, const KParams& kp, cudaStream_t st) {
   // the high-water mark lives in a static of this instantiation (one per function), indexed by device.
   static std::atomic<size_t> high_water[64];
   if (smem > high_water[e->device & 63].load(std::memory_order_acquire)) {
-    int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(mdx_env_kernel<kMode, LPE, kS, kSmall, kFix>), smem, e->carveout);
+    int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(mdx_env_kernel<kMode, LPE, kS, kSmall, kFix, kTrkTU>), smem, e->carveout);
     if (rc != MDX_OK) return rc;
     size_t prev = high_water[e->device & 63].load(std::memory_order_relaxed);
     while (prev < smem && !high_water[e->device & 63].compare_exchange_weak(prev, smem)) {
@@ -32,7 +37,7 @@ int launch_variant(mdx_env* e, const KParams& kp, cudaStream_t st) {
   KParams q = kp;
   q.smem_per_warp = spe;
   const unsigned grid = (unsigned)((kp.n + epb - 1) / epb);
-  mdx_env_kernel<kMode, LPE, kS, kSmall, kFix><<<grid, threads, smem, st>>>(q);
+  mdx_env_kernel<kMode, LPE, kS, kSmall, kFix, kTrkTU><<<grid, threads, smem, st>>>(q);
   CU(cudaGetLastError());
   return MDX_OK;
 }
@@ -58,8 +63,10 @@ int launch_lpe(mdx_env* e, const KParams& kp, cudaStream_t st, int ks) {
     case 4:
       if (small) return launch_variant<kMode, LPE, 4, true, 0>(e, kp, st);
       // four-slice planes with a long package list (C4, C5): the build with the looser register cap (MDX_NOFAT=1: the capped one)
-      if (LPE == 32 && kMode != 5 && !e->no_fat)
-        return launch_variant<kMode, (LPE == 32 ? 32 : LPE), 4, false, (LPE == 32 ? 2 : 0)>(e, kp, st);
+      if constexpr (!kTrkTU) {
+        if (LPE == 32 && kMode != 5 && !e->no_fat)
+          return launch_variant<kMode, (LPE == 32 ? 32 : LPE), 4, false, (LPE == 32 ? 2 : 0)>(e, kp, st);
+      }
       return launch_variant<kMode, LPE, 4, false, 0>(e, kp, st);
     default: return small ? launch_variant<kMode, LPE, 0, true, 0>(e, kp, st) : launch_variant<kMode, LPE, 0, false, 0>(e, kp, st);
   }
@@ -83,6 +90,9 @@ int launch_env_kernel(mdx_env* e, const KParams& kp, cudaStream_t st) {
   if constexpr (kMode == 5) {
     return launch_lpe<kMode, 32>(e, kp, st, slices(32));
   } else {
+  if constexpr (kTrkTU) {
+    return launch_lpe<kMode, 32>(e, kp, st, kMode == 1 ? 0 : slices(32));
+  } else {
   int lpe = 32;
   // Step-only launches have no store phase: they are bound by instruction issue once the batch fills the GPU a few times over, and
   // packing four environments into a warp amortises the warp-uniform work (65 536 envs: 78 -> 60 us per step); small batches are
@@ -103,12 +113,17 @@ int launch_env_kernel(mdx_env* e, const KParams& kp, cudaStream_t st) {
   if (lpe == 16) return launch_lpe<kMode, 16>(e, kp, st, ks);
   return launch_lpe<kMode, 32>(e, kp, st, ks);
   }
+  }
 }
 
 }  // namespace
 
 #define MDX_CAT2(a, b) a##b
 #define MDX_CAT(a, b) MDX_CAT2(a, b)
+#if MDX_TRK
+int MDX_CAT(launch_env_kernel_trk_, MDX_MODE)(mdx_env* e, const KParams& kp, cudaStream_t st) { return launch_env_kernel<MDX_MODE>(e, kp, st); }
+#else
 int MDX_CAT(launch_env_kernel_, MDX_MODE)(mdx_env* e, const KParams& kp, cudaStream_t st) { return launch_env_kernel<MDX_MODE>(e, kp, st); }
+#endif
 
 }  // namespace mdx

@@ -1,0 +1,4 @@
+// stale-tracker variants (MDX_CFG_STALE_TRACKER) of kernel mode 3
+#define MDX_MODE 3
+#define MDX_TRK 1
+#include "mdx_launch.inl"

@@ -6,6 +6,8 @@
 namespace mdx {
 
 // compute_shaped_rewards on injected "current" robots against the stored state as "previous".
+// kTrk: persistent_packages_at_prev_state is the env's tracker table (MDX_CFG_STALE_TRACKER), not the env truth.
+template <bool kTrk>
 __global__ void __launch_bounds__(128) mdx_shape_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int wib = threadIdx.x >> 5;
@@ -13,12 +15,26 @@ __global__ void __launch_bounds__(128) mdx_shape_kernel(const __grid_constant__ 
   if (env >= p.n) return;
   const Grp<32> g(threadIdx.x & 31);
   const int lane = g.sl;
-  const Env w = carve(p, smem_raw + kLutBytes + (size_t)wib * p.smem_per_warp);
+  unsigned char* base = smem_raw + kLutBytes + (size_t)wib * p.smem_per_warp;
+  Env w = carve(p, base);
   const int R = p.R;
   const bool active = lane < R;
   const int t = p.t[env];
-  load_episode<32>(p, w, env, lane);
-  {
+  int Pn = p.P;
+  if constexpr (kTrk) {
+    w = carve_tracker(p, base, w);
+    Pn = p.trk_n[env];
+    const uint4* src = reinterpret_cast<const uint4*>(p.trk + (size_t)env * 5 * p.Pp8);
+    uint4* dst = reinterpret_cast<uint4*>(w.pid);
+    for (int i = lane; i < (5 * p.Pp8) >> 3; i += 32) dst[i] = src[i];
+    const uint4* ssrc = reinterpret_cast<const uint4*>(p.trk_status + (size_t)env * p.Pp16);
+    uint4* sdst = reinterpret_cast<uint4*>(w.status);
+    for (int i = lane; i < (p.Pp16 >> 4); i += 32) sdst[i] = ssrc[i];
+    for (int j = lane; j < p.Pp8; j += 32) w.slot[j] = (uint16_t)kNoSlot;
+    g.sync();
+    for (int k = lane; k < Pn; k += 32) w.slot[w.pid[k] - 1] = (uint16_t)k;
+  } else {
+    load_episode<32>(p, w, env, lane);
     const uint4* src = reinterpret_cast<const uint4*>(p.status + (size_t)env * p.Pp16);
     uint4* dst = reinterpret_cast<uint4*>(w.status);
 #pragma unroll 1
@@ -31,9 +47,9 @@ __global__ void __launch_bounds__(128) mdx_shape_kernel(const __grid_constant__ 
   decode_action(active ? (int)p.actions[(size_t)env * R + lane] : 3, mv, op);
   const int r0 = (int)__umulhi(rob0 & 0xffffu, p.mul_wout), c0 = (int)(rob0 & 0xffffu) - r0 * p.W_out;
   const int r1 = (int)__umulhi(rob1 & 0xffffu, p.mul_wout), c1 = (int)(rob1 & 0xffffu) - r1 * p.W_out;
-  const int nw = build_waiting<32>(p, w, g, t);
+  const int nw = build_waiting<32>(p, w, g, t, Pn);
   const MapDev map = p.env_map ? p.maps[p.env_map[env]] : p.map0;
-  if (p.out_agent != nullptr && active) {  // IDQ reward_shaping on the injected transition
+  if (!kTrk && p.out_agent != nullptr && active) {  // IDQ reward_shaping on the injected transition
     const int k0 = (int)(rob0 >> 16);
     const int tg = k0 ? (int)w.target[k0 - 1] : -1;
     p.out_agent[(size_t)env * R + lane] = idq_agent_reward(w, nw, (rob0 & 0xffffu) != (rob1 & 0xffffu), op, r0, c0, k0, (int)(rob1 >> 16),
@@ -41,14 +57,14 @@ __global__ void __launch_bounds__(128) mdx_shape_kernel(const __grid_constant__ 
   }
   if (p.out_shaped == nullptr) return;
   float s;
-  if (p.shaping_bfs) {
+  if (!kTrk && p.shaping_bfs) {
     const Scan sc = scan_waiting<32, false, true>(w, g, R, nw, r0, c0, r1, c1, map.bfs, p.HW, p.W_out);
     s = shaped_team_reward<32, true>(p, w, g, p.cur_t[env], r0, c0, (int)(rob0 >> 16), r1, c1, (int)(rob1 >> 16), mv, op, nw, sc,
                                      p.global_reward[env], map.bfs);
   } else {
     const Scan sc = scan_waiting<32, false, false>(w, g, R, nw, r0, c0, r1, c1, nullptr, 0, 0);
-    s = shaped_team_reward<32, false>(p, w, g, p.cur_t[env], r0, c0, (int)(rob0 >> 16), r1, c1, (int)(rob1 >> 16), mv, op, nw, sc,
-                                      p.global_reward[env], nullptr);
+    s = shaped_team_reward<32, false, kTrk>(p, w, g, p.cur_t[env], r0, c0, (int)(rob0 >> 16), r1, c1, (int)(rob1 >> 16), mv, op, nw, sc,
+                                            p.global_reward[env], nullptr);
   }
   if (lane == 0) p.out_shaped[env] = s;
 }

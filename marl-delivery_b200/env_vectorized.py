@@ -18,14 +18,17 @@ _ENV_KW = ("map_file", "max_time_steps", "n_robots", "n_packages", "move_cost", 
 class VectorizedEnv:
     def __init__(self, env_cls, num_envs, k_others=100, k_packages=100, max_robots_in_state=100,
                  max_packages_in_state=100, shaping=MAPPO_SHAPING, device=None, ring_episodes=None, first_env_index=0,
-                 bfs_shaping=False,
+                 bfs_shaping=False, stale_tracker_compat=False,
                  **env_kwargs):
         """`env_cls` is accepted for signature compatibility (the reference passes its Environment
         class); the environments are always slots of one CUDA batch.  Seeds follow
         MAPPO/env_vectorized.py:4-10: env idx uses seed + idx (all envs share the default seed 2025 when
         no seed is given, exactly like the reference).  `map_file` may be a list, then env idx uses
         map_files[idx % len] (4-map notebook).  `first_env_index` offsets idx for multi-GPU sharding so
-        that results do not depend on the number of ranks."""
+        that results do not depend on the number of ranks.  `stale_tracker_compat=True` reproduces what MAPPO/trainer.py
+        really feeds the converters and compute_shaped_rewards: its per-env package dict is never cleared on auto-reset
+        (MAPPO/trainer.py:229-234), so stale entries shadow new packages; the default is the env truth (= a
+        tracker cleared on reset, what the QMIX / IDQ trainers keep).  Call reset() before the first step, like the trainer."""
         unknown = set(env_kwargs) - set(_ENV_KW)
         if unknown:
             raise TypeError(f"unexpected Environment arguments: {sorted(unknown)}")
@@ -44,7 +47,7 @@ class VectorizedEnv:
             env_map=(gidx % len(grids)).astype(np.int32) if len(grids) > 1 else None, k_others=k_others,
             k_packages=k_packages, max_robots_in_state=max_robots_in_state,
             max_packages_in_state=max_packages_in_state, shaping=shaping, device=device,
-            bfs_shaping=bfs_shaping)
+            bfs_shaping=bfs_shaping, stale_tracker=stale_tracker_compat)
         self.num_envs = num_envs
         self.envs = _EnvList(self.batch, [files[int(g) % len(files)] for g in gidx] if len(files) > 1 else files * 1)
 

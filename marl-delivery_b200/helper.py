@@ -7,13 +7,13 @@ given (state dict, tracker dict) into a cached 1-env scratch batch and runs the 
 (one small H2D + D2H per call).  Rollouts should use `VectorizedEnv.rollout_step` /
 `DeliveryBatch.featurize`, which produce the same tensors for all envs in one launch.
 
-Assumption (holds for every tracker the reference trainers build): the tracker
-dict is keyed by package id with ascending insertion order, and statuses are 'waiting'/'in_transit'.
+The tracker dict may be any dict the reference trainers build: keyed by ascending package id (a tracker that is
+cleared on reset) it is injected as env truth; in any other insertion order (the MAPPO trainer's never-cleared dict,
+SURVEY.md Q7) it is injected, in dict order, into the scratch batch's tracker table (MDX_CFG_STALE_TRACKER).
 """
 from __future__ import annotations
 
 import numpy as np
-import torch
 
 from .batch import MAPPO_SHAPING, QMIX_SHAPING, DeliveryBatch, encode_action  # noqa: F401
 
@@ -21,14 +21,14 @@ _SCRATCH = {}
 _STATUS_CODE = {"None": 0, "waiting": 1, "in_transit": 2, "delivered": 3}
 
 
-def _scratch(grid, R, P, T, K_o, K_p, MR, MP, shaping):
-    key = (grid.tobytes(), grid.shape, R, P, T, K_o, K_p, MR, MP, tuple(shaping))
+def _scratch(grid, R, P, T, K_o, K_p, MR, MP, shaping, stale=False):
+    key = (grid.tobytes(), grid.shape, R, P, T, K_o, K_p, MR, MP, tuple(shaping), stale)
     b = _SCRATCH.get(key)
     if b is None:
         if len(_SCRATCH) > 16:
             _SCRATCH.pop(next(iter(_SCRATCH))).close()
         b = DeliveryBatch([grid], 1, R, P, T, k_others=K_o, k_packages=K_p, max_robots_in_state=MR,
-                          max_packages_in_state=MP, shaping=shaping, base_seed=0, blank=True, lax_robots=True)
+                          max_packages_in_state=MP, shaping=shaping, base_seed=0, blank=True, lax_robots=True, stale_tracker=stale)
         _SCRATCH[key] = b
     return b
 
@@ -40,28 +40,41 @@ def _pad_packages(n):
     return p
 
 
+def _ascending(tracker):
+    prev = 0
+    for pid in tracker:
+        if int(pid) <= prev:
+            return False
+        prev = int(pid)
+    return True
+
+
 def _inject(b: DeliveryBatch, state, tracker):
-    """(state dict, tracker dict) -> env 0 of the scratch batch as ONE packed row (one host -> device transfer)."""
+    """(state dict, tracker dict) -> env 0 of the scratch batch as ONE packed row (one host -> device transfer).  A dict keyed
+    by ascending package id (every tracker that is cleared on reset) goes in as the env truth; any other dict -- the MAPPO
+    trainer's never-cleared one iterates in insertion order -- goes into the scratch batch's tracker table in dict order."""
     W, P = b.cols_out, b.n_packages
     row = np.zeros(1, dtype=b._row_dtype)
     row["t"] = int(state["time_step"])
     row["robots"][0] = [((int(r) - 1) * W + int(c) - 1) | (int(k) << 16) for (r, c, k) in state["robots"]]
     sched, status = row["sched"][0], row["status"][0]
     sched[2, P:] = 0xffff
-    prev = 0
+    entries = []
     for pid, p in tracker.items():
         pid = int(pid)
-        if pid <= prev:
-            raise ValueError("tracker dict must be keyed by ascending package id")
-        prev = pid
-        j = pid - 1
         (sr, sc), (tr, tc) = p["start_pos"], p["target_pos"]
         if min(sr, sc, tr, tc) < 0 or max(sr, tr) >= b.rows_out or max(sc, tc) >= W:
             raise ValueError(f"package {pid} outside the map")
-        sched[0, j], sched[1, j], sched[2, j], sched[3, j] = sr * W + sc, tr * W + tc, int(p["start_time"]), int(p["deadline"])
-        status[j] = _STATUS_CODE[p["status"]]
+        if b.stale_tracker:
+            entries.append((pid, sr * W + sc, tr * W + tc, int(p["start_time"]), int(p["deadline"]), _STATUS_CODE[p["status"]]))
+        else:
+            j = pid - 1
+            sched[0, j], sched[1, j], sched[2, j], sched[3, j] = sr * W + sc, tr * W + tc, int(p["start_time"]), int(p["deadline"])
+            status[j] = _STATUS_CODE[p["status"]]
     # a carried id the tracker does not know stays 'None' -> "not in dict" branch of the reference
     b.set_rows([0], row)
+    if b.stale_tracker:
+        b.set_tracker(0, entries)
 
 
 def _prepare(state, tracker, T, K_o, K_p, MR, MP, shaping=MAPPO_SHAPING, min_pkg=0):
@@ -69,7 +82,7 @@ def _prepare(state, tracker, T, K_o, K_p, MR, MP, shaping=MAPPO_SHAPING, min_pkg
     R = len(state["robots"])
     ids = [int(k) for k in tracker] + [int(r[2]) for r in state["robots"]] + [min_pkg]
     P = _pad_packages(max(ids + [1]))
-    b = _scratch(grid, R, P, max(int(T), 0), K_o, K_p, MR, MP, shaping)
+    b = _scratch(grid, R, P, max(int(T), 0), K_o, K_p, MR, MP, shaping, stale=not _ascending(tracker))
     _inject(b, state, tracker)
     return b, grid.shape
 
@@ -121,8 +134,8 @@ def compute_shaped_rewards(global_reward, prev_env_state_dict, current_env_state
         prev["map"] = np.zeros((max(span[0], 2), W), np.uint8)
     b, (H, W) = _prepare(prev, persistent_packages_at_prev_state, 1, 0, 0, 1, 1, shaping=shaping,
                          min_pkg=max(int(r[2]) for r in cur_robots))
-    cur = torch.tensor([[[(int(r) - 1) * W + (int(c) - 1), int(k)] for (r, c, k) in cur_robots]], dtype=torch.int64)
-    acts = torch.tensor([[encode_action(m, p) for (m, p) in actions_taken_for_all_agents[:num_agents]]], dtype=torch.uint8)
-    out = b.shaped_reward(cur, torch.tensor([int(current_env_state_dict["time_step"])]), acts,
-                          torch.tensor([float(global_reward)], dtype=torch.float64))
-    return np.float32(out.cpu().numpy()[0])
+    cur = np.array([[((int(r) - 1) * W + (int(c) - 1)) | (int(k) << 16) for (r, c, k) in cur_robots]], dtype=np.uint32)
+    acts = np.array([[encode_action(m, p) for (m, p) in actions_taken_for_all_agents[:num_agents]]], dtype=np.uint8)
+    out = b.shaped_reward_host(cur, np.array([int(current_env_state_dict["time_step"])], np.int32), acts,
+                               np.array([float(global_reward)], np.float64))
+    return np.float32(out[0])
