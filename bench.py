@@ -329,7 +329,7 @@ class Leg:
         return ev[0].elapsed_time(ev[K]), [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
 
 
-def _secondary(mdb, torch, dev, rank, peak, name, K=40, W=5):
+def _secondary(mdb, torch, dev, rank, peak, name, K=40, W=5, split=1):
     """A short leg of another BASELINE.json config in the same process (its own batch, freed afterwards)."""
     wl = WORKLOADS[name]
     N = wl["envs"]
@@ -342,11 +342,30 @@ def _secondary(mdb, torch, dev, rank, peak, name, K=40, W=5):
     ms, per = leg.timed(torch, K, W, per_launch=wl["feat"])
     Bytes = _bytes_per_env_step(wl, leg.b)
     mean_ms = statistics.mean(per)
-    achieved = Bytes * N / (mean_ms * 1e-3) / 1e9
-    res = {"workload": wl["desc"], "envs": N, "steps": K, "warmup": W + 20, "value": N * K / (ms * 1e-3), "unit": "env-steps/s",
-           "robot_steps_per_s": N * K / (ms * 1e-3) * wl["R"], "ms_per_step": ms / K,
+    single_frac = Bytes * N / (mean_ms * 1e-3) / 1e9 / peak
+    step_ms, issue = ms / K, "one fused launch per step"
+    if wl["feat"] and split > 1 and N % (4 * split) == 0:  # the headline's issue mode: env ranges on their own streams
+        sp = leg.ve.split(split, out=leg.out, feat_out=leg.feat)
+        sp.fork()
+        for s in range(4):
+            sp.step(leg.act_list[s % 16])
+        sp.join()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sp.fork()
+        for s in range(K):
+            sp.step(leg.act_list[s % 16])
+        sp.join()
+        e1.record()
+        torch.cuda.synchronize()
+        step_ms, issue = e0.elapsed_time(e1) / K, f"VectorizedEnv.split({split}): {split} launches per step on {split} streams"
+    achieved = Bytes * N / (step_ms * 1e-3) / 1e9
+    res = {"workload": wl["desc"], "envs": N, "steps": K, "warmup": W + 20, "value": N / (step_ms * 1e-3), "unit": "env-steps/s",
+           "robot_steps_per_s": N / (step_ms * 1e-3) * wl["R"], "ms_per_step": step_ms, "issue": issue,
            "roofline": {"bound": "hbm" if wl["feat"] else "latency (state is L2-resident)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "bytes_per_env_step": Bytes, "mean_launch_ms": mean_ms, "kernel": _kernel_name(wl)}}
+                        "frac": achieved / peak, "bytes_per_env_step": Bytes, "kernel": _kernel_name(wl),
+                        "single_launch": {"mean_launch_ms": mean_ms, "frac": single_frac}}}
     if not wl["feat"]:  # launch-bound: also the graph-captured multi-step entry point
         try:
             S = 64
@@ -426,24 +445,49 @@ def gpu_arm(args):
             dist.all_reduce(stats)
 
     # ---- device-resident arm ------------------------------------------------------------------
+    # Two ways to issue the same K steps over the same N envs:
+    #   single: one fused launch per step on the current stream;
+    #   split:  VectorizedEnv.split(P): P contiguous env ranges, each stepped on its own stream into the same full-batch tensors
+    #           (P launches per step).  Ranges never wait for each other, so one range's launch ramp / drain overlaps another's
+    #           steady state.  This is the headline mode when --split > 1.
+    split = args.split if (kind == "path" and feat_on and N % (4 * max(1, args.split)) == 0) else 1
+    sp = ve.split(split, out=out, feat_out=feat) if split > 1 else None
+
+    def run_region(k_steps, first, use_split):
+        """k_steps steps + the end-of-rollout collective between two events on the current stream -> (ms total, ms collective, per-launch list or None)"""
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        per = None
+        evs[0].record()
+        if use_split:
+            sp.fork()
+            for s in range(k_steps):
+                sp.step(actions[(first + s) % n_act])
+            sp.join()
+        else:
+            pl = [torch.cuda.Event(enable_timing=True) for _ in range(k_steps + 1)]
+            pl[0].record()
+            for s in range(k_steps):
+                one_step(actions[(first + s) % n_act])
+                pl[s + 1].record()
+            per = pl
+        evs[1].record()
+        end_of_rollout()
+        evs[2].record()
+        return evs, per
+
     for s in range(W):
         one_step(actions[s % n_act])
+    if sp is not None:
+        run_region(3, W, True)
     end_of_rollout()
     end_of_rollout()
     t_h = b.time_steps_host()  # (one D2H, outside the timed region) where in the episode the timed window sits
     barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
-    ev_end = torch.cuda.Event(enable_timing=True)
-    ev[0].record()
-    for s in range(K):
-        one_step(actions[(W + s) % n_act])
-        ev[s + 1].record()
-    end_of_rollout()
-    ev_end.record()
+    evs, per = run_region(K, W, sp is not None)
     barrier()
-    ms_total = ev[0].elapsed_time(ev_end)
-    collective_ms = ev[K].elapsed_time(ev_end)
-    per_launch = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
+    ms_total = evs[0].elapsed_time(evs[2])
+    collective_ms = evs[1].elapsed_time(evs[2])
+    steps_ms = evs[0].elapsed_time(evs[1])
     t_ms = torch.tensor([ms_total, collective_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -451,6 +495,17 @@ def gpu_arm(args):
     stats_h = stats.cpu().tolist()
     t0_min, t0_max = int(t_h.min()), int(t_h.max())
     waves_in_window = int(((t_h + K) >= T).sum()) if T > 0 else 0
+    # the other mode, timed the same way (reported next to the headline; for split runs this is the kernel's own launch duration)
+    single = None
+    if sp is not None:
+        barrier()
+        evs1, per = run_region(K, W + K, False)
+        barrier()
+        t1 = torch.tensor([evs1[0].elapsed_time(evs1[2])], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t1, op=dist.ReduceOp.MAX)
+        single = {"ms_total": float(t1.item())}
+    per_launch = [per[i].elapsed_time(per[i + 1]) for i in range(K)]
 
     # ---- sustained arm: >= 3 episodes back to back, every env resets (draws its next block in the kernel) several times
     # inside the timed region; nothing is pre-sampled, the host only launches
@@ -461,8 +516,14 @@ def gpu_arm(args):
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        for s in range(Ks):
-            one_step(actions[s % n_act])
+        if sp is not None:
+            sp.fork()
+            for s in range(Ks):
+                sp.step(actions[s % n_act])
+            sp.join()
+        else:
+            for s in range(Ks):
+                one_step(actions[s % n_act])
         end_of_rollout()
         s1.record()
         barrier()
@@ -563,6 +624,39 @@ def gpu_arm(args):
             dist.all_reduce(t_p, op=dist.ReduceOp.MAX)
         pipe_ms = float(t_p.item())
 
+    # ---- end to end with the dependency a trainer has, range by range (VectorizedEnv.split_host): range k's next actions are
+    # submitted only after range k's results of the previous step were read on the host; the other range's kernel runs meanwhile
+    split_e2e_ms = None
+    if sp is not None:
+        hs = ve.split_host(split, feat_out=feat)
+        acc = 0.0
+        for s in range(3):
+            for k in range(hs.parts):
+                hs.submit(k, h_act[s % len(h_act)])
+            for k in range(hs.parts):
+                hs.result(k)
+        hs.join()
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for s in range(Ke):
+            ha = h_act[s % len(h_act)]
+            for k in range(hs.parts):
+                if s > 0:
+                    sh, dn = hs.result(k)  # the host reads range k's shaped rewards + done flags of step s - 1 ...
+                    acc += float(sh[0]) + float(dn[0])
+                hs.submit(k, ha)           # ... before it hands over range k's actions of step s
+        for k in range(hs.parts):
+            sh, dn = hs.result(k)
+            acc += float(sh[0]) + float(dn[0])
+        hs.join()
+        q1.record()
+        barrier()
+        t_q = torch.tensor([q0.elapsed_time(q1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_q, op=dist.ReduceOp.MAX)
+        split_e2e_ms = float(t_q.item())
+
     # ---- the reference API literally returns numpy: the same steps with ALL feature tensors copied to pinned host memory every
     # step (PCIe-bound; reported so that the question is closed, not a configuration anyone should train in)
     feat_host = None
@@ -598,7 +692,7 @@ def gpu_arm(args):
         secondary = {}
         for name in ("c2", "c3k100", "c4", "c5"):
             try:
-                secondary[name] = _secondary(mdb, torch, dev, rank, peak, name)
+                secondary[name] = _secondary(mdb, torch, dev, rank, peak, name, split=split)
             except Exception as ex:  # pragma: no cover
                 secondary[name] = {"unavailable": str(ex)[:200]}
     if world > 1:
@@ -608,8 +702,10 @@ def gpu_arm(args):
         return
 
     Bytes = _bytes_per_env_step(wl, b)
-    mean_launch_ms = statistics.mean(per_launch)
-    achieved = Bytes * N / (mean_launch_ms * 1e-3) / 1e9
+    mean_launch_ms = statistics.mean(per_launch)          # one fused launch over all N envs, alone on the GPU
+    single_frac = Bytes * N / (mean_launch_ms * 1e-3) / 1e9 / peak
+    step_ms = steps_ms / K                                # the headline mode's time per step (all launches of a step)
+    achieved = Bytes * N / (step_ms * 1e-3) / 1e9
     value = world * N * K / (ms_total_max * 1e-3)
     if T > 0 and waves_in_window == 0:
         ar = (f"on-device, drawn inside the kernel by the env's own lane group; the {K} timed steps cover t = {t0_min}..{t0_max + K} of "
@@ -628,24 +724,41 @@ def gpu_arm(args):
         "config": {"workload": wl["desc"], "envs_per_gpu": N, "envs_total": N * world, "parallelism": f"env-shards x{world}",
                    "l2": (f"outputs are {Bytes * N / 1e6:.0f} MB per step per GPU, larger than the 126 MB L2 (no flush needed)" if feat_on
                           else "state (a few MB) is L2-resident by design: this workload is launch/latency-bound, not HBM-bound"),
-                   "auto_reset": ar, "host_cores_per_rank": cores_per_rank},
+                   "auto_reset": ar, "host_cores_per_rank": cores_per_rank,
+                   "issue": (f"VectorizedEnv.split({split}): {split} env ranges on {split} streams, {split} launches per step" if split > 1
+                             else "one fused launch per step")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "kernel": _kernel_name(wl),
-                     "bytes_per_env_step": Bytes, "mean_launch_ms": mean_launch_ms,
-                     "median_launch_ms": statistics.median(per_launch)},
+                     "bytes_per_env_step": Bytes, "step_ms": step_ms,
+                     "how": (f"algorithmic bytes of one step (all {N} envs) / device time per step; a step is {split} launches of the kernel over "
+                             f"{N // split} envs each, on {split} streams, overlapping" if split > 1 else
+                             "algorithmic bytes of one launch / mean launch duration (CUDA events around every launch)"),
+                     "single_launch": {"mean_launch_ms": mean_launch_ms, "median_launch_ms": statistics.median(per_launch),
+                                       "frac": single_frac,
+                                       "note": "the same kernel as ONE launch over all envs, alone on the GPU (events around every launch)"}},
+        "launches_per_step": split * launches_per_step,
         "collective_ms": collective_ms_max,
-        "e2e": {"value": world * N * Ke / (e2e_ms * 1e-3), "unit": "env-steps/s", "steps": Ke,
+        "e2e": {"value": world * N * Ke / ((split_e2e_ms or e2e_ms) * 1e-3), "unit": "env-steps/s", "steps": Ke,
                 "h2d_bytes_per_step": N * R, "d2h_bytes_per_step": N * 5,
-                "note": "synchronous: actions from pinned host memory, shaped reward + done read back and waited for every step; "
-                        "features stay in HBM",
+                "note": ((f"VectorizedEnv.split_host({split}): every step copies its actions from pinned host memory in and its shaped rewards + "
+                          f"done flags out; {split} env ranges on {split} streams, and a range's next actions are submitted only after the host "
+                          "has read that range's results of the previous step (a trainer's dependency); features stay in HBM")
+                         if split_e2e_ms else
+                         "synchronous: actions from pinned host memory, shaped reward + done read back and waited for every step; "
+                         "features stay in HBM"),
+                "sync_value": world * N * Ke / (e2e_ms * 1e-3),
+                "sync_note": "whole batch at once through rollout_step: H2D actions -> one launch -> D2H shaped + done -> wait, every step",
                 **({"pipelined_value": world * N * Ke / (pipe_ms * 1e-3),
                     "pipelined_note": "VectorizedEnv.host_pipeline(): same copies every step, double-buffered on copy streams so "
                                       "that they overlap the kernel (the host reads step n-1 while step n runs)"} if pipe_ms else {}),
                 **({"features_to_host": feat_host} if feat_host else {})},
-        "gpu_launches": K * launches_per_step + 1,
+        "gpu_launches": K * launches_per_step * split + 1,
         "clocks": clocks,
         "episode_stats": dict(zip(mdb.STAT_NAMES, stats_h)), "starved_envs": starved,
     }
+    if single is not None:
+        line["single_stream"] = {"value": world * N * K / (single["ms_total"] * 1e-3), "unit": "env-steps/s", "ms_per_step": single["ms_total"] / K,
+                                 "note": "the same K steps as one launch per step on one stream (round-1 headline mode)"}
     if sustained is not None:
         line["sustained"] = sustained
     if graph_ms is not None:
@@ -736,6 +849,7 @@ def main():
     ap.add_argument("--cpu-envs", type=int, default=5, help="envs per core in the CPU arm (the reference trains with 5)")
     ap.add_argument("--cpu-steps", type=int, default=600, help="steps per core in the CPU arm")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--split", type=int, default=2, help="env ranges stepped on their own streams (VectorizedEnv.split); 1 = one launch per step")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short C2 / C3-K100 / C4 / C5 legs (N=1, c3 only)")
     ap.add_argument("--no-feat-host", action="store_true", help="skip the features-to-host end-to-end leg")
     ap.add_argument("--sustained-episodes", type=int, default=3, help="whole episodes timed back to back in the sustained leg (0 = off)")

@@ -190,6 +190,17 @@ int32_t mdx_step_featurize(mdx_env* env, const uint8_t* d_actions, const int32_t
                            double* d_reward, float* d_shaped, uint8_t* d_done, float* d_obs,
                            float* d_vec, float* d_gstate, float* d_gvec, uint32_t flags, void* stream);
 
+/* mdx_step / mdx_step_featurize for the CONTIGUOUS env range [first_env, first_env + n): every pointer addresses row 0 of
+ * the range (the caller offsets its full-batch tensors).  Ranges of one instance are independent, so a caller may keep
+ * several in flight on different streams -- VectorizedEnv.split() steps two half-batches on two streams, which hides one
+ * half's launch ramp and drain behind the other half's steady state and lets a trainer overlap policy inference on one half
+ * with env stepping of the other (MAPPO/trainer.py:172-286 is one such loop per env slice). */
+int32_t mdx_step_range(mdx_env* env, const uint8_t* d_actions, int32_t first_env, int32_t n, double* d_reward, float* d_shaped,
+                       uint8_t* d_done, uint32_t flags, void* stream);
+int32_t mdx_step_featurize_range(mdx_env* env, const uint8_t* d_actions, int32_t first_env, int32_t n, double* d_reward,
+                                 float* d_shaped, uint8_t* d_done, float* d_obs, float* d_vec, float* d_gstate, float* d_gvec,
+                                 uint32_t flags, void* stream);
+
 /* compute_shaped_rewards on caller-supplied "current" robots (MAPPO/helper.py:257-369) against the
  * stored state as "previous": d_cur_robots [n, R] u32 = cell | carry << 16, d_cur_t [n] int32,
  * d_global_reward [n] f64 -> d_out [n] f32.  Does not modify the environments. */

@@ -87,6 +87,8 @@ SYMBOLS = {
     "mdx_tracker_clear": (C.c_int32, [_VP, _VP, C.c_int32, _VP]),
     "mdx_tracker_get": (C.c_int32, [_VP, C.c_int32, _VP, _VP, _VP, _VP]),
     "mdx_tracker_set": (C.c_int32, [_VP, C.c_int32, C.c_int32, _VP, _VP, _VP]),
+    "mdx_step_range": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, _VP, _VP, C.c_uint32, _VP]),
+    "mdx_step_featurize_range": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_uint32, _VP]),
     "mdx_step_n": (C.c_int32, [_VP, _VP, C.c_int32, _VP, _VP, _VP, C.c_uint32, _VP]),
     "mdx_state_row_bytes": (C.c_int64, [_VP]),
     "mdx_get_states": (C.c_int32, [_VP, _VP, C.c_int32, _VP, _VP]),

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128) mdx_alt_featurize_kernel(const __grid_con
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int widx = blockIdx.x * (blockDim.x >> 5) + wib;
   if (widx >= p.n) return;
-  const int env = p.env_ids ? __ldg(p.env_ids + widx) : widx;
+  const int env = p.env_ids ? __ldg(p.env_ids + widx) : p.env_base + widx;
   if ((unsigned)env >= (unsigned)p.n_envs) return;  // a bad caller-supplied id never becomes an out-of-bounds access (row left unwritten)
   const int R = p.R, P = p.P, HW = p.HW, W32 = p.W32;
   float* urg = reinterpret_cast<float*>(alt_smem + (size_t)wib * a.smem_per_warp);  // [HW rounded up to 4]
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(128) mdx_alt_featurize_sliced(const __grid_con
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int widx = blockIdx.x * (blockDim.x >> 5) + wib;
   if (widx >= p.n) return;
-  const int env = p.env_ids ? __ldg(p.env_ids + widx) : widx;
+  const int env = p.env_ids ? __ldg(p.env_ids + widx) : p.env_base + widx;
   if ((unsigned)env >= (unsigned)p.n_envs) return;  // a bad caller-supplied id never becomes an out-of-bounds access (row left unwritten)
   const int R = p.R, P = p.P, HW = p.HW, W32 = p.W32;
   float* urg = reinterpret_cast<float*>(alt_smem + kLutBytes + (size_t)wib * a.smem_per_warp);

@@ -393,7 +393,8 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
     const int o_wkey = take(need_wkey ? 4 * b.Pp8 : 0);
     const int o_rinfo = take(2 * 5 * 32);
     const int o_alist = take(2 * std::max(8, round_up(std::min(b.MP, std::max(1, e->P)), 8)));
-    const int o_sel = take(2 * std::max(8, round_up(rpf * std::max(1, b.sel_k), 8)));
+    // (+ 32 candidate slots behind the selected indices for the few-slots / long-list selection path: P > 64, <= 5 slots)
+    const int o_sel = take(2 * (std::max(8, round_up(rpf * std::max(1, b.sel_k), 8)) + ((e->P > 64 && b.sel_k <= 5) ? 32 : 0)));
     const int o_masks = take(4 * 10 * b.W32);
     const int o_stage = off;
     // (the fused IDQ featuriser keeps its H*W urgency plane in the stage)
@@ -582,7 +583,7 @@ int32_t mdx_get_dims(const mdx_env* e, mdx_dims* out) {
 static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int32_t* d_env_ids, int32_t n, double* d_reward,
                        float* d_shaped, uint8_t* d_done, float* d_obs, float* d_vec, float* d_gstate, float* d_gvec,
                        uint32_t flags, void* stream, double* d_agent = nullptr, int ops_as_int = 0, float* d_obs6 = nullptr,
-                       float* d_g7 = nullptr, uint32_t internal_flags = 0);
+                       float* d_g7 = nullptr, uint32_t internal_flags = 0, int32_t first_env = -1);
 
 // MDX_CFG_STALE_TRACKER: the trainer's dict sees the reset state (MAPPO/trainer.py:232-233) -- internal flag 4 of the
 // featurise-mode kernel with no outputs; internal flag 8 empties the dict instead.
@@ -636,14 +637,20 @@ int32_t mdx_prefetch(mdx_env* e, int32_t ahead, void* stream) {
 
 static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int32_t* d_env_ids, int32_t n, double* d_reward,
                        float* d_shaped, uint8_t* d_done, float* d_obs, float* d_vec, float* d_gstate, float* d_gvec,
-                       uint32_t flags, void* stream, double* d_agent, int ops_as_int, float* d_obs6, float* d_g7, uint32_t internal_flags) {
+                       uint32_t flags, void* stream, double* d_agent, int ops_as_int, float* d_obs6, float* d_g7, uint32_t internal_flags,
+                       int32_t first_env) {
   if (!e) return fail(MDX_E_INVALID, "null env");
   if (e->stale && (d_agent || mode == 5))
     return fail(MDX_E_INVALID, "the IDQ entry points read the env truth (IDQ/trainer.py:236 clears its tracker); not available on an "
                                "MDX_CFG_STALE_TRACKER instance");
   if ((mode & 1) && !d_actions) return fail(MDX_E_INVALID, "actions are required");
   if ((mode & 1) && (e->cfg.flags & MDX_CFG_LAX_ROBOTS)) return fail(MDX_E_INVALID, "an MDX_CFG_LAX_ROBOTS instance cannot be stepped");
-  if (d_env_ids == nullptr && n != e->n) return fail(MDX_E_INVALID, "n must equal n_envs when env ids are not given (got %d, have %d)", n, e->n);
+  if (first_env < 0) {  // (the plain entry points: all envs, or the listed ones)
+    first_env = 0;
+    if (d_env_ids == nullptr && n != e->n) return fail(MDX_E_INVALID, "n must equal n_envs when env ids are not given (got %d, have %d)", n, e->n);
+  } else if (d_env_ids != nullptr || first_env > e->n - n) {
+    return fail(MDX_E_INVALID, "bad env range [%d, %d + %d) of %d envs", first_env, first_env, n, e->n);
+  }
   if (n < 0 || n > e->n) return fail(MDX_E_INVALID, "bad env count %d", n);
   if (n == 0) return MDX_OK;
   int rc;
@@ -654,6 +661,7 @@ static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int
   KParams kp = e->base;
   kp.actions = d_actions;
   kp.env_ids = d_env_ids;
+  kp.env_base = first_env;
   kp.n = n;
   kp.flags = (flags & 3u) | internal_flags;
   kp.out_reward = d_reward;
@@ -727,6 +735,20 @@ int32_t mdx_step_featurize(mdx_env* e, const uint8_t* d_actions, const int32_t* 
                            float* d_shaped, uint8_t* d_done, float* d_obs, float* d_vec, float* d_gstate, float* d_gvec,
                            uint32_t flags, void* stream) {
   return step_common(e, 3, d_actions, d_env_ids, n, d_reward, d_shaped, d_done, d_obs, d_vec, d_gstate, d_gvec, flags, stream);
+}
+
+int32_t mdx_step_range(mdx_env* e, const uint8_t* d_actions, int32_t first_env, int32_t n, double* d_reward, float* d_shaped,
+                       uint8_t* d_done, uint32_t flags, void* stream) {
+  if (first_env < 0) return fail(MDX_E_INVALID, "negative first env");
+  return step_common(e, 1, d_actions, nullptr, n, d_reward, d_shaped, d_done, nullptr, nullptr, nullptr, nullptr, flags, stream, nullptr, 0,
+                     nullptr, nullptr, 0, first_env);
+}
+
+int32_t mdx_step_featurize_range(mdx_env* e, const uint8_t* d_actions, int32_t first_env, int32_t n, double* d_reward, float* d_shaped,
+                                 uint8_t* d_done, float* d_obs, float* d_vec, float* d_gstate, float* d_gvec, uint32_t flags, void* stream) {
+  if (first_env < 0) return fail(MDX_E_INVALID, "negative first env");
+  return step_common(e, 3, d_actions, nullptr, n, d_reward, d_shaped, d_done, d_obs, d_vec, d_gstate, d_gvec, flags, stream, nullptr, 0,
+                     nullptr, nullptr, 0, first_env);
 }
 
 static int shape_common(mdx_env* e, const uint32_t* d_cur_robots, const int32_t* d_cur_t, const uint8_t* d_actions,

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(128) mdx_greedy_kernel(const __grid_constant__
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int widx = blockIdx.x * (blockDim.x >> 5) + wib;
   if (widx >= p.n) return;
-  const int env = p.env_ids ? __ldg(p.env_ids + widx) : widx;
+  const int env = p.env_ids ? __ldg(p.env_ids + widx) : p.env_base + widx;
   if ((unsigned)env >= (unsigned)p.n_envs) return;  // a bad caller-supplied id never becomes an out-of-bounds access (row left unwritten)
   uint32_t* fr = sm_free + (size_t)wib * a.fw;
   MapDev map = p.map0;

@@ -118,6 +118,7 @@ struct KParams {
   // call arguments
   const uint8_t* actions;
   const int32_t* env_ids;
+  int32_t env_base;         // env_ids == nullptr: launch row i works on env env_base + i (contiguous range)
   int32_t n;
   uint32_t flags;
   double* out_reward;

@@ -544,6 +544,50 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
       nws[s_] = ok ? (w.planes[2 * W32 + wi] >> sh) & 15u : 0u;
       nat[s_] = ok ? (w.planes[3 * W32 + wi] >> sh) & 15u : 0u;
     }
+#ifndef MDX_FIX_HOIST
+#define MDX_FIX_HOIST 0  // 1: the shape-specialised variant (kFix = 1) also takes the hoisted store loop below
+#endif
+    if constexpr (kFix != 1 || MDX_FIX_HOIST) {
+      // Slice-outer loop.  The planes every robot shares (obstacles, waiting starts, active targets; all robots for gstate) are
+      // expanded ONCE per slice into registers that stay live across the robot loop, and the three per-robot planes (this robot,
+      // the others, own target) are built with compares / selects instead of table loads.  Every store of a robot therefore reads
+      // its own register quad: ncu showed the old loop recycling ONE quad for every `LDS.128 -> STG.128` pair, so that each table
+      // load waited (long scoreboard) until the previous store had drained its operands -- 24 serialised pairs per robot on a
+      // 20 x 20 map.  No shared-memory traffic is left in the loop except one broadcast word per robot.
+      float4* gout = p.gstate != nullptr ? reinterpret_cast<float4*>(p.gstate + (size_t)row * 4 * HW) : nullptr;
+      float4* obase = p.obs != nullptr ? reinterpret_cast<float4*>(p.obs + (size_t)row * R * 6 * HW) : nullptr;
+#pragma unroll
+      for (int s_ = 0; s_ < NS; ++s_) {
+        const int q = sl + LPE * s_;
+        if (q < n4p) {
+          const float4 G = lut[ng[s_]], Rb = lut[nrb[s_]], Wt = lut[nws[s_]], At = lut[nat[s_]];
+          if (gout != nullptr) {
+            __stcs(gout + q, G);
+            __stcs(gout + n4p + q, Rb);
+            __stcs(gout + 2 * n4p + q, Wt);
+            __stcs(gout + 3 * n4p + q, At);
+          }
+          if (obase != nullptr) {
+            const uint32_t c0 = (uint32_t)q << 2;  // first cell of this lane's float4
+            float4* o = obase + q;
+#pragma unroll 2
+            for (int i = 0; i < R; ++i) {
+              const uint32_t dr_ = (uint32_t)w.rcell[i] - c0, dt_ = (uint32_t)w.rtgt[i] - c0;  // 0..3 <=> the cell is in this float4
+              const float4 S = make_float4(dr_ == 0u ? 1.f : 0.f, dr_ == 1u ? 1.f : 0.f, dr_ == 2u ? 1.f : 0.f, dr_ == 3u ? 1.f : 0.f);
+              const float4 O = make_float4(dr_ == 0u ? 0.f : Rb.x, dr_ == 1u ? 0.f : Rb.y, dr_ == 2u ? 0.f : Rb.z, dr_ == 3u ? 0.f : Rb.w);
+              const float4 Tg = make_float4(dt_ == 0u ? 1.f : 0.f, dt_ == 1u ? 1.f : 0.f, dt_ == 2u ? 1.f : 0.f, dt_ == 3u ? 1.f : 0.f);
+              __stcs(o, G);             // 0: obstacles
+              __stcs(o + n4p, S);       // 1: this robot
+              __stcs(o + 2 * n4p, O);   // 2: other robots
+              __stcs(o + 3 * n4p, Wt);  // 3: waiting starts
+              __stcs(o + 4 * n4p, At);  // 4: active targets
+              __stcs(o + 5 * n4p, Tg);  // 5: own carried target (rtgt = 0xFFFF when there is none: never inside a plane)
+              o += 6 * n4p;
+            }
+          }
+        }
+      }
+    } else {
     if (p.gstate != nullptr) {
       float4* out4 = reinterpret_cast<float4*>(p.gstate + (size_t)row * 4 * HW);
 #pragma unroll
@@ -578,6 +622,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
           }
         }
       }
+    }
     }
   } else {
     // ---- generic path: flat loops, per robot three private planes (double-buffered) ---------------
@@ -664,6 +709,56 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
     const bool lane_sel = kSmall && Ksel <= LPE;
     const int RP = lane_sel ? (int)div_magic((uint32_t)LPE, p.mul_ksel) : 1;  // robots per pass = LPE / Ksel
     const int sel_ii = (int)div_magic((uint32_t)sl, p.mul_ksel), sel_q = sl - sel_ii * Ksel;
+    // Few slots on a long waiting list (C4 / C5: K_p <= 5, P > 64).  The selection order is (remaining deadline, distance rank,
+    // list index) and the deadline does not depend on the robot, so only entries whose remaining deadline is <= the nsel-th
+    // smallest one (with multiplicity) can ever be selected, for ANY robot.  That candidate set is found once per env; while it
+    // fits the group (it nearly always does: it only grows with ties, i.e. many packages past their deadline), every robot costs
+    // one key per lane and nsel arg-min rounds instead of a pass over the whole list.
+    bool use_cand = false;
+    uint32_t c_k = MDX_NONE32, c_dlk = 0u;
+    int c_off = 0;
+    if constexpr (!kSmall && kFix != 1) {
+      if (Ksel <= 5 && nsel > 0 && nw > LPE) {
+        uint32_t d0 = MDX_NONE32, d1 = MDX_NONE32, d2 = MDX_NONE32, d3 = MDX_NONE32, d4 = MDX_NONE32;
+#pragma unroll 2
+        for (int k = sl; k < nw; k += LPE) {
+          uint32_t x = w.wdl[k], lo;
+          lo = min(d0, x), x = max(d0, x), d0 = lo;
+          lo = min(d1, x), x = max(d1, x), d1 = lo;
+          lo = min(d2, x), x = max(d2, x), d2 = lo;
+          lo = min(d3, x), x = max(d3, x), d3 = lo;
+          d4 = min(d4, x);
+        }
+        uint32_t thr = 0u;
+#pragma unroll 1
+        for (int q = 0; q < nsel; ++q) {  // pop the nsel smallest deadlines one at a time (ties: the lowest lane pops)
+          thr = g.rmin(d0);
+          const unsigned m = g.ballot(d0 == thr);
+          if (sl == __ffs(m) - 1) d0 = d1, d1 = d2, d2 = d3, d3 = d4, d4 = MDX_NONE32;
+        }
+        uint16_t* cand = w.sel + ((rpf * Ksel + 7) & ~7);
+        int ncand = 0;
+#pragma unroll 1
+        for (int base = 0; base < nw; base += LPE) {
+          const int k = base + sl;
+          const bool is = k < nw && (uint32_t)w.wdl[k] <= thr;
+          const unsigned m = g.ballot(is);
+          if (is) {
+            const int pos = ncand + __popc(m & lt);
+            if (pos < LPE) cand[pos] = (uint16_t)k;
+          }
+          ncand += __popc(m);
+        }
+        g.sync();
+        use_cand = ncand <= LPE;
+        if (use_cand && sl < ncand) {
+          c_k = cand[sl];
+          const uint32_t rc = w.wrc[c_k];
+          c_off = (int)(rc >> 8) * NC + (int)(rc & 255u);
+          c_dlk = (uint32_t)w.wdl[c_k] * (uint32_t)p.nranks_max;
+        }
+      }
+    }
 #pragma unroll 1
     for (int i0 = 0; i0 < R; i0 += rpf) {
       const int nrows = min(rpf, R - i0);
@@ -899,6 +994,23 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
         // Few slots, long waiting list (C4 / C5): while it computes the keys of its entries, every lane keeps its
         // own five smallest in sorted registers; a round is then one group arg-min over the lanes' heads and a
         // register shift in the winning lane -- no key array in shared memory, no rescans.
+        if (use_cand) {
+#pragma unroll 2
+          for (int i = i0; i < i0 + nrows; ++i) {
+            const uint32_t rci = w.rrc[i];
+            const int bi = (Hm1 - (int)(rci >> 8)) * NC + (Wm1 - (int)(rci & 255u));
+            uint16_t* selp = w.sel + (i - i0) * Ksel;
+            uint32_t key = c_k != MDX_NONE32 ? (((c_dlk + (uint32_t)__ldg(map.rank + c_off + bi)) << p.key_wbits) | c_k) : MDX_NONE32;
+#pragma unroll 1
+            for (int q = 0; q < nsel; ++q) {
+              const uint32_t best = g.rmin(key);
+              if (key == best) {  // exactly one lane: keys are unique
+                selp[q] = (uint16_t)(best & wmask);
+                key = MDX_NONE32;
+              }
+            }
+          }
+        } else {
 #pragma unroll 1
         for (int i = i0; i < i0 + nrows; ++i) {
           const uint32_t rci = w.rrc[i];
@@ -925,6 +1037,7 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
               a0 = a1, a1 = a2, a2 = a3, a3 = a4, a4 = MDX_NONE32;
             }
           }
+        }
         }
         g.sync();
         const int nslot = nrows * Ksel;
@@ -1309,7 +1422,7 @@ __global__ void __launch_bounds__((kFix == 1 && (kMode & 2)) ? MDX_FIX_THREADS :
   const Grp<LPE> g(threadIdx.x & 31);
   const int sl = g.sl;
   const Env w = carve(p, smem_raw + kLutBytes + (size_t)gib * p.smem_per_warp);
-  const int env = p.env_ids ? __ldg(p.env_ids + widx) : widx;
+  const int env = p.env_ids ? __ldg(p.env_ids + widx) : p.env_base + widx;
   if ((unsigned)env >= (unsigned)p.n_envs) return;  // a bad caller-supplied id never becomes an out-of-bounds access (row left unwritten)
   const int R = p.R, P = p.P, Wo = p.W_out;
   const bool active = sl < R;

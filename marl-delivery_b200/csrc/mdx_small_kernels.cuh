@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) mdx_reset_kernel(const __grid_constant__ 
   const int wib = threadIdx.x >> 5;
   const int widx = blockIdx.x * (blockDim.x >> 5) + wib;
   if (widx >= p.n) return;
-  const int env = p.env_ids ? p.env_ids[widx] : widx;
+  const int env = p.env_ids ? p.env_ids[widx] : p.env_base + widx;
   const MapDev map = p.env_map ? p.maps[p.env_map[env]] : p.map0;
   uint16_t* s_sched = reinterpret_cast<uint16_t*>(smem_raw + (size_t)wib * 8 * p.Pp8);
   const int cell = sample_episode<32>(p, map.free_cells, map.n_free, map.H, s_sched, env);

@@ -110,9 +110,150 @@ class VectorizedEnv:
         RolloutGraph."""
         return RolloutGraph(self, n_steps, auto_reset=auto_reset)
 
+    def split(self, parts=2, out=None, feat_out=None, auto_reset=True, featurize=True):
+        """The batch as `parts` contiguous env ranges, each stepped on its own CUDA stream; see SplitRollout."""
+        return SplitRollout(self, parts, out=out, feat_out=feat_out, auto_reset=auto_reset, featurize=featurize)
+
+    def split_host(self, parts=2, feat_out=None, auto_reset=True):
+        """`split()` for callers whose actions and results live in HOST memory; see SplitHostStepper."""
+        return SplitHostStepper(self, parts, feat_out=feat_out, auto_reset=auto_reset)
+
     def host_pipeline(self, feat_out=None, auto_reset=True):
         """Double-buffered host <-> device stepping for callers whose actions live in HOST memory; see HostPipeline."""
         return HostPipeline(self, feat_out=feat_out, auto_reset=auto_reset)
+
+
+class SplitRollout:
+    """`rollout_step` over `parts` contiguous env ranges, each on its own CUDA stream, writing into ONE set of full-batch tensors.
+
+    Environments are independent, so nothing orders range A's step s + 1 after range B's step s: with two ranges in flight the GPU
+    always has a launch in its steady state while the other one ramps up or drains (a 65 536-env launch spends ~17 us of its
+    ~224 us there), and a trainer can run policy inference on one range's fresh observations while the other range steps
+    (the loop of MAPPO/trainer.py:172-286, once per range).
+
+        sp = ve.split(2)
+        sp.fork()                          # the range streams wait for what the current stream has enqueued (e.g. the actions)
+        for s in range(K):
+            sp.step(actions[s])            # uint8 [N, R] on the GPU: range k reads its rows, launches on stream k
+        sp.join()                          # the current stream waits for every range
+        reward, shaped, done = sp.out;  obs, vec, gstate, gvec = sp.feat
+
+    `step_part(k, actions)` launches one range only (range k's rows of the same full tensors).  Results are identical to
+    rollout_step on the whole batch (tests/test_gpu_r2.py)."""
+
+    def __init__(self, ve, parts=2, out=None, feat_out=None, auto_reset=True, featurize=True):
+        b = ve.batch
+        self.batch, self.auto_reset, self.featurize = b, auto_reset, featurize
+        N, R, dev = b.n_envs, b.n_robots, b.device
+        if not 1 <= parts <= N:
+            raise ValueError("parts must be in [1, n_envs]")
+        bounds = [N * i // parts for i in range(parts + 1)]
+        self.ranges = [(lo, hi) for lo, hi in zip(bounds[:-1], bounds[1:]) if hi > lo]
+        self.streams = [torch.cuda.Stream(dev) for _ in self.ranges]
+        self.out = out if out is not None else (torch.empty(N, dtype=torch.float64, device=dev), torch.empty(N, dtype=torch.float32, device=dev),
+                                                torch.empty(N, dtype=torch.uint8, device=dev))
+        pr, ps, pd = b._check_out(self.out, b._rsd_specs(N, ("shaped", N, torch.float32)))
+        self.feat = None
+        fp, frow = (None, None, None, None), (0, 0, 0, 0)
+        if featurize:
+            self.feat = feat_out if feat_out is not None else b.alloc_features(N)
+            fp = b._check_out(self.feat, b._feat_specs(N))
+            HW = b.rows_out * b.cols_out
+            frow = (4 * R * 6 * HW, 4 * R * b.vec_dim, 4 * 4 * HW, 4 * b.gvec_dim)
+        off = lambda p, lo, row: None if p is None else p + lo * row  # noqa: E731
+        # 16-byte alignment of every range's first feature row (the kernels store float4)
+        for lo, _ in self.ranges:
+            for p_, row in zip(fp, frow):
+                if p_ is not None and (p_ + lo * row) % 16:
+                    raise ValueError("a range would start at a feature row that is not 16-byte aligned: use a different number of parts")
+        self._args = [(lo, hi - lo, off(pr, lo, 8), off(ps, lo, 4), off(pd, lo, 1), *(off(p_, lo, row) for p_, row in zip(fp, frow)))
+                      for lo, hi in self.ranges]
+        self._ev = [torch.cuda.Event() for _ in self.ranges]
+        self._fork_ev = torch.cuda.Event()
+        self._flags = 1 if auto_reset else 0
+
+    def fork(self):
+        self._fork_ev.record(torch.cuda.current_stream(self.batch.device))
+        for st in self.streams:
+            st.wait_event(self._fork_ev)
+
+    def join(self):
+        cur = torch.cuda.current_stream(self.batch.device)
+        for st, ev in zip(self.streams, self._ev):
+            ev.record(st)
+            cur.wait_event(ev)
+
+    def step_part(self, k, actions):
+        """Range k only.  `actions`: the FULL uint8 [N, R] action tensor (range k reads its own rows)."""
+        b = self.batch
+        if not (actions.__class__ is torch.Tensor and actions.dtype is torch.uint8 and actions.is_cuda and actions.is_contiguous()
+                and tuple(actions.shape) == (b.n_envs, b.n_robots)):
+            raise ValueError("actions must be a contiguous uint8 CUDA tensor [n_envs, n_robots]")
+        lo, n, pr, ps, pd, po, pv, pg, pgv = self._args[k]
+        a = actions.data_ptr() + lo * b.n_robots
+        st = self.streams[k].cuda_stream
+        if self.featurize:
+            rc = b._L.mdx_step_featurize_range(b._h, a, lo, n, pr, ps, pd, po, pv, pg, pgv, self._flags, st)
+        else:
+            rc = b._L.mdx_step_range(b._h, a, lo, n, pr, ps, pd, self._flags, st)
+        if rc:
+            from . import _lib
+            _lib.check(rc)
+        b._version += 1
+
+    def step(self, actions):
+        for k in range(len(self.ranges)):
+            self.step_part(k, actions)
+        return self.out, self.feat
+
+
+class SplitHostStepper:
+    """`rollout_step` for HOST actions and HOST results, env range by env range, with the true data dependency of a trainer's
+    loop: range k's actions for step s + 1 are submitted only after range k's results of step s have been read on the host.
+
+        hs = ve.split_host(2)
+        for k in range(hs.parts): hs.submit(k, h_actions)          # pinned uint8 [N, R]; range k reads its rows
+        while training:
+            for k in range(hs.parts):
+                shaped_k, done_k = hs.result(k)                    # numpy views of pinned memory: range k's rows of the last step
+                ... choose range k's next actions from them ...
+                hs.submit(k, h_actions)
+
+    Each range has its own stream, on which its H2D copy, its launch and its D2H copies are enqueued in order; while one range's
+    copies and host work are in flight the other range's kernel keeps HBM busy, so a step costs (about) one kernel pass over the
+    batch although every step moves its actions in and its shaped rewards + done flags out.  Feature tensors stay in HBM."""
+
+    def __init__(self, ve, parts=2, feat_out=None, auto_reset=True):
+        self.sp = sp = SplitRollout(ve, parts, feat_out=feat_out, auto_reset=auto_reset)
+        b = ve.batch
+        N, R, dev = b.n_envs, b.n_robots, b.device
+        self.parts = len(sp.ranges)
+        self.feat = sp.feat
+        self.d_act = torch.empty((N, R), dtype=torch.uint8, device=dev)
+        self.h_shaped = torch.empty(N, dtype=torch.float32).pin_memory()
+        self.h_done = torch.empty(N, dtype=torch.uint8).pin_memory()
+        np_sh, np_dn = self.h_shaped.numpy(), self.h_done.numpy()
+        self._v = [(lo, hi, self.d_act[lo:hi], sp.out[1][lo:hi], sp.out[2][lo:hi], self.h_shaped[lo:hi], self.h_done[lo:hi], np_sh[lo:hi],
+                    np_dn[lo:hi]) for lo, hi in sp.ranges]
+        self._ev = [torch.cuda.Event() for _ in sp.ranges]
+
+    def submit(self, k, h_actions):
+        lo, hi, d_a, d_sh, d_dn, h_sh, h_dn, _, _ = self._v[k]
+        st = self.sp.streams[k]
+        with torch.cuda.stream(st):
+            d_a.copy_(h_actions[lo:hi], non_blocking=True)
+            self.sp.step_part(k, self.d_act)
+            h_sh.copy_(d_sh, non_blocking=True)
+            h_dn.copy_(d_dn, non_blocking=True)
+            self._ev[k].record(st)
+
+    def result(self, k):
+        """Blocks until range k's last submitted step is on the host -> (shaped float32 [n_k], done uint8 [n_k]) numpy views."""
+        self._ev[k].synchronize()
+        return self._v[k][7], self._v[k][8]
+
+    def join(self):
+        self.sp.join()
 
 
 class RolloutGraph:

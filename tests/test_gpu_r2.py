@@ -140,6 +140,70 @@ def test_step_n_and_rollout_graph_equal_step_by_step():
         a.batch.step_n(acts[:, :7])
 
 
+def test_split_rollout_on_two_streams_equals_whole_batch_steps():
+    kw = dict(map_file="map1.txt", n_robots=5, n_packages=50, max_time_steps=25, seed=77, k_others=4, k_packages=5)
+    N, S = 600, 60
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    acts = torch.randint(0, 15, (S, N, 5), dtype=torch.uint8, device="cuda", generator=gen)
+    for parts in (2, 3):
+        ref = mdb.VectorizedEnv(mdb.Environment, N, **kw)
+        ref.batch.reset()
+        ve = mdb.VectorizedEnv(mdb.Environment, N, **kw)
+        ve.batch.reset()
+        sp = ve.split(parts)
+        assert [hi - lo for lo, hi in sp.ranges] == [N // parts] * parts
+        for s in range(S):
+            want = [t.clone() for t in ref.rollout_step(acts[s])]
+            sp.fork()
+            if s % 2:
+                sp.step(acts[s])
+            else:  # ranges may also be stepped one at a time, in any order
+                for k in reversed(range(parts)):
+                    sp.step_part(k, acts[s])
+            sp.join()
+            got = list(sp.out) + list(sp.feat)
+            for x, y in zip(want, got):
+                assert torch.equal(x, y), (parts, s)
+        assert torch.equal(ref.batch.episode_stats(), ve.batch.episode_stats())
+    # many steps in flight without joining: ranges never wait for each other, the results are the same
+    ve = mdb.VectorizedEnv(mdb.Environment, N, **kw)
+    ve.batch.reset()
+    ref = mdb.VectorizedEnv(mdb.Environment, N, **kw)
+    ref.batch.reset()
+    sp = ve.split(2, featurize=False)
+    sp.fork()
+    for s in range(S):
+        sp.step(acts[s])
+        ref.step_tensor(acts[s], auto_reset=True)
+    sp.join()
+    torch.cuda.synchronize()
+    assert ve.batch.get_rows().tobytes() == ref.batch.get_rows().tobytes()
+    with pytest.raises(ValueError):
+        ve.split(2).step_part(0, acts[0][:10])
+
+
+def test_split_host_stepper_equals_host_pipeline_results():
+    kw = dict(map_file="map1.txt", n_robots=5, n_packages=50, max_time_steps=15, seed=19, k_others=4, k_packages=5)
+    N, S = 256, 40
+    h_act = torch.randint(0, 15, (S, N, 5), dtype=torch.uint8, generator=torch.Generator().manual_seed(2)).pin_memory()
+    ref = mdb.VectorizedEnv(mdb.Environment, N, **kw)
+    ref.batch.reset()
+    ve = mdb.VectorizedEnv(mdb.Environment, N, **kw)
+    ve.batch.reset()
+    hs = ve.split_host(2)
+    for s in range(S):
+        r, sh, d, o, v, g, gv = ref.rollout_step(h_act[s].cuda())
+        for k in range(hs.parts):
+            hs.submit(k, h_act[s])
+        got_sh = np.concatenate([hs.result(k)[0] for k in range(hs.parts)])
+        got_dn = np.concatenate([hs.result(k)[1] for k in range(hs.parts)])
+        assert np.array_equal(_bits(got_sh), _bits(sh.cpu().numpy())) and np.array_equal(got_dn, d.cpu().numpy()), s
+        hs.join()
+        torch.cuda.synchronize()
+        for x, y in zip((o, v, g, gv), hs.feat):
+            assert torch.equal(x, y), s
+
+
 # ---------------------------------------------------------------------------------------------- memory safety
 CANARY = 1024  # elements on each side
 
