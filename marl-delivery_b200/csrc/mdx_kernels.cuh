@@ -544,50 +544,11 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
       nws[s_] = ok ? (w.planes[2 * W32 + wi] >> sh) & 15u : 0u;
       nat[s_] = ok ? (w.planes[3 * W32 + wi] >> sh) & 15u : 0u;
     }
-#ifndef MDX_FIX_HOIST
-#define MDX_FIX_HOIST 0  // 1: the shape-specialised variant (kFix = 1) also takes the hoisted store loop below
-#endif
-    if constexpr (kFix != 1 || MDX_FIX_HOIST) {
-      // Slice-outer loop.  The planes every robot shares (obstacles, waiting starts, active targets; all robots for gstate) are
-      // expanded ONCE per slice into registers that stay live across the robot loop, and the three per-robot planes (this robot,
-      // the others, own target) are built with compares / selects instead of table loads.  Every store of a robot therefore reads
-      // its own register quad: ncu showed the old loop recycling ONE quad for every `LDS.128 -> STG.128` pair, so that each table
-      // load waited (long scoreboard) until the previous store had drained its operands -- 24 serialised pairs per robot on a
-      // 20 x 20 map.  No shared-memory traffic is left in the loop except one broadcast word per robot.
-      float4* gout = p.gstate != nullptr ? reinterpret_cast<float4*>(p.gstate + (size_t)row * 4 * HW) : nullptr;
-      float4* obase = p.obs != nullptr ? reinterpret_cast<float4*>(p.obs + (size_t)row * R * 6 * HW) : nullptr;
-#pragma unroll
-      for (int s_ = 0; s_ < NS; ++s_) {
-        const int q = sl + LPE * s_;
-        if (q < n4p) {
-          const float4 G = lut[ng[s_]], Rb = lut[nrb[s_]], Wt = lut[nws[s_]], At = lut[nat[s_]];
-          if (gout != nullptr) {
-            __stcs(gout + q, G);
-            __stcs(gout + n4p + q, Rb);
-            __stcs(gout + 2 * n4p + q, Wt);
-            __stcs(gout + 3 * n4p + q, At);
-          }
-          if (obase != nullptr) {
-            const uint32_t c0 = (uint32_t)q << 2;  // first cell of this lane's float4
-            float4* o = obase + q;
-#pragma unroll 2
-            for (int i = 0; i < R; ++i) {
-              const uint32_t dr_ = (uint32_t)w.rcell[i] - c0, dt_ = (uint32_t)w.rtgt[i] - c0;  // 0..3 <=> the cell is in this float4
-              const float4 S = make_float4(dr_ == 0u ? 1.f : 0.f, dr_ == 1u ? 1.f : 0.f, dr_ == 2u ? 1.f : 0.f, dr_ == 3u ? 1.f : 0.f);
-              const float4 O = make_float4(dr_ == 0u ? 0.f : Rb.x, dr_ == 1u ? 0.f : Rb.y, dr_ == 2u ? 0.f : Rb.z, dr_ == 3u ? 0.f : Rb.w);
-              const float4 Tg = make_float4(dt_ == 0u ? 1.f : 0.f, dt_ == 1u ? 1.f : 0.f, dt_ == 2u ? 1.f : 0.f, dt_ == 3u ? 1.f : 0.f);
-              __stcs(o, G);             // 0: obstacles
-              __stcs(o + n4p, S);       // 1: this robot
-              __stcs(o + 2 * n4p, O);   // 2: other robots
-              __stcs(o + 3 * n4p, Wt);  // 3: waiting starts
-              __stcs(o + 4 * n4p, At);  // 4: active targets
-              __stcs(o + 5 * n4p, Tg);  // 5: own carried target (rtgt = 0xFFFF when there is none: never inside a plane)
-              o += 6 * n4p;
-            }
-          }
-        }
-      }
-    } else {
+    // (Round 2 tried the obvious alternative -- expand the planes all robots share once per slice into registers and build the three
+    // per-robot planes with compares / selects, so that no store waits for a table load: 12-15 % SLOWER on C4 / C5 / K = 100
+    // (profiles/r2_experiments.txt).  Stores hold their data AND address registers until the LSU has read them; a loop whose
+    // next iteration rewrites those registers with ALU results stalls on that release (long scoreboard) every iteration, whereas
+    // the table loads below are themselves scoreboarded and overlap it.)
     if (p.gstate != nullptr) {
       float4* out4 = reinterpret_cast<float4*>(p.gstate + (size_t)row * 4 * HW);
 #pragma unroll
@@ -622,7 +583,6 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
           }
         }
       }
-    }
     }
   } else {
     // ---- generic path: flat loops, per robot three private planes (double-buffered) ---------------
