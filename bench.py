@@ -242,10 +242,11 @@ def _pin_rank_to_cores(local, world):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
-def _make_env(mdb, wl, N, rank):
+def _make_env(mdb, wl, N, rank, specialize=False):
     return mdb.VectorizedEnv(mdb.Environment, N, map_file=wl["maps"] if len(wl["maps"]) > 1 else wl["maps"][0], n_robots=wl["R"],
                              n_packages=wl["P"], max_time_steps=wl["T"], seed=BASE_SEED, k_others=wl["K_o"], k_packages=wl["K_p"],
-                             max_robots_in_state=wl["MR"], max_packages_in_state=wl["MP"], first_env_index=rank * N)
+                             max_robots_in_state=wl["MR"], max_packages_in_state=wl["MP"], first_env_index=rank * N,
+                             specialize=specialize)
 
 
 def _bytes_per_env_step(wl, b):
@@ -268,10 +269,12 @@ def _kernel_name(wl):
 class Leg:
     """One workload on this rank's GPU: the env batch, its output tensors and a `one_step(actions)` closure."""
 
-    def __init__(self, mdb, torch, wl, N, rank, dev, n_act):
+    def __init__(self, mdb, torch, wl, N, rank, dev, n_act, specialize=False):
         self.wl, self.N = wl, N
         R = wl["R"]
-        self.ve = _make_env(mdb, wl, N, rank)
+        # specialize: the fused kernel is compiled at run time (NVRTC) for this workload's shape; the C3 shape has a baked variant
+        self.ve = _make_env(mdb, wl, N, rank, specialize=bool(specialize and wl["feat"] and wl.get("kind", "path") == "path"))
+        self.jit = self.ve.batch.jit_status()
         self.b = b = self.ve.batch
         b.reset()  # VectorizedEnv.reset() minus the list of 65k state dicts it would build
         gen = torch.Generator(device=dev)
@@ -329,11 +332,11 @@ class Leg:
         return ev[0].elapsed_time(ev[K]), [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
 
 
-def _secondary(mdb, torch, dev, rank, peak, name, K=40, W=5, split=1):
+def _secondary(mdb, torch, dev, rank, peak, name, K=40, W=5, split=1, specialize=True):
     """A short leg of another BASELINE.json config in the same process (its own batch, freed afterwards)."""
     wl = WORKLOADS[name]
     N = wl["envs"]
-    leg = Leg(mdb, torch, wl, N, rank, dev, 16)
+    leg = Leg(mdb, torch, wl, N, rank, dev, 16, specialize=specialize)
     if wl["T"] > 0:  # step into the episode so that packages are in flight (the headline leg does the same via its warm-up)
         for s in range(20):
             leg.one_step(leg.actions[s % 16])
@@ -363,6 +366,8 @@ def _secondary(mdb, torch, dev, rank, peak, name, K=40, W=5, split=1):
     achieved = Bytes * N / (step_ms * 1e-3) / 1e9
     res = {"workload": wl["desc"], "envs": N, "steps": K, "warmup": W + 20, "value": N / (step_ms * 1e-3), "unit": "env-steps/s",
            "robot_steps_per_s": N / (step_ms * 1e-3) * wl["R"], "ms_per_step": step_ms, "issue": issue,
+           "kernel_build": ("compiled at run time for this shape (NVRTC, MDX_CFG_JIT_SHAPE)" if leg.jit[0] == 1 else
+                            "precompiled run-time-shape variant" + (f" (run-time specialisation unavailable: {leg.jit[1]})" if leg.jit[0] < 0 else "")),
            "roofline": {"bound": "hbm" if wl["feat"] else "latency (state is L2-resident)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "bytes_per_env_step": Bytes, "kernel": _kernel_name(wl),
                         "single_launch": {"mean_launch_ms": mean_ms, "frac": single_frac}}}
@@ -424,7 +429,7 @@ def gpu_arm(args):
     N = args.envs_per_gpu or wl["envs"]
     K, W = args.steps, args.warmup
     n_act = min(K + W, 64)  # distinct pre-generated action batches, cycled
-    leg = Leg(mdb, torch, wl, N, rank, dev, n_act)
+    leg = Leg(mdb, torch, wl, N, rank, dev, n_act, specialize=(args.workload != "c3" and not args.no_specialize) or args.specialize)
     ve, b, actions, feat, out, sd_dev, kind = leg.ve, leg.b, leg.act_list, leg.feat, leg.out, leg.sd_dev, leg.kind
     one_step = leg.one_step
     launches_per_step = leg.launches_per_step
@@ -692,7 +697,7 @@ def gpu_arm(args):
         secondary = {}
         for name in ("c2", "c3k100", "c4", "c5"):
             try:
-                secondary[name] = _secondary(mdb, torch, dev, rank, peak, name, split=split)
+                secondary[name] = _secondary(mdb, torch, dev, rank, peak, name, split=split, specialize=not args.no_specialize)
             except Exception as ex:  # pragma: no cover
                 secondary[name] = {"unavailable": str(ex)[:200]}
     if world > 1:
@@ -726,7 +731,9 @@ def gpu_arm(args):
                           else "state (a few MB) is L2-resident by design: this workload is launch/latency-bound, not HBM-bound"),
                    "auto_reset": ar, "host_cores_per_rank": cores_per_rank,
                    "issue": (f"VectorizedEnv.split({split}): {split} env ranges on {split} streams, {split} launches per step" if split > 1
-                             else "one fused launch per step")},
+                             else "one fused launch per step"),
+                   "kernel_build": ("compiled at run time for this shape (NVRTC)" if leg.jit[0] == 1 else
+                                    "precompiled" + (" (shape-specialised C3 variant)" if args.workload == "c3" else " run-time-shape variant"))},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "kernel": _kernel_name(wl),
                      "bytes_per_env_step": Bytes, "step_ms": step_ms,
@@ -849,6 +856,8 @@ def main():
     ap.add_argument("--cpu-envs", type=int, default=5, help="envs per core in the CPU arm (the reference trains with 5)")
     ap.add_argument("--cpu-steps", type=int, default=600, help="steps per core in the CPU arm")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-specialize", action="store_true", help="never compile the kernel at run time for the workload's shape")
+    ap.add_argument("--specialize", action="store_true", help="also for c3 (whose shape has a baked variant)")
     ap.add_argument("--split", type=int, default=2, help="env ranges stepped on their own streams (VectorizedEnv.split); 1 = one launch per step")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short C2 / C3-K100 / C4 / C5 legs (N=1, c3 only)")
     ap.add_argument("--no-feat-host", action="store_true", help="skip the features-to-host end-to-end leg")

@@ -73,6 +73,14 @@ enum {
                                    The dict starts empty: call mdx_reset before the first step, as the trainer does.  Default (flag \
                                    off) = env truth = a tracker cleared on reset. */
 
+#define MDX_CFG_JIT_SHAPE 16 /* compile the fused step + featurise kernel AT RUN TIME (NVRTC, sm_100a) for this instance's shape --     \
+                                (H, W, R, P, T, K_o, K_p, MR, MP) and the shared-memory carve-up become compile-time constants, loops    \
+                                unroll and index arithmetic folds, as in the one shape round 1 baked in (C3) -- and let               \
+                                mdx_step_featurize launch it.  The cubin is cached on disk ($MDX_JIT_CACHE, default                   \
+                                /tmp/mdx_jit_cache).  Needs libnvrtc.so.12 and the kernel sources next to libmdx.so; if either is      \
+                                missing the instance keeps the precompiled run-time-shape kernels (see mdx_jit_status).  Same results, \
+                                bit for bit. */
+
 /* Shaping constants of compute_shaped_rewards, in this order (MAPPO/helper.py:271-279,
  * QMIX/helper.py:270-278). */
 typedef struct mdx_shaping {
@@ -147,6 +155,9 @@ int32_t mdx_version(void);
 int32_t mdx_create(const mdx_config* cfg, mdx_env** out);
 int32_t mdx_destroy(mdx_env* env);
 int32_t mdx_get_dims(const mdx_env* env, mdx_dims* out);
+/* 1: the run-time-specialised kernel (MDX_CFG_JIT_SHAPE) is loaded and used; 0: not requested; -1: requested but unavailable
+ * (msg, if not NULL, receives the reason) -- the precompiled kernels run. */
+int32_t mdx_jit_status(const mdx_env* env, char* msg, int32_t msg_bytes);
 
 /* Environment.reset / VectorizedEnv.reset(indices) (env.py:81-125, QMIX/env_vectorized.py:13-22):
  * every listed env (HOST int32 ids, NULL = all) advances to its next reset block, drawn ON THE DEVICE

@@ -15,6 +15,7 @@ MDX_CFG_BLANK = 1
 MDX_CFG_BFS_SHAPING = 2
 MDX_CFG_LAX_ROBOTS = 4
 MDX_CFG_STALE_TRACKER = 8
+MDX_CFG_JIT_SHAPE = 16
 MDX_MAX_ROBOTS = 32
 
 
@@ -73,6 +74,7 @@ SYMBOLS = {
     "mdx_create": (C.c_int32, [C.POINTER(Config), C.POINTER(_VP)]),
     "mdx_destroy": (C.c_int32, [_VP]),
     "mdx_get_dims": (C.c_int32, [_VP, C.POINTER(Dims)]),
+    "mdx_jit_status": (C.c_int32, [_VP, C.c_char_p, C.c_int32]),
     "mdx_reset": (C.c_int32, [_VP, _I32P, C.c_int32, _VP]),
     "mdx_prefetch": (C.c_int32, [_VP, C.c_int32, _VP]),
     "mdx_step": (C.c_int32, [_VP, _VP, _VP, C.c_int32, _VP, _VP, _VP, C.c_uint32, _VP]),

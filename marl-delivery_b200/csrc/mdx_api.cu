@@ -188,6 +188,7 @@ int32_t mdx_version(void) { return MDX_VERSION; }
 int32_t mdx_destroy(mdx_env* e) {
   if (!e) return MDX_OK;
   DeviceGuard g(e->device);
+  jit_release(e);
   cudaFree(e->d_blob);
   cudaFree(e->d_t);
   cudaFree(e->d_ep);
@@ -559,8 +560,18 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
     mdx_destroy(e.release());
     return MDX_E_CUDA;
   }
+  if ((cfg->flags & MDX_CFG_JIT_SHAPE) && jit_build(raw) != MDX_OK) raw->jit_log = g_err;  // the precompiled variants run (mdx_jit_status tells why)
   *out = e.release();
   return MDX_OK;
+}
+
+int32_t mdx_jit_status(const mdx_env* e, char* msg, int32_t msg_bytes) {
+  if (!e) return fail(MDX_E_INVALID, "null env");
+  if (msg && msg_bytes > 0) {
+    const std::string m = e->jit_state > 0 ? std::string("specialised kernel loaded") : e->jit_state < 0 ? e->jit_log : std::string("not requested");
+    snprintf(msg, (size_t)msg_bytes, "%s", m.c_str());
+  }
+  return e->jit_state;
 }
 
 int32_t mdx_get_dims(const mdx_env* e, mdx_dims* out) {
@@ -676,6 +687,7 @@ static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int
   kp.alt_obs6 = d_obs6;
   kp.alt_g7 = d_g7;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode == 3 && e->jit_func != nullptr) return jit_launch(e, kp, st);
   if (e->stale) return mode == 1 ? launch_env_kernel_trk_1(e, kp, st) : mode == 2 ? launch_env_kernel_trk_2(e, kp, st) : launch_env_kernel_trk_3(e, kp, st);
   if (mode == 5) return launch_env_kernel_5(e, kp, st);
   if (mode == 1) return launch_env_kernel_1(e, kp, st);

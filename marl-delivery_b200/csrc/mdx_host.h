@@ -89,6 +89,12 @@ struct mdx_env {
   uint8_t* d_status = nullptr;
   uint16_t* d_cur = nullptr;
   uint32_t* d_counters = nullptr;
+  // MDX_CFG_JIT_SHAPE: the fused kernel compiled at run time for this instance's shape (mdx_jit.cpp)
+  void* jit_module = nullptr;      // CUmodule
+  void* jit_func = nullptr;        // CUfunction
+  int jit_state = 0;               // 0 not tried, 1 loaded, -1 unavailable (the precompiled variants run)
+  int jit_blocks = 0;
+  std::string jit_log;
   bool stale = false;              // MDX_CFG_STALE_TRACKER
   uint16_t* d_trk = nullptr;       // [n][5][Pp8]
   uint8_t* d_trk_status = nullptr; // [n][Pp16]
@@ -117,6 +123,15 @@ struct mdx_env {
 
 
 namespace mdx {
+// The one shape with a BAKED specialised variant (kFix = 1 of mdx_kernels.cuh: the C3 benchmark / MAPPO trainer call site -- map1 10 x 10,
+// 5 robots, <= 56 packages, K_o = 4, K_p = 5, MR = MP = 100) incl. the shared-memory carve-up that variant hard-codes.
+inline bool baked_c3_shape(const mdx_env* e) {
+  const KParams& b = e->base;
+  return !e->no_fixed && !b.shaping_bfs && b.R == 5 && b.Pp8 == 56 && b.Pp16 == 64 && b.H_out == 10 && b.W_out == 10 && b.K_o == 4 && b.K_p == 5 &&
+         b.sel_k == 5 && b.MR == 100 && b.MP == 100 && b.vec_rows_per_flush == 5 && b.stage_b == 44 && b.off_sched == 0 && b.off_status == 448 &&
+         b.off_wlist == 512 && b.off_wkey == 848 && b.off_rinfo == 1072 && b.off_alist == 1392 && b.off_sel == 1504 && b.off_masks == 1568 &&
+         b.off_stage == 1728 && b.key_wbits == 6;
+}
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the kernel FUNCTION on a device, shared by every mdx_env of the
 // process: raise it to `bytes` if the high-water mark recorded for (function, current device) is lower.
 int ensure_dynamic_smem(const void* func, size_t bytes, int carveout);
@@ -129,6 +144,10 @@ int launch_env_kernel_trk_2(mdx_env* e, const KParams& kp, cudaStream_t st);
 int launch_env_kernel_trk_3(mdx_env* e, const KParams& kp, cudaStream_t st);
 int launch_env_kernel_5(mdx_env* e, const KParams& kp, cudaStream_t st);  // step + IDQ featurisers; MDX_E_UNSUPPORTED_SHAPE: use two launches
 constexpr int MDX_E_UNSUPPORTED_SHAPE = -100;  // internal: never crosses the C ABI
+// run-time shape specialisation (mdx_jit.cpp)
+int jit_build(mdx_env* e);
+void jit_release(mdx_env* e);
+int jit_launch(mdx_env* e, const KParams& kp, cudaStream_t st);
 // builds the all-pairs BFS tables and publishes them in the map descriptors (idempotent)
 int ensure_bfs(mdx_env* e);
 }  // namespace mdx

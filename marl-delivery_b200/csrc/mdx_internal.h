@@ -1,10 +1,22 @@
 // Internal declarations shared by the host sampler, the C-ABI glue and the kernels.
 #pragma once
+#ifdef __CUDACC_RTC__
+// run-time compilation of a shape-specialised kernel (mdx_jit.cpp): NVRTC has no host headers
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t;
+#else
 #include <cstdint>
 #include <vector>
+#endif
 
 namespace mdx {
 
+#ifndef __CUDACC_RTC__
 struct Mt19937 {
   uint32_t mt[624];
   int pos;
@@ -40,6 +52,7 @@ struct EpisodeSampler {
 void build_quotient_lut(int n, int n_out, float* out);
 int build_rank_lut(int rows, int cols, int rows_out, int cols_out, uint16_t* out);
 float np_sum_f32(const float* a, int n);
+#endif  // !__CUDACC_RTC__
 
 // ---- device-side views ------------------------------------------------------------------------
 

@@ -23,8 +23,10 @@
 // produces).  Sort keys are dense ranks of the reference's float64 keys, ties broken by the original
 // list order like Python's stable sort.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <cstdint>
+#endif
 
 #include "mdx_internal.h"
 
@@ -43,6 +45,9 @@ namespace mdx {
 #ifndef MDX_FAT_BLOCKS
 #define MDX_FAT_BLOCKS 5   // big-plane variant (kFix = 2): 96 registers.  Measured: C4 45.1 (4) / 47.9 (5) / 47.2 (6) vs 45.8 M env-steps/s
                            // for the 7-CTA build; C5 (shared memory allows 4 CTAs/SM) 13.6 / 13.7 / 13.8 vs 13.1 M
+#endif
+#ifndef MDX_JIT_BLOCKS
+#define MDX_JIT_BLOCKS 7   // run-time-compiled variant (kFix = 3): chosen by mdx_jit.cpp from the instance's shared-memory footprint
 #endif
 #ifndef MDX_FIX_THREADS
 #define MDX_FIX_THREADS 128  // CTA size of the shape-specialised variant (one warp per env)
@@ -1320,6 +1325,23 @@ __device__ __forceinline__ int tracker_update(const KParams& p, const Env& w, co
 
 template <int kFix>
 __device__ __forceinline__ void specialise(KParams& p) {
+#ifdef MDX_JIT_SHAPE
+  // kFix = 3: this translation unit is being compiled AT RUN TIME (mdx_jit.cpp, NVRTC) for the shape of one mdx_env instance; every
+  // shape parameter arrives as a macro, so loops unroll and index arithmetic folds exactly like in the baked C3 variant (kFix = 1) --
+  // for ANY (H, W, R, P, K_o, K_p, MR, MP).  The algorithms are the run-time-shape ones (kFix = 0 code paths).
+  if (kFix == 3) {
+    p.R = MDX_J_R, p.P = MDX_J_P, p.T = MDX_J_T, p.Pp8 = MDX_J_PP8, p.Pp16 = MDX_J_PP16;
+    p.H_out = MDX_J_H, p.W_out = MDX_J_W, p.HW = MDX_J_H * MDX_J_W, p.W32 = (MDX_J_H * MDX_J_W + 31) / 32;
+    p.K_o = MDX_J_KO, p.K_p = MDX_J_KP, p.sel_k = MDX_J_SELK, p.MR = MDX_J_MR, p.MP = MDX_J_MP;
+    p.D = 6 + 5 * MDX_J_KO + 5 * MDX_J_KP + 1, p.Dg = 6 * MDX_J_MR + 7 * MDX_J_MP + 1;
+    p.vec_rows_per_flush = MDX_J_RPF, p.stage_b = MDX_J_STAGEB, p.key_wbits = MDX_J_WBITS, p.nranks_max = MDX_J_NRANKS;
+    p.mul_wout = MDX_J_MUL_WOUT, p.mul_r = MDX_J_MUL_R, p.mul_ksel = MDX_J_MUL_KSEL, p.mul_plane = MDX_J_MUL_PLANE;
+    p.pair_g = 32 / MDX_J_R, p.sel_rp = MDX_J_SELRP, p.tq_len = MDX_J_TQLEN;
+    p.off_sched = MDX_J_OFF_SCHED, p.off_status = MDX_J_OFF_STATUS, p.off_wlist = MDX_J_OFF_WLIST, p.off_wkey = MDX_J_OFF_WKEY;
+    p.off_rinfo = MDX_J_OFF_RINFO, p.off_alist = MDX_J_OFF_ALIST, p.off_sel = MDX_J_OFF_SEL, p.off_masks = MDX_J_OFF_MASKS;
+    p.off_stage = MDX_J_OFF_STAGE, p.smem_per_warp = MDX_J_SPW;
+  }
+#endif
   if (kFix == 1) {
     p.R = 5;
     p.Pp8 = 56;
@@ -1362,7 +1384,7 @@ __device__ __forceinline__ void specialise(KParams& p) {
 // flags bit 3 (internal): empty the dict first (mdx_tracker_clear).
 template <int kMode, int LPE, int kS, bool kSmall, int kFix, bool kTrk = false>
 __global__ void __launch_bounds__((kFix == 1 && (kMode & 2)) ? MDX_FIX_THREADS : 128,
-                                   (kMode & 2) ? (kFix == 1 ? MDX_FIX_BLOCKS : kFix == 2 ? MDX_FAT_BLOCKS : MDX_FEAT_BLOCKS)
+                                   (kMode & 2) ? (kFix == 1 ? MDX_FIX_BLOCKS : kFix == 2 ? MDX_FAT_BLOCKS : kFix == 3 ? MDX_JIT_BLOCKS : MDX_FEAT_BLOCKS)
                                                : ((kMode & 4) && kS > 2) ? 6 : 8) mdx_env_kernel(const __grid_constant__ KParams pg) {
   KParams p = pg;
   specialise<kFix>(p);

@@ -104,10 +104,7 @@ int launch_env_kernel(mdx_env* e, const KParams& kp, cudaStream_t st) {
   const int ks = kMode == 1 ? 0 : slices(lpe);
   // the headline MAPPO shape has a fully specialised instantiation
   const KParams& b = e->base;
-  if ((kMode & 2) && lpe == 32 && ks == 1 && !e->no_fixed && !b.shaping_bfs && b.R == 5 && b.Pp8 == 56 && b.Pp16 == 64 && b.H_out == 10 && b.W_out == 10 &&
-      b.K_o == 4 && b.K_p == 5 && b.sel_k == 5 && b.MR == 100 && b.MP == 100 && b.vec_rows_per_flush == 5 && b.stage_b == 44 &&
-      b.off_sched == 0 && b.off_status == 448 && b.off_wlist == 512 && b.off_wkey == 848 && b.off_rinfo == 1072 && b.off_alist == 1392 &&
-      b.off_sel == 1504 && b.off_masks == 1568 && b.off_stage == 1728 && b.key_wbits == 6)
+  if ((kMode & 2) && lpe == 32 && ks == 1 && baked_c3_shape(e))
     return launch_variant<kMode, 32, 1, true, 1>(e, kp, st);
   if (lpe == 8) return launch_lpe<kMode, 8>(e, kp, st, ks);
   if (lpe == 16) return launch_lpe<kMode, 16>(e, kp, st, ks);

@@ -18,7 +18,7 @@ _ENV_KW = ("map_file", "max_time_steps", "n_robots", "n_packages", "move_cost", 
 class VectorizedEnv:
     def __init__(self, env_cls, num_envs, k_others=100, k_packages=100, max_robots_in_state=100,
                  max_packages_in_state=100, shaping=MAPPO_SHAPING, device=None, ring_episodes=None, first_env_index=0,
-                 bfs_shaping=False, stale_tracker_compat=False,
+                 bfs_shaping=False, stale_tracker_compat=False, specialize=None,
                  **env_kwargs):
         """`env_cls` is accepted for signature compatibility (the reference passes its Environment
         class); the environments are always slots of one CUDA batch.  Seeds follow
@@ -47,7 +47,7 @@ class VectorizedEnv:
             env_map=(gidx % len(grids)).astype(np.int32) if len(grids) > 1 else None, k_others=k_others,
             k_packages=k_packages, max_robots_in_state=max_robots_in_state,
             max_packages_in_state=max_packages_in_state, shaping=shaping, device=device,
-            bfs_shaping=bfs_shaping, stale_tracker=stale_tracker_compat)
+            bfs_shaping=bfs_shaping, stale_tracker=stale_tracker_compat, specialize=specialize)
         self.num_envs = num_envs
         self.envs = _EnvList(self.batch, [files[int(g) % len(files)] for g in gidx] if len(files) > 1 else files * 1)
 

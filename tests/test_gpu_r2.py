@@ -204,6 +204,44 @@ def test_split_host_stepper_equals_host_pipeline_results():
             assert torch.equal(x, y), s
 
 
+# ---------------------------------------------------------------------------------------------- run-time shape specialisation
+@pytest.mark.parametrize("name,R,P,T,K_o,K_p,MR,MP", [
+    ("map1.txt", 5, 50, 30, 100, 100, 100, 100),   # the K = 100 defaults of generate_vector_features
+    ("map5.txt", 10, 100, 40, 9, 5, 100, 100),     # C4-like: four-slice planes, long package list
+    ("map.txt", 3, 8, 12, 2, 3, 4, 6),             # 7x7: generic (H*W % 4 != 0) path
+    ("map5.txt", 32, 70, 20, 31, 5, 32, 64),       # full warp of robots
+    ("map3.txt", 4, 20, 25, 3, 4, 10, 20),         # QMIX sizes
+])
+def test_runtime_specialised_kernel_is_bit_identical(name, R, P, T, K_o, K_p, MR, MP, tmp_path, monkeypatch):
+    """MDX_CFG_JIT_SHAPE: the fused kernel compiled by NVRTC for the instance's shape must reproduce the precompiled run-time-shape
+    kernel bit for bit, through auto-resets, and the second instance of the same shape must come from the disk cache."""
+    monkeypatch.setenv("MDX_JIT_CACHE", str(tmp_path))
+    grid = mdb.maps.stock_map(name)
+    N = 9
+    kw = dict(base_seed=31, k_others=K_o, k_packages=K_p, max_robots_in_state=MR, max_packages_in_state=MP)
+    a_ = mdb.DeliveryBatch([grid], N, R, P, T, **kw)
+    b_ = mdb.DeliveryBatch([grid], N, R, P, T, specialize=True, **kw)
+    st, msg = b_.jit_status()
+    assert st == 1, msg
+    assert a_.jit_status()[0] == 0
+    assert len(list(tmp_path.glob("*.cubin"))) == 1
+    c_ = mdb.DeliveryBatch([grid], N, R, P, T, specialize=True, **kw)   # served from the cache
+    assert c_.jit_status()[0] == 1 and len(list(tmp_path.glob("*.cubin"))) == 1
+    for x in (a_, b_, c_):
+        x.reset()
+    rs = np.random.RandomState(6)
+    for s in range(2 * T + 3):
+        a = torch.from_numpy(rs.randint(0, 15, size=(N, R)).astype(np.uint8))
+        want = [t.clone() for t in a_.step_featurize(a, auto_reset=True)]
+        for x in (b_, c_) if s % 5 == 0 else (b_,):
+            got = x.step_featurize(a, auto_reset=True)
+            for u, v in zip(want, got):
+                assert torch.equal(u, v), s
+        if s % 5:
+            c_.step_featurize(a, auto_reset=True)
+    assert torch.equal(a_.episode_stats(), b_.episode_stats())
+
+
 # ---------------------------------------------------------------------------------------------- memory safety
 CANARY = 1024  # elements on each side
 
