@@ -103,7 +103,6 @@ int launch_env_kernel(mdx_env* e, const KParams& kp, cudaStream_t st) {
     while (lpe < 32 && slices(lpe) == 0) lpe *= 2;
   const int ks = kMode == 1 ? 0 : slices(lpe);
   // the headline MAPPO shape has a fully specialised instantiation
-  const KParams& b = e->base;
   if ((kMode & 2) && lpe == 32 && ks == 1 && baked_c3_shape(e))
     return launch_variant<kMode, 32, 1, true, 1>(e, kp, st);
   if (lpe == 8) return launch_lpe<kMode, 8>(e, kp, st, ks);
