@@ -777,8 +777,10 @@ def gpu_arm(args):
     if os.path.exists(traffic_file) and args.workload == "c3":
         try:
             tr = json.load(open(traffic_file))
-            if tr.get("envs") == N:
-                line["roofline"]["traffic"] = tr["dram_bytes_per_launch"]
+            if tr.get("envs") * split == N:  # one ncu capture of ONE launch (envs per launch as in this run) x launches per step
+                line["roofline"]["traffic"] = tr["dram_bytes_per_launch"] * split
+                line["roofline"]["traffic_note"] = (f"dram read + write bytes of one launch over {tr['envs']} envs (ncu --set full) x {split} launches "
+                                                    f"per step; algorithmic bytes per step: {Bytes * N}")
                 line["roofline"]["traffic_source"] = tr.get("source")
         except Exception:
             pass

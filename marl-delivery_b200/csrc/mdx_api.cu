@@ -381,7 +381,7 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   // the key array is only touched by the selection paths for more than 5 slots per robot on a long waiting list (P > 64);
   // with <= 5 slots those environments keep their candidates in registers (featurize_env), so C4 / C5 do not pay for it
   const bool need_wkey = e->P <= 64 || b.sel_k > 5;
-  auto carve = [&](int rpf, bool commit) {
+  auto carve = [&](int rpf, int gch, bool commit) {
     int off = 0;
     auto take = [&](int bytes) {
       const int at = off;
@@ -399,7 +399,7 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
     const int o_masks = take(4 * 10 * b.W32);
     const int o_stage = off;
     // (the fused IDQ featuriser keeps its H*W urgency plane in the stage)
-    const int stage_floats = std::max(std::max(rpf * b.D + 8, b.stage_b + 7 * std::min(e->P, b.MP) + 12), b.HW + 4);
+    const int stage_floats = std::max(std::max(rpf * b.D + 8, b.stage_b + 7 * gch + 12), b.HW + 4);
     off = round_up(off + 4 * stage_floats, 16);
     const int o_trk = off;
     if (e->stale) off = round_up(off + 10 * b.Pp8 + b.Pp16 + 2 * b.Pp8, 16);
@@ -408,6 +408,7 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
       b.off_sched = o_sched, b.off_status = o_status, b.off_wlist = o_wlist, b.off_wkey = o_wkey, b.off_rinfo = o_rinfo;
       b.off_alist = o_alist, b.off_sel = o_sel, b.off_masks = o_masks, b.off_stage = o_stage;
       b.vec_rows_per_flush = rpf;
+      b.gvec_chunk = gch;
       b.smem_per_warp = off;
     }
     return off;
@@ -418,15 +419,23 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   const char* sc = getenv("MDX_STAGE_BYTES");
   if (sc) stage_cap = std::max(1024, atoi(sc));
   while (rpf > 1 && rpf * b.D * 4 > stage_cap) --rpf;
+  // `gch` = package rows of gvec staged per flush (all min(P, MP) of them unless a smaller chunk lets one more CTA fit: C5 14.0 -> 10.6 KB
+  // per warp = 4 -> 5 CTAs/SM)
+  const int gch_full = std::max(1, std::min(e->P, b.MP));
+  int gch = gch_full;
   if (!sc) {
-    int best = rpf, best_ctas = ctas_per_sm(carve(rpf, false));
-    for (int r = rpf - 1; r >= 1; --r) {
-      const int c = ctas_per_sm(carve(r, false));
-      if (c > best_ctas) best = r, best_ctas = c;
+    int best = rpf, best_g = gch_full, best_ctas = ctas_per_sm(carve(rpf, gch_full, false));
+    for (int gc : {gch_full, 64, 48, 32, 24, 16}) {
+      if (gc > gch_full) continue;
+      for (int r = rpf; r >= 1; --r) {
+        const int c = ctas_per_sm(carve(r, gc, false));
+        if (c > best_ctas) best = r, best_g = gc, best_ctas = c;
+      }
     }
-    rpf = best;
+    rpf = best, gch = best_g;
   }
-  carve(rpf, true);
+  if (const char* gs = getenv("MDX_GVEC_CHUNK")) gch = std::max(1, std::min(gch_full, atoi(gs)));
+  carve(rpf, gch, true);
   if (b.smem_per_warp > 220 * 1024)
     return fail(MDX_E_INVALID, "per-environment working set (%d bytes) exceeds shared memory", b.smem_per_warp);
 

@@ -90,6 +90,7 @@ struct KParams {
   int32_t nranks_max;
   int32_t tq_len;
   int32_t vec_rows_per_flush;
+  int32_t gvec_chunk;    // package rows of gvec staged per flush
   uint32_t mul_plane;    // ceil(2^32 / HW)       : e / HW        for e < 2^32 / HW
   uint32_t mul_wout;     // ceil(2^32 / W_out)    : cell / W_out
   uint32_t mul_r;        // ceil(2^32 / R)        : lane / R

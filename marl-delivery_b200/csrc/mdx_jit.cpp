@@ -11,6 +11,7 @@
 #include <dlfcn.h>
 #include <nvrtc.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -117,7 +118,7 @@ void jit_source(const mdx_env* e, std::string* src, std::string* name_expr, int*
   auto def = [&](const char* k, long long v) { o << "#define MDX_J_" << k << " " << v << "\n"; };
   auto defu = [&](const char* k, uint32_t v) { o << "#define MDX_J_" << k << " " << v << "u\n"; };
   def("R", b.R), def("P", b.P), def("T", b.T), def("PP8", b.Pp8), def("PP16", b.Pp16), def("H", b.H_out), def("W", b.W_out);
-  def("KO", b.K_o), def("KP", b.K_p), def("SELK", b.sel_k), def("MR", b.MR), def("MP", b.MP), def("RPF", b.vec_rows_per_flush);
+  def("KO", b.K_o), def("KP", b.K_p), def("SELK", b.sel_k), def("MR", b.MR), def("MP", b.MP), def("RPF", b.vec_rows_per_flush), def("GCH", b.gvec_chunk);
   def("STAGEB", b.stage_b), def("WBITS", b.key_wbits), def("NRANKS", b.nranks_max), def("SELRP", b.sel_rp), def("TQLEN", b.tq_len);
   defu("MUL_WOUT", b.mul_wout), defu("MUL_R", b.mul_r), defu("MUL_KSEL", b.mul_ksel), defu("MUL_PLANE", b.mul_plane);
   def("OFF_SCHED", b.off_sched), def("OFF_STATUS", b.off_status), def("OFF_WLIST", b.off_wlist), def("OFF_WKEY", b.off_wkey);
@@ -159,59 +160,64 @@ int jit_build(mdx_env* e) {
   char key[64];
   snprintf(key, sizeof(key), "%016llx", (unsigned long long)h);
   const std::string cubin_path = cache_dir + "/" + key + ".cubin", name_path = cache_dir + "/" + key + ".name";
-  std::string cubin = slurp(cubin_path), lowered = slurp(name_path);
-  if (cubin.empty() || lowered.empty()) {
-    nvrtcProgram prog = nullptr;
-    if (a.CreateProgram(&prog, src.c_str(), "mdx_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
-      return fail(MDX_E_INVALID, "nvrtcCreateProgram failed");
-    a.AddNameExpression(prog, name.c_str());
-    const std::string inc = "-I" + dir;
-    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-fmad=false", "-lineinfo", inc.c_str()};
-    const nvrtcResult rc = a.CompileProgram(prog, 5, opts);
-    if (rc != NVRTC_SUCCESS) {
-      size_t n = 0;
-      a.GetProgramLogSize(prog, &n);
-      std::string log(n, '\0');
-      if (n) a.GetProgramLog(prog, &log[0]);
-      a.DestroyProgram(&prog);
-      e->jit_log = log;
-      return fail(MDX_E_INVALID, "run-time specialisation: NVRTC compilation failed: %.380s", log.c_str());
-    }
-    const char* low = nullptr;
-    size_t n = 0;
-    if (a.GetLoweredName(prog, name.c_str(), &low) != NVRTC_SUCCESS || a.GetCUBINSize(prog, &n) != NVRTC_SUCCESS || n == 0) {
-      a.DestroyProgram(&prog);
-      return fail(MDX_E_INVALID, "run-time specialisation: no cubin / lowered name from NVRTC");
-    }
-    lowered = low;
-    cubin.resize(n);
-    a.GetCUBIN(prog, &cubin[0]);
-    a.DestroyProgram(&prog);
-    {  // best effort: a later process (or instance) of the same shape skips the compilation
-      std::ofstream(cubin_path + ".tmp", std::ios::binary).write(cubin.data(), (std::streamsize)cubin.size());
-      std::ofstream(name_path, std::ios::binary) << lowered;
-      rename((cubin_path + ".tmp").c_str(), cubin_path.c_str());
-    }
-  }
   DeviceGuard g(e->device);
   cudaFree(nullptr);  // make sure the primary context exists and is current
-  CUmodule mod = nullptr;
-  CUfunction fn = nullptr;
-  if (a.ModuleLoadData(&mod, cubin.data()) != CUDA_SUCCESS) return fail(MDX_E_CUDA, "run-time specialisation: cuModuleLoadData failed");
-  if (a.ModuleGetFunction(&fn, mod, lowered.c_str()) != CUDA_SUCCESS) {
-    a.ModuleUnload(mod);
-    return fail(MDX_E_CUDA, "run-time specialisation: kernel %s not found in the module", lowered.c_str());
-  }
   const size_t smem = 256 + (size_t)4 * e->base.smem_per_warp;
-  if (a.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)std::max<size_t>(smem, 48 * 1024)) != CUDA_SUCCESS) {
-    a.ModuleUnload(mod);
-    return fail(MDX_E_CUDA, "run-time specialisation: shared-memory attribute refused");
+  // two attempts: a cached cubin first (if any), then -- should that one not load, e.g. a file truncated by a crash -- a fresh compilation
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    std::string cubin = attempt == 0 ? slurp(cubin_path) : std::string(), lowered = attempt == 0 ? slurp(name_path) : std::string();
+    const bool from_cache = !cubin.empty() && !lowered.empty();
+    if (!from_cache) {
+      nvrtcProgram prog = nullptr;
+      if (a.CreateProgram(&prog, src.c_str(), "mdx_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+        return fail(MDX_E_INVALID, "nvrtcCreateProgram failed");
+      a.AddNameExpression(prog, name.c_str());
+      const std::string inc = "-I" + dir;
+      const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-fmad=false", "-lineinfo", inc.c_str()};
+      const nvrtcResult rc = a.CompileProgram(prog, 5, opts);
+      if (rc != NVRTC_SUCCESS) {
+        size_t n = 0;
+        a.GetProgramLogSize(prog, &n);
+        std::string log(n, '\0');
+        if (n) a.GetProgramLog(prog, &log[0]);
+        a.DestroyProgram(&prog);
+        return fail(MDX_E_INVALID, "run-time specialisation: NVRTC compilation failed: %.380s", log.c_str());
+      }
+      const char* low = nullptr;
+      size_t n = 0;
+      if (a.GetLoweredName(prog, name.c_str(), &low) != NVRTC_SUCCESS || a.GetCUBINSize(prog, &n) != NVRTC_SUCCESS || n == 0) {
+        a.DestroyProgram(&prog);
+        return fail(MDX_E_INVALID, "run-time specialisation: no cubin / lowered name from NVRTC");
+      }
+      lowered = low;
+      cubin.resize(n);
+      a.GetCUBIN(prog, &cubin[0]);
+      a.DestroyProgram(&prog);
+      {  // best effort: a later process (or instance) of the same shape skips the compilation.  Written under a per-process name and
+         // renamed, so that ranks compiling the same shape at the same time never see (or produce) a partial file.
+        const std::string tag = "." + std::to_string((long long)getpid());
+        std::ofstream(cubin_path + tag, std::ios::binary).write(cubin.data(), (std::streamsize)cubin.size());
+        std::ofstream(name_path + tag, std::ios::binary) << lowered;
+        rename((name_path + tag).c_str(), name_path.c_str());
+        rename((cubin_path + tag).c_str(), cubin_path.c_str());
+      }
+    }
+    CUmodule mod = nullptr;
+    CUfunction fn = nullptr;
+    if (a.ModuleLoadData(&mod, cubin.data()) == CUDA_SUCCESS && a.ModuleGetFunction(&fn, mod, lowered.c_str()) == CUDA_SUCCESS &&
+        a.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)std::max<size_t>(smem, 48 * 1024)) == CUDA_SUCCESS) {
+      e->jit_module = mod;
+      e->jit_func = fn;
+      e->jit_blocks = blocks;
+      e->jit_state = 1;
+      return MDX_OK;
+    }
+    if (mod) a.ModuleUnload(mod);
+    if (!from_cache) return fail(MDX_E_CUDA, "run-time specialisation: the compiled module could not be loaded (%s)", lowered.c_str());
+    remove(cubin_path.c_str());  // a bad cache entry: compile afresh
+    remove(name_path.c_str());
   }
-  e->jit_module = mod;
-  e->jit_func = fn;
-  e->jit_blocks = blocks;
-  e->jit_state = 1;
-  return MDX_OK;
+  return fail(MDX_E_CUDA, "run-time specialisation: module load failed");
 }
 
 void jit_release(mdx_env* e) {

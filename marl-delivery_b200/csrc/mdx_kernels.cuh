@@ -74,6 +74,8 @@ struct Grp {
   __device__ __forceinline__ uint32_t rmin(uint32_t v) const { return __reduce_min_sync(mask, v); }
   template <typename T>
   __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(mask, v, src, LPE); }  // src is group-relative
+  template <typename T>
+  __device__ __forceinline__ T shfl_xor(T v, int lane_mask) const { return __shfl_xor_sync(mask, v, lane_mask, LPE); }
 };
 
 }  // namespace mdx
@@ -747,7 +749,52 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
         rowp[D - 1] = tfrac;
       }
       // other robots, stable-sorted by the float64 key rank (:115-141)
-      if (K_o > 0 && R > 1) {
+      if (kFix != 1 && LPE == 32 && K_o > 0 && G == 1) {
+        // More than 16 robots: one robot per pass, lane j holds the key of "other robot j".  Counting the smaller keys costs 32
+        // shuffles + compares per pass (20 % of C5's instructions); a bitonic network sorts the 32 keys in 15 shuffle + min/max steps
+        // instead, after which lane p holds the p-th nearest other robot (its index sits in the key's low 5 bits) and writes row p.
+        uint32_t dirmask = 0u;  // bit s: this lane keeps the MIN in compare-exchange step s
+        {
+          int st_ = 0;
+#pragma unroll
+          for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1, ++st_) dirmask |= ((((sl & j) == 0) == ((sl & k) == 0)) ? 1u : 0u) << st_;
+        }
+#pragma unroll 1
+        for (int i = i0; i < i0 + nrows; ++i) {
+          const uint32_t rci = w.rrc[i];
+          uint32_t sk = MDX_NONE32;
+          if (sl < R && sl != i) {
+            const uint32_t rcj = w.rrc[sl];
+            const int dr = (int)(rcj >> 8) - (int)(rci >> 8), dc = (int)(rcj & 255u) - (int)(rci & 255u);
+            sk = ((uint32_t)__ldg(map.rank + (dr + Hm1) * NC + (dc + Wm1)) << 5) | (uint32_t)sl;
+          }
+          {
+            int st_ = 0;
+#pragma unroll
+            for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+              for (int j = k >> 1; j > 0; j >>= 1, ++st_) {
+                const uint32_t other = g.shfl_xor(sk, j);
+                sk = ((dirmask >> st_) & 1u) ? min(sk, other) : max(sk, other);
+              }
+          }
+          const int jj = (int)(sk & 31u);
+          const float cf_j = g.shfl(cflag, jj);
+          const float otr_j = g.shfl(ot_r, jj), otc_j = g.shfl(ot_c, jj);
+          if (sk != MDX_NONE32 && sl < K_o) {
+            const uint32_t rcj = w.rrc[jj];
+            const int dr = (int)(rcj >> 8) - (int)(rci >> 8), dc = (int)(rcj & 255u) - (int)(rci & 255u);
+            float* o = chunk + (i - i0) * D + 6 + sl * 5;
+            o[0] = __ldg(qr + (dr + Hm1));
+            o[1] = __ldg(qc + (dc + Wm1));
+            o[2] = cf_j;
+            o[3] = otr_j;
+            o[4] = otc_j;
+          }
+        }
+      } else if (K_o > 0 && R > 1) {
 #pragma unroll 1
         for (int ib = i0; ib < i0 + nrows; ib += G) {
           const int i = ib + gi;
@@ -1087,8 +1134,10 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
   if (p.gvec != nullptr) {
     const int Dg = p.Dg, MR = p.MR, MP = p.MP;
     const size_t gA = (size_t)row * Dg, gB = gA + 6 * (size_t)MR;
-    const int offA = (int)(gA & 3), offB = (int)(gB & 3);
+    const int offA = (int)(gA & 3);
+    if constexpr (kFix == 1) {  // the baked C3 shape stages all its (<= 56) package rows at once: round-1 code, kept verbatim (56 registers)
     const int nA = 6 * min(R, MR), nrow = min(na, MP), nB = 7 * nrow;
+    const int offB = (int)(gB & 3);
     float* stA = w.stage;
     float* stB = w.stage + p.stage_b;
     zero_stage<LPE>(stA, nA + 8, sl);
@@ -1134,6 +1183,74 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
     g.sync();
     flush_seg<LPE>(p.gvec + gA, stA, offA, nA, 6 * MR, sl);
     flush_seg<LPE>(p.gvec + gB, stB, offB, nB, 7 * MP, sl);
+    } else {
+    const int nA = 6 * min(R, MR), nrow = min(na, MP);
+    float* stA = w.stage;
+    float* stB = w.stage + p.stage_b;
+    // package rows go out p.gvec_chunk at a time (all at once unless a smaller stage lets one more CTA fit the SM); the first chunk
+    // is staged together with the robot rows so that the usual single-chunk case leaves as one burst; the last chunk also writes
+    // the segment's zero tail
+    const int CH = p.gvec_chunk;
+    auto fill_rows = [&](int r0, int nr, int offC) {
+#pragma unroll 1
+      for (int k = r0 + sl; k < r0 + nr; k += LPE) {
+        const int j = w.alist[k];
+        const bool wait = w.status[j] == ST_WAITING;
+        const uint32_t sc = w.start[j], tc_ = w.target[j];
+        const int sr = (int)__umulhi(sc, p.mul_wout), scol = (int)sc - sr * Wo;
+        const int tr = (int)__umulhi(tc_, p.mul_wout), tcol = (int)tc_ - tr * Wo;
+        float* o = stB + offC + 7 * (k - r0);
+        if (wait) {
+          o[0] = __ldg(qr + (sr + Hm1));
+          o[1] = __ldg(qc + (scol + Wm1));
+        }
+        o[2] = __ldg(qr + (tr + Hm1));
+        o[3] = __ldg(qc + (tcol + Wm1));
+        o[4] = tnorm(p, max(0, (int)w.dl[j] - t));
+        o[5] = wait ? 0.0f : 1.0f;
+        float cn = -1.0f;
+        if (!wait) {
+          for (int ridx = 0; ridx < R; ++ridx)
+            if ((int)w.rcarry[ridx] == id_of<kTrk>(w, j)) {
+              cn = __ldg(p.cq + ridx);  // ridx / (MR - 1), or 0 when MR <= 1
+              break;
+            }
+        }
+        o[6] = cn;
+      }
+    };
+    const int offB = (int)(gB & 3), nr0 = min(CH, nrow);
+    zero_stage<LPE>(stA, nA + 8, sl);
+    zero_stage<LPE>(stB, 7 * nr0 + 8, sl);
+    g.sync();
+    if (active && sl < MR) {
+      float* o = stA + offA + sl * 6;
+      o[0] = __ldg(qr + (r + Hm1));
+      o[1] = __ldg(qc + (c + Wm1));
+      o[2] = carry != 0 ? 1.0f : 0.0f;
+      if (carrying_it) {
+        o[3] = __ldg(qr + (tr_own + Hm1));
+        o[4] = __ldg(qc + (tc_own + Wm1));
+        o[5] = tnorm(p, own_rem);
+      }
+    }
+    fill_rows(0, nr0, offB);
+    g.sync();
+    flush_seg<LPE>(p.gvec + gA, stA, offA, nA, 6 * MR, sl);
+    flush_seg<LPE>(p.gvec + gB, stB, offB, 7 * nr0, CH >= nrow ? 7 * MP : 7 * nr0, sl);
+#pragma unroll 1
+    for (int r0 = CH; r0 < nrow; r0 += CH) {
+      const int nr = min(CH, nrow - r0);
+      const size_t gC = gB + 7 * (size_t)r0;
+      const int offC = (int)(gC & 3);
+      g.sync();
+      zero_stage<LPE>(stB, 7 * nr + 8, sl);
+      g.sync();
+      fill_rows(r0, nr, offC);
+      g.sync();
+      flush_seg<LPE>(p.gvec + gC, stB, offC, 7 * nr, r0 + CH >= nrow ? 7 * (MP - r0) : 7 * nr, sl);
+    }
+    }
     if (sl == 0) __stcs(p.gvec + gA + Dg - 1, tnorm(p, t));
     g.sync();
   }
@@ -1334,7 +1451,7 @@ __device__ __forceinline__ void specialise(KParams& p) {
     p.H_out = MDX_J_H, p.W_out = MDX_J_W, p.HW = MDX_J_H * MDX_J_W, p.W32 = (MDX_J_H * MDX_J_W + 31) / 32;
     p.K_o = MDX_J_KO, p.K_p = MDX_J_KP, p.sel_k = MDX_J_SELK, p.MR = MDX_J_MR, p.MP = MDX_J_MP;
     p.D = 6 + 5 * MDX_J_KO + 5 * MDX_J_KP + 1, p.Dg = 6 * MDX_J_MR + 7 * MDX_J_MP + 1;
-    p.vec_rows_per_flush = MDX_J_RPF, p.stage_b = MDX_J_STAGEB, p.key_wbits = MDX_J_WBITS, p.nranks_max = MDX_J_NRANKS;
+    p.vec_rows_per_flush = MDX_J_RPF, p.gvec_chunk = MDX_J_GCH, p.stage_b = MDX_J_STAGEB, p.key_wbits = MDX_J_WBITS, p.nranks_max = MDX_J_NRANKS;
     p.mul_wout = MDX_J_MUL_WOUT, p.mul_r = MDX_J_MUL_R, p.mul_ksel = MDX_J_MUL_KSEL, p.mul_plane = MDX_J_MUL_PLANE;
     p.pair_g = 32 / MDX_J_R, p.sel_rp = MDX_J_SELRP, p.tq_len = MDX_J_TQLEN;
     p.off_sched = MDX_J_OFF_SCHED, p.off_status = MDX_J_OFF_STATUS, p.off_wlist = MDX_J_OFF_WLIST, p.off_wkey = MDX_J_OFF_WKEY;

@@ -242,6 +242,38 @@ def test_runtime_specialised_kernel_is_bit_identical(name, R, P, T, K_o, K_p, MR
     assert torch.equal(a_.episode_stats(), b_.episode_stats())
 
 
+@pytest.mark.parametrize("chunk", ["8", "24"])
+@pytest.mark.parametrize("name,R,P,T,K_o,K_p,MR,MP", [
+    ("map1.txt", 5, 60, 40, 4, 5, 100, 100),     # more active packages than a chunk, zero tail behind the last chunk
+    ("map5.txt", 20, 90, 30, 19, 5, 20, 37),     # MP not a multiple of the chunk; bitonic other-robot ranking (> 16 robots)
+    ("map.txt", 3, 30, 25, 2, 3, 4, 30),         # 7x7 generic path
+])
+def test_gvec_package_rows_flushed_in_chunks(chunk, name, R, P, T, K_o, K_p, MR, MP, monkeypatch):
+    """A smaller gvec stage (MDX_GVEC_CHUNK rows per flush; chosen automatically where it buys a resident CTA, e.g. C5) must not
+    change a bit of gvec -- or of anything else."""
+    grid = mdb.maps.stock_map(name)
+    N = 7
+    kw = dict(base_seed=5, k_others=K_o, k_packages=K_p, max_robots_in_state=MR, max_packages_in_state=MP, specialize=False)
+    a_ = mdb.DeliveryBatch([grid], N, R, P, T, **kw)
+    monkeypatch.setenv("MDX_GVEC_CHUNK", chunk)
+    b_ = mdb.DeliveryBatch([grid], N, R, P, T, **kw)
+    c_ = mdb.DeliveryBatch([grid], N, R, P, T, **{**kw, "specialize": True})
+    monkeypatch.delenv("MDX_GVEC_CHUNK")
+    assert c_.jit_status()[0] == 1
+    for x in (a_, b_, c_):
+        x.reset()
+    rs = np.random.RandomState(7)
+    for s in range(2 * T + 2):
+        a = rs.randint(0, 15, size=(N, R)).astype(np.uint8)
+        if s % 2:
+            a = (a % 5 + 5).astype(np.uint8)  # many pickups: in-transit rows with carrier indices
+        a = torch.from_numpy(a)
+        want = [t.clone() for t in a_.step_featurize(a, auto_reset=True)]
+        for x in (b_, c_):
+            for u, v in zip(want, x.step_featurize(a, auto_reset=True)):
+                assert torch.equal(u, v), s
+
+
 # ---------------------------------------------------------------------------------------------- memory safety
 CANARY = 1024  # elements on each side
 
