@@ -371,8 +371,21 @@ def _secondary(mdb, torch, dev, rank, peak, name, K=40, W=5, split=1, specialize
            "roofline": {"bound": "hbm" if wl["feat"] else "latency (state is L2-resident)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "bytes_per_env_step": Bytes, "kernel": _kernel_name(wl),
                         "single_launch": {"mean_launch_ms": mean_ms, "frac": single_frac}}}
-    if not wl["feat"]:  # launch-bound: also the graph-captured multi-step entry point
+    if not wl["feat"]:  # launch-bound: also the pre-bound stepper, the multi-step call and the graph-captured entry point
         try:
+            stp = leg.b.stepper(leg.out, auto_reset=True)
+            seq = [leg.act_list[s % 16] for s in range(400)]
+            for a in seq[:20]:
+                stp(a)
+            torch.cuda.synchronize()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for a in seq:
+                stp(a)
+            b1.record()
+            torch.cuda.synchronize()
+            res["stepper"] = {"ms_per_step": b0.elapsed_time(b1) / 400, "value": N / (b0.elapsed_time(b1) / 400 * 1e-3), "unit": "env-steps/s",
+                              "note": "DeliveryBatch.stepper(out): one pre-bound ctypes call per step from a Python loop"}
             S = 64
             acts = leg.actions[torch.arange(S, device=dev) % len(leg.actions)].contiguous()
             outn = leg.b.step_n(acts)  # warm

@@ -293,6 +293,40 @@ class DeliveryBatch:
         self._version += 1
         return reward, shaped, done
 
+    def stepper(self, out, feat_out=None, auto_reset: bool = True):
+        """A pre-bound `step` / `step_featurize` for hot loops over ALL envs with fixed caller-owned outputs: everything that does
+        not change from step to step (output addresses, flags, the C function, the validation of `out` / `feat_out`) is resolved
+        once; the returned callable takes the step's uint8 action tensor [n_envs, R] on this device and costs one ctypes call
+        (launch-bound batches: ~2 us less per step than step(); results are identical)."""
+        n, R = self.n_envs, self.n_robots
+        p_r, p_s, p_d = self._check_out(out, self._rsd_specs(n, ("shaped", n, torch.float32)))
+        flags = MDX_F_AUTO_RESET if auto_reset else 0
+        h, idx, raw = self._h, self._dev_index, _raw_stream
+        u8 = torch.uint8
+        if feat_out is None:
+            fn = self._L.mdx_step
+
+            def call(actions):
+                if actions.dtype is not u8 or actions.shape[0] != n or actions.get_device() != idx or not actions.is_contiguous():
+                    raise ValueError("actions must be a contiguous uint8 tensor [n_envs, n_robots] on the batch's device")
+                rc = fn(h, actions.data_ptr(), None, n, p_r, p_s, p_d, flags, raw(idx) or None)
+                if rc:
+                    _lib.check(rc)
+                self._version += 1
+        else:
+            fp = self._check_out(feat_out, self._feat_specs(n))
+            fn = self._L.mdx_step_featurize
+
+            def call(actions):
+                if actions.dtype is not u8 or actions.shape[0] != n or actions.get_device() != idx or not actions.is_contiguous():
+                    raise ValueError("actions must be a contiguous uint8 tensor [n_envs, n_robots] on the batch's device")
+                rc = fn(h, actions.data_ptr(), None, n, p_r, p_s, p_d, fp[0], fp[1], fp[2], fp[3], flags, raw(idx) or None)
+                if rc:
+                    _lib.check(rc)
+                self._version += 1
+        call.out, call.feat_out = out, feat_out  # keep the tensors (and so their addresses) alive as long as the callable
+        return call
+
     def step_n(self, actions, auto_reset: bool = True, out=None):
         """`n_steps` consecutive step() calls over all envs in ONE C call (include/mdx.h: mdx_step_n): actions uint8
         [n_steps, n_envs, R] on the GPU -> (reward f64, shaped f32, done u8), each [n_steps, n_envs].  For launch-bound

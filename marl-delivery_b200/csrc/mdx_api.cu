@@ -238,6 +238,7 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
   e->T = cfg->max_time_steps;
   e->E = 0;
   if (const char* s = getenv("MDX_WPB")) e->wpb_override = atoi(s);
+  if (const char* s = getenv("MDX_PDL")) e->pdl = atoi(s);
   if (const char* s = getenv("MDX_GENERIC")) e->force_generic = atoi(s);
   if (const char* s = getenv("MDX_LPE")) e->lpe_override = atoi(s);
   if (const char* s = getenv("MDX_NOFIX")) e->no_fixed = atoi(s);

@@ -113,6 +113,7 @@ struct mdx_env {
   uint32_t* d_greedy = nullptr;    // [n][32]  target id | carried id seen at the previous call << 16
   uint32_t* d_gfree = nullptr;     // [n][gfree_words] packages_free bits over the agent's own list
   int gfree_words = 0;
+  int pdl = 1;            // MDX_PDL: 0 never, 1 programmatic dependent launch for step-only launches (default), 2 for every mode
   int wpb_override = 0;
   int carveout = -1;      // MDX_CARVEOUT=0..100: preferred shared-memory carve-out of the env kernels (-1 = driver default)
   int no_fixed = 0;       // MDX_NOFIX=1: never use the shape-specialised instantiation

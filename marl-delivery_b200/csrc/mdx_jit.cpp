@@ -113,8 +113,13 @@ void jit_source(const mdx_env* e, std::string* src, std::string* name_expr, int*
   int blocks = (int)std::min<size_t>((ks == 4 && !small) ? 6 : 7, std::max<size_t>(1, (227 * 1024) / cta_smem));
   if (const char* s = getenv("MDX_JIT_BLOCKS")) blocks = std::max(1, std::min(9, atoi(s)));
   *blocks_out = blocks;
+  // the interleaved package selection of the baked C3 variant (R independent arg-min chains in flight, winners kept in lanes) for every
+  // shape it fits: few robots, R * slots <= 32 lanes, short package lists, all vec rows of an env staged at once
+  const bool interleave = small && b.R <= 8 && b.sel_k >= 1 && b.R * b.sel_k <= 32 && b.vec_rows_per_flush == b.R && !getenv("MDX_JIT_NO_INTERLEAVE");
+  if (interleave && ks == 1 && !getenv("MDX_JIT_BLOCKS")) blocks = (int)std::min<size_t>(9, std::max<size_t>(1, (227 * 1024) / cta_smem));  // like the baked variant: 56 registers
+  *blocks_out = blocks;
   std::ostringstream o;
-  o << "#define MDX_JIT_SHAPE 1\n#define MDX_JIT_BLOCKS " << blocks << "\n";
+  o << "#define MDX_JIT_SHAPE 1\n#define MDX_JIT_BLOCKS " << blocks << "\n#define MDX_J_INTERLEAVE " << (interleave ? 1 : 0) << "\n#define MDX_J_NR " << b.R << "\n";
   auto def = [&](const char* k, long long v) { o << "#define MDX_J_" << k << " " << v << "\n"; };
   auto defu = [&](const char* k, uint32_t v) { o << "#define MDX_J_" << k << " " << v << "u\n"; };
   def("R", b.R), def("P", b.P), def("T", b.T), def("PP8", b.Pp8), def("PP16", b.Pp16), def("H", b.H_out), def("W", b.W_out);

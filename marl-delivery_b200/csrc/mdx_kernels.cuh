@@ -828,11 +828,15 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
       //   (remaining deadline * nranks + rank of the float64 distance key) << wbits | list index;
       // the winner of round q for the ii-th robot of a pass is remembered by lane ii*Ksel+q, which then
       // writes that row.
-      if (kFix == 1 && nsel > 0) {
-        // Shape-specialised selection (5 robots, 5 slots, one pass): the rounds of all five robots run
-        // interleaved -- five independent group reductions in flight per round instead of 25 dependent ones --
-        // and a lane holds ONE key per robot while the waiting list fits the group (nw <= LPE).
-        constexpr int NR = 5;
+#ifndef MDX_J_INTERLEAVE
+#define MDX_J_INTERLEAVE 0  // run-time-compiled variant: 1 = this shape qualifies for the interleaved selection (mdx_jit.cpp decides)
+#define MDX_J_NR 5
+#endif
+      if ((kFix == 1 || (kFix == 3 && MDX_J_INTERLEAVE)) && nsel > 0) {
+        // Shape-specialised selection (baked C3: 5 robots, 5 slots; run-time-compiled: any R <= 8 robots with R * slots <= 32, P <= 64,
+        // all rows staged at once): the rounds of all robots run interleaved -- R independent group reductions in flight per round
+        // instead of R * slots dependent ones -- and a lane holds ONE key per robot while the waiting list fits the group (nw <= LPE).
+        constexpr int NR = kFix == 1 ? 5 : MDX_J_NR;
         int bi[NR];
 #pragma unroll
         for (int ii = 0; ii < NR; ++ii) {
@@ -1503,6 +1507,12 @@ template <int kMode, int LPE, int kS, bool kSmall, int kFix, bool kTrk = false>
 __global__ void __launch_bounds__((kFix == 1 && (kMode & 2)) ? MDX_FIX_THREADS : 128,
                                    (kMode & 2) ? (kFix == 1 ? MDX_FIX_BLOCKS : kFix == 2 ? MDX_FAT_BLOCKS : kFix == 3 ? MDX_JIT_BLOCKS : MDX_FEAT_BLOCKS)
                                                : ((kMode & 4) && kS > 2) ? 6 : 8) mdx_env_kernel(const __grid_constant__ KParams pg) {
+  // Programmatic dependent launch (sm_90+): when the launch carries the programmatic-stream-serialisation attribute (launch-bound
+  // step-only batches, mdx_launch.inl), this grid may be scheduled while its predecessor on the stream is still draining; it lets ITS
+  // successor do the same right away and then waits here until the predecessor's writes (the env state) are complete and visible.
+  // Without the attribute both instructions are no-ops.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   KParams p = pg;
   specialise<kFix>(p);
   extern __shared__ __align__(16) unsigned char smem_raw[];

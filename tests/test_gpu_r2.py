@@ -138,6 +138,21 @@ def test_step_n_and_rollout_graph_equal_step_by_step():
     assert torch.equal(ref.batch.episode_stats(), g.batch.episode_stats())
     with pytest.raises(ValueError):
         a.batch.step_n(acts[:, :7])
+    # the pre-bound stepper: same results as step(), fused and step-only
+    c1 = mdb.VectorizedEnv(mdb.Environment, N, **kw)
+    c2 = mdb.VectorizedEnv(mdb.Environment, N, **kw)
+    c1.batch.reset()
+    c2.batch.reset()
+    out = (torch.empty(N, dtype=torch.float64, device="cuda"), torch.empty(N, dtype=torch.float32, device="cuda"), torch.empty(N, dtype=torch.uint8, device="cuda"))
+    feat = c1.batch.alloc_features(N)
+    st1, st2 = c1.batch.stepper(out, feat_out=feat), c2.batch.stepper(out)
+    for s in range(S):
+        st1(acts[s])
+        assert all(torch.equal(x, y) for x, y in zip(out, want[s]))
+        st2(acts[s])
+        assert all(torch.equal(x, y) for x, y in zip(out, want[s]))
+    with pytest.raises(ValueError):
+        st1(acts[0].to(torch.int64))
 
 
 def test_split_rollout_on_two_streams_equals_whole_batch_steps():
@@ -210,16 +225,19 @@ def test_split_host_stepper_equals_host_pipeline_results():
     ("map5.txt", 10, 100, 40, 9, 5, 100, 100),     # C4-like: four-slice planes, long package list
     ("map.txt", 3, 8, 12, 2, 3, 4, 6),             # 7x7: generic (H*W % 4 != 0) path
     ("map5.txt", 32, 70, 20, 31, 5, 32, 64),       # full warp of robots
-    ("map3.txt", 4, 20, 25, 3, 4, 10, 20),         # QMIX sizes
+    ("map3.txt", 4, 20, 25, 3, 4, 10, 20),         # QMIX sizes: qualifies for the interleaved selection (R * slots <= 32, P <= 64)
+    ("map1.txt", 5, 50, 30, 4, 5, 100, 100),       # the C3 shape itself (normally served by the baked variant: forced here), > 32 waiting
+    ("map1.txt", 6, 64, 30, 5, 5, 6, 64),          # 6 x 5 = 30 lanes of (robot, slot) pairs, a full 64-entry list
 ])
 def test_runtime_specialised_kernel_is_bit_identical(name, R, P, T, K_o, K_p, MR, MP, tmp_path, monkeypatch):
     """MDX_CFG_JIT_SHAPE: the fused kernel compiled by NVRTC for the instance's shape must reproduce the precompiled run-time-shape
     kernel bit for bit, through auto-resets, and the second instance of the same shape must come from the disk cache."""
     monkeypatch.setenv("MDX_JIT_CACHE", str(tmp_path))
+    monkeypatch.setenv("MDX_JIT_FORCE", "1")
     grid = mdb.maps.stock_map(name)
     N = 9
     kw = dict(base_seed=31, k_others=K_o, k_packages=K_p, max_robots_in_state=MR, max_packages_in_state=MP)
-    a_ = mdb.DeliveryBatch([grid], N, R, P, T, **kw)
+    a_ = mdb.DeliveryBatch([grid], N, R, P, T, specialize=False, **kw)
     b_ = mdb.DeliveryBatch([grid], N, R, P, T, specialize=True, **kw)
     st, msg = b_.jit_status()
     assert st == 1, msg
