@@ -94,14 +94,18 @@ class VectorizedEnv:
     # ------------------------------------------------------------------ tensor fast path
     def step_tensor(self, actions, indices=None, auto_reset=False):
         """actions: uint8 [n, R] codes (a % 5 -> 'DLRSU', a // 5 -> package op).  -> reward f64, shaped f32,
-        done u8 tensors on the GPU."""
+        done u8 tensors on the GPU.  The returned tensors are buffers owned by the batch, shared by step_tensor / rollout_step and
+        OVERWRITTEN BY THE NEXT CALL: clone what must survive, or use `self.batch.step(..., out=...)` with your own tensors."""
         return self.batch.step(actions, ids=indices, auto_reset=auto_reset)
 
     def featurize(self, indices=None, out=None):
+        """-> (obs, vec, gstate, gvec) CUDA tensors; with out=None they are batch-owned buffers overwritten by the next call."""
         return self.batch.featurize(ids=indices, out=out)
 
     def rollout_step(self, actions, auto_reset=True, out=None, feat_out=None):
-        """One fused launch per MAPPO rollout iteration (MAPPO/trainer.py:172-286 without the nets)."""
+        """One fused launch per MAPPO rollout iteration (MAPPO/trainer.py:172-286 without the nets).  With `out` / `feat_out` left
+        None the results live in buffers owned by the batch that the next call overwrites (pass slices of your rollout buffers to
+        keep them, as rollout.collect_rollouts does)."""
         return self.batch.step_featurize(actions, auto_reset=auto_reset, out=out, feat_out=feat_out)
 
     def rollout_graph(self, n_steps, auto_reset=True):
