@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--parts", type=int, default=1, help="env ranges, each with its own stream for its policy evaluation + env launch")
     args = ap.parse_args()
     N, R = args.envs, 5
     vec_env = mdb.VectorizedEnv(mdb.Environment, N, map_file="map1.txt", n_robots=R, n_packages=50, max_time_steps=500, seed=42,
@@ -56,7 +57,7 @@ def main():
     actor, critic = Actor(b.vec_dim).cuda(), Critic(b.gvec_dim).cuda()
 
     def policy(obs, vec, gstate, gvec):  # -> int64 actions [N, R], log-probs [N, R], values [N]
-        logits = actor(obs.flatten(0, 1), vec.flatten(0, 1)).view(N, R, -1)
+        logits = actor(obs.flatten(0, 1), vec.flatten(0, 1)).view(obs.shape[0], R, -1)  # (a range of the envs when --parts > 1)
         dist = torch.distributions.Categorical(logits=logits)
         a = dist.sample()
         return a, dist.log_prob(a), critic(gstate, gvec)
@@ -65,7 +66,8 @@ def main():
     for it in range(args.iters):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        out = collect_rollouts(vec_env, policy, critic, args.steps, gamma=0.99, gae_lambda=0.95, buffers=buffers, fresh=buffers is None)
+        out = collect_rollouts(vec_env, policy, critic, args.steps, gamma=0.99, gae_lambda=0.95, buffers=buffers, fresh=buffers is None,
+                               parts=args.parts)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         b_obs, b_vec, b_gs, b_gv, b_act, b_lp, b_adv, b_ret, rewards, buffers = out

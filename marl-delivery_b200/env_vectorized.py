@@ -187,19 +187,42 @@ class SplitRollout:
             ev.record(st)
             cur.wait_event(ev)
 
-    def step_part(self, k, actions):
-        """Range k only.  `actions`: the FULL uint8 [N, R] action tensor (range k reads its own rows)."""
+    def _bind(self, out, feat_out):
+        """Per-range pointer arguments for another set of full-batch output tensors (e.g. step t's slices of the rollout buffers)."""
         b = self.batch
-        if not (actions.__class__ is torch.Tensor and actions.dtype is torch.uint8 and actions.is_cuda and actions.is_contiguous()
-                and tuple(actions.shape) == (b.n_envs, b.n_robots)):
-            raise ValueError("actions must be a contiguous uint8 CUDA tensor [n_envs, n_robots]")
-        lo, n, pr, ps, pd, po, pv, pg, pgv = self._args[k]
-        a = actions.data_ptr() + lo * b.n_robots
+        N, R = b.n_envs, b.n_robots
+        pr, ps, pd = b._check_out(out, b._rsd_specs(N, ("shaped", N, torch.float32)))
+        fp, frow = (None, None, None, None), (0, 0, 0, 0)
+        if self.featurize:
+            fp = b._check_out(feat_out, b._feat_specs(N))
+            HW = b.rows_out * b.cols_out
+            frow = (4 * R * 6 * HW, 4 * R * b.vec_dim, 4 * 4 * HW, 4 * b.gvec_dim)
+        off = lambda p, lo, row: None if p is None else p + lo * row  # noqa: E731
+        for lo, _ in self.ranges:
+            for p_, row in zip(fp, frow):
+                if p_ is not None and (p_ + lo * row) % 16:
+                    raise ValueError("a range would start at a feature row that is not 16-byte aligned: use a different number of parts")
+        return [(lo, hi - lo, off(pr, lo, 8), off(ps, lo, 4), off(pd, lo, 1), *(off(p_, lo, row) for p_, row in zip(fp, frow)))
+                for lo, hi in self.ranges]
+
+    def step_part(self, k, actions, out=None, feat_out=None):
+        """Range k only.  `actions`: the FULL [N, R] action tensor -- uint8 codes, or the policy's int64 samples (decoded in the
+        kernel) -- of which range k reads its own rows.  `out` / `feat_out`: other full-batch output tensors than the ones given at
+        construction (both or neither; e.g. step t's slices of the rollout buffers)."""
+        b = self.batch
+        if not (actions.__class__ is torch.Tensor and actions.is_cuda and actions.is_contiguous()
+                and tuple(actions.shape) == (b.n_envs, b.n_robots) and actions.dtype in (torch.uint8, torch.int64)):
+            raise ValueError("actions must be a contiguous uint8 or int64 CUDA tensor [n_envs, n_robots]")
+        wide = actions.dtype is torch.int64
+        args = self._args if out is None else self._bind(out, feat_out)
+        lo, n, pr, ps, pd, po, pv, pg, pgv = args[k]
+        a = actions.data_ptr() + lo * b.n_robots * (8 if wide else 1)
+        flags = self._flags | (2 if wide else 0)  # MDX_F_ACTIONS_I64
         st = self.streams[k].cuda_stream
         if self.featurize:
-            rc = b._L.mdx_step_featurize_range(b._h, a, lo, n, pr, ps, pd, po, pv, pg, pgv, self._flags, st)
+            rc = b._L.mdx_step_featurize_range(b._h, a, lo, n, pr, ps, pd, po, pv, pg, pgv, flags, st)
         else:
-            rc = b._L.mdx_step_range(b._h, a, lo, n, pr, ps, pd, self._flags, st)
+            rc = b._L.mdx_step_range(b._h, a, lo, n, pr, ps, pd, flags, st)
         if rc:
             from . import _lib
             _lib.check(rc)

@@ -306,6 +306,33 @@ def test_collect_rollouts_matches_trainer_loop():
     assert torch.equal(b_lp, (buf.vector_obs[:K, :, :, 0] - 1.0).reshape(-1))
 
 
+def test_collect_rollouts_over_two_env_ranges_equals_one_range():
+    """parts = 2: each env range has its own stream for its policy evaluation and its fused env launch.  With a deterministic
+    row-wise policy every buffer, the advantages and the returns equal the single-range rollout."""
+    N, R, K = 64, 5, 45
+    kw = dict(map_file="map1.txt", n_robots=R, n_packages=50, max_time_steps=20, seed=7, k_others=R - 1, k_packages=5)
+
+    def policy(obs, vec, gstate, gvec):  # row-wise and deterministic: a hash of each env's own features
+        h = (vec * 997.0).sum(2) + obs.flatten(2).sum(2) * 3.0
+        a = (h.abs() * 31.0).long() % 15
+        return a, vec[:, :, 1] * 0.5, gvec[:, :40].sum(1) * 0.01
+
+    def value(gstate, gvec):
+        return gvec[:, :40].sum(1) * 0.01
+
+    outs = []
+    for parts in (1, 2, 4):
+        ve = mdb.VectorizedEnv(mdb.Environment, N, **kw)
+        ve.batch.reset()
+        res = mdb.rollout.collect_rollouts(ve, policy, value, K, parts=parts)
+        torch.cuda.synchronize()
+        outs.append([t.clone() for t in res[:9]] + [res[9].dones.clone(), res[9].env_rewards.clone(), ve.batch.episode_stats().clone()])
+    for other in outs[1:]:
+        for x, y in zip(outs[0], other):
+            assert torch.equal(x, y)
+    assert int(outs[0][9].sum()) == 2 * N  # two auto-resets per env inside the rollout
+
+
 def test_host_pipeline_equals_synchronous_rollout_steps():
     """VectorizedEnv.host_pipeline(): host actions in, (shaped, done) out, copies overlapped with the kernel -- every
     step's results and the final features / episode statistics equal the step-by-step rollout_step() on the same actions,
