@@ -478,9 +478,16 @@ def gpu_arm(args):
         evs[0].record()
         if use_split:
             sp.fork()
+            lev = [[] for _ in sp.ranges]  # one event behind every launch, on the launch's own stream
             for s in range(k_steps):
-                sp.step(actions[(first + s) % n_act])
+                a = actions[(first + s) % n_act]
+                for k in range(len(sp.ranges)):
+                    sp.step_part(k, a)
+                    ev_k = torch.cuda.Event(enable_timing=True)
+                    ev_k.record(sp.streams[k])
+                    lev[k].append(ev_k)
             sp.join()
+            per = lev
         else:
             pl = [torch.cuda.Event(enable_timing=True) for _ in range(k_steps + 1)]
             pl[0].record()
@@ -503,6 +510,10 @@ def gpu_arm(args):
     barrier()
     evs, per = run_region(K, W, sp is not None)
     barrier()
+    overlapped_launch_ms = None
+    if sp is not None:  # duration of a range's launch while the other range's launch shares the GPU: consecutive launch-end events per stream
+        d = [lv[i].elapsed_time(lv[i + 1]) for lv in per for i in range(len(lv) - 1)]
+        overlapped_launch_ms = statistics.mean(d) if d else None
     ms_total = evs[0].elapsed_time(evs[2])
     collective_ms = evs[1].elapsed_time(evs[2])
     steps_ms = evs[0].elapsed_time(evs[1])
@@ -753,6 +764,10 @@ def gpu_arm(args):
                      "how": (f"algorithmic bytes of one step (all {N} envs) / device time per step; a step is {split} launches of the kernel over "
                              f"{N // split} envs each, on {split} streams, overlapping" if split > 1 else
                              "algorithmic bytes of one launch / mean launch duration (CUDA events around every launch)"),
+                     **({"overlapped_launch": {"launches_in_flight": split, "envs_per_launch": N // split, "mean_launch_ms": overlapped_launch_ms,
+                                               "note": ("CUDA events behind every launch on its own stream: one range's launch takes this long WHILE the other "
+                                                        "range's launch shares the GPU; bytes of one launch / this = each launch's own rate, x launches in flight "
+                                                        "= the step's rate above")}} if overlapped_launch_ms else {}),
                      "single_launch": {"mean_launch_ms": mean_launch_ms, "median_launch_ms": statistics.median(per_launch),
                                        "frac": single_frac,
                                        "note": "the same kernel as ONE launch over all envs, alone on the GPU (events around every launch)"}},
