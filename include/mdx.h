@@ -174,7 +174,11 @@ int32_t mdx_prefetch(mdx_env* env, int32_t episodes_ahead, void* stream);
 
 /* Environment.step / VectorizedEnv.step(actions, indices) (env.py:173-306,
  * QMIX/env_vectorized.py:24-37) fused with compute_shaped_rewards (MAPPO/helper.py:257-369).
- * d_actions [n, n_robots] u8; d_env_ids [n] int32 device ids or NULL (= all, n must be n_envs).
+ * d_actions [n, n_robots] u8; d_env_ids [n] int32 DEVICE ids or NULL (= all, n must be n_envs).  Device ids cannot be
+ * checked on the host without a synchronisation: they must be pairwise distinct (two lane groups stepping one env in the
+ * same launch would race; the reference steps a repeated index twice in sequence), and an id outside [0, n_envs) is
+ * skipped by the kernel (its output row is left unwritten) rather than dereferenced.  The Python mirror validates id
+ * lists on the host and id tensors once per tensor version.
  * Outputs (each may be NULL): d_reward [n] f64 env reward, d_shaped [n] f32 shaped team reward,
  * d_done [n] u8.  Rows follow the order of d_env_ids. */
 int32_t mdx_step(mdx_env* env, const uint8_t* d_actions, const int32_t* d_env_ids, int32_t n,
