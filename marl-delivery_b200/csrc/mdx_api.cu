@@ -570,7 +570,12 @@ int32_t mdx_create(const mdx_config* cfg, mdx_env** out) {
     mdx_destroy(e.release());
     return MDX_E_CUDA;
   }
-  if ((cfg->flags & MDX_CFG_JIT_SHAPE) && jit_build(raw) != MDX_OK) raw->jit_log = g_err;  // the precompiled variants run (mdx_jit_status tells why)
+  {
+    // MDX_JIT=1 / 0 overrides the flag for every instance of the process (e.g. the whole parity suite on run-time-compiled kernels)
+    bool want = (cfg->flags & MDX_CFG_JIT_SHAPE) != 0;
+    if (const char* s = getenv("MDX_JIT")) want = atoi(s) != 0 && !raw->stale && !b.shaping_bfs;
+    if (want && jit_build(raw) != MDX_OK) raw->jit_log = g_err;  // the precompiled variants run (mdx_jit_status tells why)
+  }
   *out = e.release();
   return MDX_OK;
 }

@@ -241,7 +241,7 @@ def test_runtime_specialised_kernel_is_bit_identical(name, R, P, T, K_o, K_p, MR
     b_ = mdb.DeliveryBatch([grid], N, R, P, T, specialize=True, **kw)
     st, msg = b_.jit_status()
     assert st == 1, msg
-    assert a_.jit_status()[0] == 0
+    assert a_.jit_status()[0] == 0 or os.environ.get("MDX_JIT")  # (MDX_JIT=1 forces the run-time-compiled kernel onto every instance)
     assert len(list(tmp_path.glob("*.cubin"))) == 1
     c_ = mdb.DeliveryBatch([grid], N, R, P, T, specialize=True, **kw)   # served from the cache
     assert c_.jit_status()[0] == 1 and len(list(tmp_path.glob("*.cubin"))) == 1
