@@ -76,7 +76,7 @@ enum {
 #define MDX_CFG_JIT_SHAPE 16 /* compile the fused step + featurise kernel AT RUN TIME (NVRTC, sm_100a) for this instance's shape --     \
                                 (H, W, R, P, T, K_o, K_p, MR, MP) and the shared-memory carve-up become compile-time constants, loops    \
                                 unroll and index arithmetic folds, as in the one shape round 1 baked in (C3) -- and let               \
-                                mdx_step_featurize launch it.  The cubin is cached on disk ($MDX_JIT_CACHE, default                   \
+                                mdx_step_featurize / mdx_featurize launch it.  The cubin is cached on disk ($MDX_JIT_CACHE, default                   \
                                 /tmp/mdx_jit_cache).  Needs libnvrtc.so.12 and the kernel sources next to libmdx.so; if either is      \
                                 missing the instance keeps the precompiled run-time-shape kernels (see mdx_jit_status).  Same results, \
                                 bit for bit. */

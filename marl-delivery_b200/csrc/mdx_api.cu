@@ -702,7 +702,7 @@ static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int
   kp.alt_obs6 = d_obs6;
   kp.alt_g7 = d_g7;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (mode == 3 && e->jit_func != nullptr) return jit_launch(e, kp, st);
+  if ((mode == 3 || (mode == 2 && internal_flags == 0)) && e->jit_func != nullptr) return jit_launch(e, kp, st, mode);
   if (e->stale) return mode == 1 ? launch_env_kernel_trk_1(e, kp, st) : mode == 2 ? launch_env_kernel_trk_2(e, kp, st) : launch_env_kernel_trk_3(e, kp, st);
   if (mode == 5) return launch_env_kernel_5(e, kp, st);
   if (mode == 1) return launch_env_kernel_1(e, kp, st);

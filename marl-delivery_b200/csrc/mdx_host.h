@@ -91,7 +91,8 @@ struct mdx_env {
   uint32_t* d_counters = nullptr;
   // MDX_CFG_JIT_SHAPE: the fused kernel compiled at run time for this instance's shape (mdx_jit.cpp)
   void* jit_module = nullptr;      // CUmodule
-  void* jit_func = nullptr;        // CUfunction
+  void* jit_func = nullptr;        // CUfunction: fused step + featurise (mode 3)
+  void* jit_func2 = nullptr;       // CUfunction: featurise only (mode 2)
   int jit_state = 0;               // 0 not tried, 1 loaded, -1 unavailable (the precompiled variants run)
   int jit_blocks = 0;
   std::string jit_log;
@@ -148,7 +149,7 @@ constexpr int MDX_E_UNSUPPORTED_SHAPE = -100;  // internal: never crosses the C 
 // run-time shape specialisation (mdx_jit.cpp)
 int jit_build(mdx_env* e);
 void jit_release(mdx_env* e);
-int jit_launch(mdx_env* e, const KParams& kp, cudaStream_t st);
+int jit_launch(mdx_env* e, const KParams& kp, cudaStream_t st, int mode);
 // builds the all-pairs BFS tables and publishes them in the map descriptors (idempotent)
 int ensure_bfs(mdx_env* e);
 }  // namespace mdx

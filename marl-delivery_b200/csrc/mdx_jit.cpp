@@ -133,7 +133,7 @@ void jit_source(const mdx_env* e, std::string* src, std::string* name_expr, int*
   *src = o.str();
   std::ostringstream n;
   n << "mdx::mdx_env_kernel<3, 32, " << ks << ", " << (small ? "true" : "false") << ", 3, false>";
-  *name_expr = n.str();
+  *name_expr = n.str();  // (the featurise-only kernel of the same shape: the same expression with mode 2, see jit_build)
 }
 
 // Compiles (or fetches from the disk cache) and loads the specialised fused kernel of `e`.  MDX_OK: e->jit_func is set.
@@ -150,6 +150,8 @@ int jit_build(mdx_env* e) {
   std::string src, name;
   int blocks = 7;
   jit_source(e, &src, &name, &blocks);
+  std::string name2 = name;  // mdx_featurize (mode 2) of the same shape
+  name2.replace(name2.find("<3,"), 3, "<2,");
   const std::string dir = source_dir();
   // cache key: the specialised source + every header it includes (by content) + the target
   uint64_t h = fnv(1469598103934665603ull, src.data(), src.size());
@@ -177,6 +179,7 @@ int jit_build(mdx_env* e) {
       if (a.CreateProgram(&prog, src.c_str(), "mdx_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
         return fail(MDX_E_INVALID, "nvrtcCreateProgram failed");
       a.AddNameExpression(prog, name.c_str());
+      a.AddNameExpression(prog, name2.c_str());
       const std::string inc = "-I" + dir;
       const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-fmad=false", "-lineinfo", inc.c_str()};
       const nvrtcResult rc = a.CompileProgram(prog, 5, opts);
@@ -188,13 +191,14 @@ int jit_build(mdx_env* e) {
         a.DestroyProgram(&prog);
         return fail(MDX_E_INVALID, "run-time specialisation: NVRTC compilation failed: %.380s", log.c_str());
       }
-      const char* low = nullptr;
+      const char *low = nullptr, *low2 = nullptr;
       size_t n = 0;
-      if (a.GetLoweredName(prog, name.c_str(), &low) != NVRTC_SUCCESS || a.GetCUBINSize(prog, &n) != NVRTC_SUCCESS || n == 0) {
+      if (a.GetLoweredName(prog, name.c_str(), &low) != NVRTC_SUCCESS || a.GetLoweredName(prog, name2.c_str(), &low2) != NVRTC_SUCCESS ||
+          a.GetCUBINSize(prog, &n) != NVRTC_SUCCESS || n == 0) {
         a.DestroyProgram(&prog);
         return fail(MDX_E_INVALID, "run-time specialisation: no cubin / lowered name from NVRTC");
       }
-      lowered = low;
+      lowered = std::string(low) + "\n" + low2;
       cubin.resize(n);
       a.GetCUBIN(prog, &cubin[0]);
       a.DestroyProgram(&prog);
@@ -208,11 +212,16 @@ int jit_build(mdx_env* e) {
       }
     }
     CUmodule mod = nullptr;
-    CUfunction fn = nullptr;
-    if (a.ModuleLoadData(&mod, cubin.data()) == CUDA_SUCCESS && a.ModuleGetFunction(&fn, mod, lowered.c_str()) == CUDA_SUCCESS &&
-        a.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)std::max<size_t>(smem, 48 * 1024)) == CUDA_SUCCESS) {
+    CUfunction fn = nullptr, fn2 = nullptr;
+    const size_t nl = lowered.find('\n');
+    const std::string l3 = lowered.substr(0, nl), l2 = nl == std::string::npos ? std::string() : lowered.substr(nl + 1);
+    if (!l2.empty() && a.ModuleLoadData(&mod, cubin.data()) == CUDA_SUCCESS && a.ModuleGetFunction(&fn, mod, l3.c_str()) == CUDA_SUCCESS &&
+        a.ModuleGetFunction(&fn2, mod, l2.c_str()) == CUDA_SUCCESS &&
+        a.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)std::max<size_t>(smem, 48 * 1024)) == CUDA_SUCCESS &&
+        a.FuncSetAttribute(fn2, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)std::max<size_t>(smem, 48 * 1024)) == CUDA_SUCCESS) {
       e->jit_module = mod;
       e->jit_func = fn;
+      e->jit_func2 = fn2;
       e->jit_blocks = blocks;
       e->jit_state = 1;
       return MDX_OK;
@@ -229,15 +238,16 @@ void jit_release(mdx_env* e) {
   if (e->jit_module && api().ok) api().ModuleUnload(static_cast<CUmodule>(e->jit_module));
   e->jit_module = nullptr;
   e->jit_func = nullptr;
+  e->jit_func2 = nullptr;
 }
 
-int jit_launch(mdx_env* e, const KParams& kp, cudaStream_t st) {
+int jit_launch(mdx_env* e, const KParams& kp, cudaStream_t st, int mode) {
   KParams q = kp;
   q.smem_per_warp = e->base.smem_per_warp;
   void* params[] = {&q};
   const size_t smem = 256 + (size_t)4 * e->base.smem_per_warp;
   const unsigned grid = (unsigned)((kp.n + 3) / 4);
-  const CUresult rc = api().LaunchKernel(static_cast<CUfunction>(e->jit_func), grid, 1, 1, 128, 1, 1, (unsigned)smem, reinterpret_cast<CUstream>(st),
+  const CUresult rc = api().LaunchKernel(static_cast<CUfunction>(mode == 2 ? e->jit_func2 : e->jit_func), grid, 1, 1, 128, 1, 1, (unsigned)smem, reinterpret_cast<CUstream>(st),
                                          params, nullptr);
   if (rc != CUDA_SUCCESS) return fail(MDX_E_CUDA, "launch of the run-time-specialised kernel failed (CUresult %d)", (int)rc);
   return MDX_OK;

@@ -257,6 +257,12 @@ def test_runtime_specialised_kernel_is_bit_identical(name, R, P, T, K_o, K_p, MR
                 assert torch.equal(u, v), s
         if s % 5:
             c_.step_featurize(a, auto_reset=True)
+        if s % 7 == 0:  # the featurise-only kernel of the shape is compiled along with the fused one
+            for u, v in zip(a_.featurize(), b_.featurize()):
+                assert torch.equal(u, v), s
+            sub = [N - 1, 0, 3]
+            for u, v in zip(a_.featurize(ids=sub), b_.featurize(ids=sub)):
+                assert torch.equal(u.clone(), v), s
     assert torch.equal(a_.episode_stats(), b_.episode_stats())
 
 
