@@ -332,7 +332,7 @@ class Leg:
         return ev[0].elapsed_time(ev[K]), [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
 
 
-def _secondary(mdb, torch, dev, rank, peak, name, K=40, W=5, split=1, specialize=True):
+def _secondary(mdb, torch, dev, rank, peak, name, K=40, W=5, split=1, specialize=True, write_peak=None):
     """A short leg of another BASELINE.json config in the same process (its own batch, freed afterwards)."""
     wl = WORKLOADS[name]
     N = wl["envs"]
@@ -370,6 +370,7 @@ def _secondary(mdb, torch, dev, rank, peak, name, K=40, W=5, split=1, specialize
                             "precompiled run-time-shape variant" + (f" (run-time specialisation unavailable: {leg.jit[1]})" if leg.jit[0] < 0 else "")),
            "roofline": {"bound": "hbm" if wl["feat"] else "latency (state is L2-resident)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "bytes_per_env_step": Bytes, "kernel": _kernel_name(wl),
+                        **({"frac_of_write_only_peak": achieved / write_peak} if (write_peak and wl["feat"]) else {}),
                         "single_launch": {"mean_launch_ms": mean_ms, "frac": single_frac}}}
     if not wl["feat"]:  # launch-bound: also the pre-bound stepper, the multi-step call and the graph-captured entry point
         try:
@@ -716,12 +717,31 @@ def gpu_arm(args):
     clocks = sampler.stop() if sampler else None
 
     peak, peak_src = _peaks()
+    # context for fractions close to (or above) 1: MEASURED_PEAKS.json holds the bandwidth of a COPY (read + write streams); this path only
+    # writes.  A write-only stream measured live on this GPU, same units:
+    write_peak = None
+    if rank == 0:
+        try:
+            wbuf = torch.empty(1 << 30, dtype=torch.float32, device=dev)  # 4 GiB
+            best = 1e9
+            for _ in range(6):
+                w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                w0.record()
+                wbuf.fill_(1.0)
+                w1.record()
+                torch.cuda.synchronize()
+                best = min(best, w0.elapsed_time(w1))
+            write_peak = wbuf.numel() * 4 / (best * 1e-3) / 1e9
+            del wbuf
+            torch.cuda.empty_cache()
+        except Exception:  # pragma: no cover
+            write_peak = None
     secondary = None
     if world == 1 and args.workload == "c3" and not args.no_secondary:
         secondary = {}
         for name in ("c2", "c3k100", "c4", "c5"):
             try:
-                secondary[name] = _secondary(mdb, torch, dev, rank, peak, name, split=split, specialize=not args.no_specialize)
+                secondary[name] = _secondary(mdb, torch, dev, rank, peak, name, split=split, specialize=not args.no_specialize, write_peak=write_peak)
             except Exception as ex:  # pragma: no cover
                 secondary[name] = {"unavailable": str(ex)[:200]}
     if world > 1:
@@ -760,6 +780,9 @@ def gpu_arm(args):
                                     "precompiled" + (" (shape-specialised C3 variant)" if args.workload == "c3" else " run-time-shape variant"))},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "kernel": _kernel_name(wl),
+                     **({"write_only_peak": {"gbs": write_peak, "frac": achieved / write_peak,
+                                             "how": "torch fill_ of a 4 GiB tensor on this GPU, best of 6, CUDA events: the path only WRITES, `peak` is a "
+                                                    "read + write copy; this is the pure-write ceiling measured live in the same process"}} if write_peak else {}),
                      "bytes_per_env_step": Bytes, "step_ms": step_ms,
                      "how": (f"algorithmic bytes of one step (all {N} envs) / device time per step; a step is {split} launches of the kernel over "
                              f"{N // split} envs each, on {split} streams, overlapping" if split > 1 else
