@@ -489,6 +489,9 @@ def gpu_arm(args):
                     lev[k].append(ev_k)
             sp.join()
             per = lev
+        elif not feat_on:  # launch-bound workloads: an event per ~9 us launch would be part of what is measured
+            for s in range(k_steps):
+                one_step(actions[(first + s) % n_act])
         else:
             pl = [torch.cuda.Event(enable_timing=True) for _ in range(k_steps + 1)]
             pl[0].record()
@@ -535,7 +538,7 @@ def gpu_arm(args):
         if world > 1:
             dist.all_reduce(t1, op=dist.ReduceOp.MAX)
         single = {"ms_total": float(t1.item())}
-    per_launch = [per[i].elapsed_time(per[i + 1]) for i in range(K)]
+    per_launch = [per[i].elapsed_time(per[i + 1]) for i in range(K)] if per is not None else [steps_ms / K] * K
 
     # ---- sustained arm: >= 3 episodes back to back, every env resets (draws its next block in the kernel) several times
     # inside the timed region; nothing is pre-sampled, the host only launches
