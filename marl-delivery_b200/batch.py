@@ -179,8 +179,10 @@ class DeliveryBatch:
         for t, (name, numel, dtype) in zip(tensors, specs):
             if t is None:
                 continue
-            if not isinstance(t, torch.Tensor) or not t.is_cuda or t.device != self.device:
-                raise ValueError(f"output '{name}' must be a CUDA tensor on {self.device}")
+            on_device = isinstance(t, torch.Tensor) and t.is_cuda and t.device == self.device
+            zero_copy = isinstance(t, torch.Tensor) and t.device.type == "cpu" and t.is_pinned()  # written by the kernel over PCIe
+            if not (on_device or zero_copy):
+                raise ValueError(f"output '{name}' must be a CUDA tensor on {self.device} (or a pinned host tensor: zero-copy)")
             if t.dtype != dtype or t.numel() != numel or not t.is_contiguous():
                 raise ValueError(f"output '{name}' must be a contiguous {dtype} tensor of {numel} elements "
                                  f"(got {t.dtype}, {t.numel()} elements, contiguous={t.is_contiguous()})")
@@ -255,6 +257,11 @@ class DeliveryBatch:
                 and actions.dim() == 2 and actions.shape[0] == n and actions.shape[1] == self.n_robots
                 and actions.get_device() == self._dev_index):
             return actions, 0  # the steady-state case: device-resident action codes of the right shape
+        if (actions.__class__ is torch.Tensor and actions.device.type == "cpu" and actions.dtype in (torch.uint8, torch.int64) and actions.is_pinned()
+                and actions.is_contiguous() and tuple(actions.shape) == (n, self.n_robots)):
+            # ZERO-COPY: pinned host memory is device-addressable (unified addressing); the kernel reads the actions over PCIe itself,
+            # no copy engine, no staging tensor (the caller must not rewrite the buffer before the launch has run)
+            return actions, (MDX_F_ACTIONS_I64 if actions.dtype is torch.int64 else 0)
         if not isinstance(actions, torch.Tensor):
             actions = torch.as_tensor(np.asarray(actions, dtype=np.uint8))
         flags = 0

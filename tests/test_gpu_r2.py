@@ -197,6 +197,31 @@ def test_split_rollout_on_two_streams_equals_whole_batch_steps():
         ve.split(2).step_part(0, acts[0][:10])
 
 
+def test_zero_copy_pinned_actions_and_outputs():
+    """Pinned host tensors may stand in for the action tensor and the small outputs: the kernel reads / writes them over PCIe itself
+    (no copy engine); results equal the device-tensor path."""
+    kw = dict(map_file="map1.txt", n_robots=5, n_packages=50, max_time_steps=15, seed=23, k_others=4, k_packages=5)
+    N, S = 200, 35
+    h_act = torch.randint(0, 15, (S, N, 5), dtype=torch.uint8, generator=torch.Generator().manual_seed(4)).pin_memory()
+    ref = mdb.VectorizedEnv(mdb.Environment, N, **kw)
+    ref.batch.reset()
+    ve = mdb.VectorizedEnv(mdb.Environment, N, **kw)
+    ve.batch.reset()
+    h_out = (torch.empty(N, dtype=torch.float64).pin_memory(), torch.empty(N, dtype=torch.float32).pin_memory(),
+             torch.empty(N, dtype=torch.uint8).pin_memory())
+    feat = ve.batch.alloc_features(N)
+    for s in range(S):
+        want = [t.clone() for t in ref.rollout_step(h_act[s].cuda())]
+        ve.rollout_step(h_act[s], out=h_out, feat_out=feat)
+        torch.cuda.current_stream().synchronize()
+        for x, y in zip(want[:3], h_out):
+            assert torch.equal(x.cpu(), y), s
+        for x, y in zip(want[3:], feat):
+            assert torch.equal(x, y), s
+    with pytest.raises(ValueError):
+        ve.rollout_step(h_act[0], out=(torch.empty(N, dtype=torch.float64), h_out[1], h_out[2]), feat_out=feat)  # pageable host memory
+
+
 def test_split_host_stepper_equals_host_pipeline_results():
     kw = dict(map_file="map1.txt", n_robots=5, n_packages=50, max_time_steps=15, seed=19, k_others=4, k_packages=5)
     N, S = 256, 40
