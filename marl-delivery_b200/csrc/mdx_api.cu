@@ -111,11 +111,17 @@ int staging(mdx_env* e, size_t bytes) {
 int check_ids(const mdx_env* e, const int32_t* h_ids, int32_t n, bool unique = false) {
   if (n < 0) return fail(MDX_E_INVALID, "negative count");
   if (unique && h_ids != nullptr && n > 1) {  // two lane groups working on one env in the same launch would race
-    std::vector<char> seen((size_t)e->n, 0);
-    for (int k = 0; k < n; ++k) {
-      if (h_ids[k] < 0 || h_ids[k] >= e->n) return fail(MDX_E_INVALID, "env id %d out of range", h_ids[k]);
-      if (seen[(size_t)h_ids[k]]) return fail(MDX_E_INVALID, "env id %d is listed twice", h_ids[k]);
-      seen[(size_t)h_ids[k]] = 1;
+    if (n <= 32) {  // (the dict drop-ins step a handful of envs per call: no allocation on that path)
+      for (int k = 1; k < n; ++k)
+        for (int j = 0; j < k; ++j)
+          if (h_ids[j] == h_ids[k]) return fail(MDX_E_INVALID, "env id %d is listed twice", h_ids[k]);
+    } else {
+      std::vector<char> seen((size_t)e->n, 0);
+      for (int k = 0; k < n; ++k) {
+        if (h_ids[k] < 0 || h_ids[k] >= e->n) return fail(MDX_E_INVALID, "env id %d out of range", h_ids[k]);
+        if (seen[(size_t)h_ids[k]]) return fail(MDX_E_INVALID, "env id %d is listed twice", h_ids[k]);
+        seen[(size_t)h_ids[k]] = 1;
+      }
     }
   }
   if (h_ids == nullptr) {
