@@ -469,8 +469,11 @@ def gpu_arm(args):
     #   split:  VectorizedEnv.split(P): P contiguous env ranges, each stepped on its own stream into the same full-batch tensors
     #           (P launches per step).  Ranges never wait for each other, so one range's launch ramp / drain overlaps another's
     #           steady state.  This is the headline mode when --split > 1.
-    split = args.split if (kind == "path" and feat_on and N % (4 * max(1, args.split)) == 0) else 1
-    sp = ve.split(split, out=out, feat_out=feat) if split > 1 else None
+    split = args.split if (((kind == "path" and feat_on) or kind == "idq") and N % (4 * max(1, args.split)) == 0) else 1
+    if split > 1 and kind == "idq":  # the IDQ trainer's iteration (f3), issued the same way
+        sp = ve.split_idq(split, out=leg.idq_out, feat_out=leg.alt_out, auto_reset=True, ops_as_int=True)
+    else:
+        sp = ve.split(split, out=out, feat_out=feat) if split > 1 else None
 
     def run_region(k_steps, first, use_split):
         """k_steps steps + the end-of-rollout collective between two events on the current stream -> (ms total, ms collective, per-launch list or None)"""
@@ -529,7 +532,7 @@ def gpu_arm(args):
     t0_min, t0_max = int(t_h.min()), int(t_h.max())
     waves_in_window = int(((t_h + K) >= T).sum()) if T > 0 else 0
     # the other mode, timed the same way (reported next to the headline; for split runs this is the kernel's own launch duration)
-    single = None
+    single, single_steps_ms = None, steps_ms
     if sp is not None:
         barrier()
         evs1, per = run_region(K, W + K, False)
@@ -538,7 +541,8 @@ def gpu_arm(args):
         if world > 1:
             dist.all_reduce(t1, op=dist.ReduceOp.MAX)
         single = {"ms_total": float(t1.item())}
-    per_launch = [per[i].elapsed_time(per[i + 1]) for i in range(K)] if per is not None else [steps_ms / K] * K
+        single_steps_ms = evs1[0].elapsed_time(evs1[1])
+    per_launch = [per[i].elapsed_time(per[i + 1]) for i in range(K)] if per is not None else [single_steps_ms / K] * K
 
     # ---- sustained arm: >= 3 episodes back to back, every env resets (draws its next block in the kernel) several times
     # inside the timed region; nothing is pre-sampled, the host only launches
@@ -660,7 +664,7 @@ def gpu_arm(args):
     # ---- end to end with the dependency a trainer has, range by range (VectorizedEnv.split_host): range k's next actions are
     # submitted only after range k's results of the previous step were read on the host; the other range's kernel runs meanwhile
     split_e2e_ms = None
-    if sp is not None:
+    if sp is not None and kind == "path":
         hs = ve.split_host(split, feat_out=feat)
         acc = 0.0
         for s in range(3):
@@ -777,7 +781,7 @@ def gpu_arm(args):
                    "l2": (f"outputs are {Bytes * N / 1e6:.0f} MB per step per GPU, larger than the 126 MB L2 (no flush needed)" if feat_on
                           else "state (a few MB) is L2-resident by design: this workload is launch/latency-bound, not HBM-bound"),
                    "auto_reset": ar, "host_cores_per_rank": cores_per_rank,
-                   "issue": (f"VectorizedEnv.split({split}): {split} env ranges on {split} streams, {split} launches per step" if split > 1
+                   "issue": (f"VectorizedEnv.{'split_idq' if kind == 'idq' else 'split'}({split}): {split} env ranges on {split} streams, {split} launches per step" if split > 1
                              else "one fused launch per step"),
                    "kernel_build": ("compiled at run time for this shape (NVRTC)" if leg.jit[0] == 1 else
                                     "precompiled" + (" (shape-specialised C3 variant)" if args.workload == "c3" else " run-time-shape variant"))},

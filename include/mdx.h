@@ -316,6 +316,13 @@ int32_t mdx_step_idq_featurize(mdx_env* env, const uint8_t* d_actions, const int
                                double* d_agent_rewards, uint8_t* d_done, float* d_obs6, float* d_gstate7, int32_t ops_as_int,
                                uint32_t flags, void* stream);
 
+/* mdx_step_idq_featurize for the CONTIGUOUS env range [first_env, first_env + n) (pointers address row 0 of the range; see
+ * mdx_step_featurize_range): several ranges of one instance may be in flight on different streams.  Fused kernel only (maps whose
+ * planes are whole float4s). */
+int32_t mdx_step_idq_featurize_range(mdx_env* env, const uint8_t* d_actions, int32_t first_env, int32_t n, double* d_reward,
+                                     double* d_agent_rewards, uint8_t* d_done, float* d_obs6, float* d_gstate7, int32_t ops_as_int,
+                                     uint32_t flags, void* stream);
+
 /* IDQ reward_shaping on caller-supplied "current" robots against the stored state as "previous" (the per-call
  * drop-in of IDQ/networks.py:228-349; same inputs as mdx_shaped_reward) -> d_out [n_envs, n_robots] f64. */
 int32_t mdx_reward_shaping_idq(mdx_env* env, const uint32_t* d_cur_robots, const int32_t* d_cur_t, const uint8_t* d_actions,

@@ -101,6 +101,7 @@ SYMBOLS = {
     "mdx_featurize_alt": (C.c_int32, [_VP, _VP, C.c_int32, _VP, _VP, _VP]),
     "mdx_step_idq": (C.c_int32, [_VP, _VP, _VP, C.c_int32, _VP, _VP, _VP, C.c_int32, C.c_uint32, _VP]),
     "mdx_step_idq_featurize": (C.c_int32, [_VP, _VP, _VP, C.c_int32, _VP, _VP, _VP, _VP, _VP, C.c_int32, C.c_uint32, _VP]),
+    "mdx_step_idq_featurize_range": (C.c_int32, [_VP, _VP, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, _VP, C.c_int32, C.c_uint32, _VP]),
     "mdx_reward_shaping_idq": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int32, _VP, _VP]),
     "mdx_gae": (C.c_int32, [_VP, _VP, _VP, _VP, C.c_int32, C.c_int32, C.c_double, C.c_double, _VP, _VP, _VP]),
     "mdx_checkpoint_bytes": (C.c_int64, [_VP]),

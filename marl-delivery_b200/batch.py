@@ -474,10 +474,23 @@ class DeliveryBatch:
         self._version += 1
         return reward, agent, done
 
-    def step_idq_featurize(self, actions, ids=None, auto_reset: bool = False, ops_as_int: bool = False, out=None, feat_out=None):
+    def step_idq_featurize(self, actions, ids=None, auto_reset: bool = False, ops_as_int: bool = False, out=None, feat_out=None,
+                           env_range=None, stream=None):
         """One IDQ trainer iteration in ONE launch (IDQ/trainer.py:276-300): step_idq, then featurize_alt of the state after
-        the step (and after any auto-reset) -> (reward, agent rewards, done, obs6, gstate7)."""
-        d_ids, _, n = self._ids(ids)
+        the step (and after any auto-reset) -> (reward, agent rewards, done, obs6, gstate7).
+
+        `env_range=(first_env, n)`: the contiguous env range only -- `actions`, `out` and `feat_out` are that range's rows (e.g.
+        slices of full-batch tensors) -- launched on `stream` (a torch.cuda.Stream; default: the current one), so that several
+        ranges of one instance can be in flight at once (see VectorizedEnv.split for the MAPPO path)."""
+        if env_range is not None:
+            if ids is not None:
+                raise ValueError("give ids or env_range, not both")
+            lo, n = int(env_range[0]), int(env_range[1])
+            if lo < 0 or n < 1 or lo + n > self.n_envs:
+                raise ValueError("env_range outside [0, n_envs)")
+            d_ids = None
+        else:
+            d_ids, _, n = self._ids(ids)
         actions, aflags = self._check_actions(actions, n)
         if out is None:
             out = (self._buf("reward", (n,), torch.float64), self._buf("agent_rewards", (n, self.n_robots), torch.float64),
@@ -490,9 +503,14 @@ class DeliveryBatch:
             feat_out = (self._buf("obs6", (n, R, 6, H, W), torch.float32), self._buf("gstate7", (n, 7, H, W), torch.float32))
         else:
             self._check_out(feat_out, self._alt_specs(n))
-        _lib.check(self._L.mdx_step_idq_featurize(self._h, _ptr(actions), _ptr(d_ids), n, _ptr(reward), _ptr(agent), _ptr(done),
-                                                  _ptr(feat_out[0]), _ptr(feat_out[1]), 1 if ops_as_int else 0,
-                                                  (MDX_F_AUTO_RESET if auto_reset else 0) | aflags, self._stream()))
+        flags = (MDX_F_AUTO_RESET if auto_reset else 0) | aflags
+        st = self._stream() if stream is None else stream.cuda_stream
+        if env_range is not None:
+            _lib.check(self._L.mdx_step_idq_featurize_range(self._h, _ptr(actions), lo, n, _ptr(reward), _ptr(agent), _ptr(done),
+                                                            _ptr(feat_out[0]), _ptr(feat_out[1]), 1 if ops_as_int else 0, flags, st))
+        else:
+            _lib.check(self._L.mdx_step_idq_featurize(self._h, _ptr(actions), _ptr(d_ids), n, _ptr(reward), _ptr(agent), _ptr(done),
+                                                      _ptr(feat_out[0]), _ptr(feat_out[1]), 1 if ops_as_int else 0, flags, st))
         self._version += 1
         return reward, agent, done, feat_out[0], feat_out[1]
 

@@ -711,6 +711,7 @@ static int step_common(mdx_env* e, int mode, const uint8_t* d_actions, const int
   kp.row_words = e->row_words, kp.row_off_robots = e->off_robots, kp.row_off_sched = e->off_sched, kp.row_off_status = e->off_status;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if ((mode == 3 || (mode == 2 && internal_flags == 0)) && e->jit_func != nullptr) return jit_launch(e, kp, st, mode);
+  if (mode == 5 && e->jit_func5 != nullptr) return jit_launch(e, kp, st, 5);
   if (e->stale) return mode == 1 ? launch_env_kernel_trk_1(e, kp, st) : mode == 2 ? launch_env_kernel_trk_2(e, kp, st) : launch_env_kernel_trk_3(e, kp, st);
   if (mode == 5) return launch_env_kernel_5(e, kp, st);
   if (mode == 1) return launch_env_kernel_1(e, kp, st);
@@ -759,6 +760,19 @@ int32_t mdx_step_idq_featurize(mdx_env* e, const uint8_t* d_actions, const int32
   rc = mdx_step_idq(e, d_actions, d_env_ids, n, d_reward, d_agent_rewards, d_done, ops_as_int, flags, stream);
   if (rc != MDX_OK) return rc;
   return mdx_featurize_alt(e, d_env_ids, n, d_obs6, d_gstate7, stream);
+}
+
+int32_t mdx_step_idq_featurize_range(mdx_env* e, const uint8_t* d_actions, int32_t first_env, int32_t n, double* d_reward,
+                                     double* d_agent_rewards, uint8_t* d_done, float* d_obs6, float* d_gstate7, int32_t ops_as_int, uint32_t flags,
+                                     void* stream) {
+  if (!d_agent_rewards) return fail(MDX_E_INVALID, "agent reward output is required");
+  if (first_env < 0) return fail(MDX_E_INVALID, "negative first env");
+  int rc;
+  if ((rc = check_ptr16(d_obs6, "obs6")) || (rc = check_ptr16(d_gstate7, "gstate7"))) return rc;
+  rc = step_common(e, 5, d_actions, nullptr, n, d_reward, nullptr, d_done, nullptr, nullptr, nullptr, nullptr, flags, stream, d_agent_rewards,
+                   ops_as_int ? 1 : 0, d_obs6, d_gstate7, 0, first_env);
+  if (rc == MDX_E_UNSUPPORTED_SHAPE) return fail(MDX_E_INVALID, "the fused IDQ iteration needs planes of whole float4s (H*W %% 4 == 0, <= 512 cells)");
+  return rc;
 }
 
 int32_t mdx_featurize(mdx_env* e, const int32_t* d_env_ids, int32_t n, float* d_obs, float* d_vec, float* d_gstate, float* d_gvec,

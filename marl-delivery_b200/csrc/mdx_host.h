@@ -93,6 +93,7 @@ struct mdx_env {
   void* jit_module = nullptr;      // CUmodule
   void* jit_func = nullptr;        // CUfunction: fused step + featurise (mode 3)
   void* jit_func2 = nullptr;       // CUfunction: featurise only (mode 2)
+  void* jit_func5 = nullptr;       // CUfunction: fused IDQ iteration (mode 5; plane-sliced maps only)
   int jit_state = 0;               // 0 not tried, 1 loaded, -1 unavailable (the precompiled variants run)
   int jit_blocks = 0;
   std::string jit_log;

@@ -150,8 +150,10 @@ int jit_build(mdx_env* e) {
   std::string src, name;
   int blocks = 7;
   jit_source(e, &src, &name, &blocks);
-  std::string name2 = name;  // mdx_featurize (mode 2) of the same shape
+  std::string name2 = name, name5 = name;  // mdx_featurize (mode 2) and the fused IDQ iteration (mode 5) of the same shape
   name2.replace(name2.find("<3,"), 3, "<2,");
+  name5.replace(name5.find("<3,"), 3, "<5,");
+  const bool with5 = name.find("<3, 32, 0,") == std::string::npos;  // the fused IDQ kernel exists for plane-sliced maps only
   const std::string dir = source_dir();
   // cache key: the specialised source + every header it includes (by content) + the target
   uint64_t h = fnv(1469598103934665603ull, src.data(), src.size());
@@ -161,6 +163,7 @@ int jit_build(mdx_env* e) {
     h = fnv(h, body.data(), body.size());
   }
   h = fnv(h, name.data(), name.size());
+  h = fnv(h, "v3", 2);  // (layout of the cached .name file: three lowered names)
   const char* cdir = getenv("MDX_JIT_CACHE");
   const std::string cache_dir = cdir ? cdir : "/tmp/mdx_jit_cache";
   mkdir(cache_dir.c_str(), 0777);
@@ -180,6 +183,7 @@ int jit_build(mdx_env* e) {
         return fail(MDX_E_INVALID, "nvrtcCreateProgram failed");
       a.AddNameExpression(prog, name.c_str());
       a.AddNameExpression(prog, name2.c_str());
+      if (with5) a.AddNameExpression(prog, name5.c_str());
       const std::string inc = "-I" + dir;
       const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-fmad=false", "-lineinfo", inc.c_str()};
       const nvrtcResult rc = a.CompileProgram(prog, 5, opts);
@@ -198,7 +202,11 @@ int jit_build(mdx_env* e) {
         a.DestroyProgram(&prog);
         return fail(MDX_E_INVALID, "run-time specialisation: no cubin / lowered name from NVRTC");
       }
-      lowered = std::string(low) + "\n" + low2;
+      lowered = std::string(low) + "\n" + low2 + "\n";
+      if (with5) {
+        const char* low5 = nullptr;
+        if (a.GetLoweredName(prog, name5.c_str(), &low5) == NVRTC_SUCCESS && low5) lowered += low5;
+      }
       cubin.resize(n);
       a.GetCUBIN(prog, &cubin[0]);
       a.DestroyProgram(&prog);
@@ -213,12 +221,22 @@ int jit_build(mdx_env* e) {
     }
     CUmodule mod = nullptr;
     CUfunction fn = nullptr, fn2 = nullptr;
-    const size_t nl = lowered.find('\n');
-    const std::string l3 = lowered.substr(0, nl), l2 = nl == std::string::npos ? std::string() : lowered.substr(nl + 1);
+    std::vector<std::string> lows;
+    {
+      std::stringstream ls(lowered);
+      std::string ln;
+      while (std::getline(ls, ln, '\n')) lows.push_back(ln);
+    }
+    const std::string l3 = lows.size() > 0 ? lows[0] : std::string(), l2 = lows.size() > 1 ? lows[1] : std::string(),
+                      l5 = lows.size() > 2 ? lows[2] : std::string();
+    CUfunction fn5 = nullptr;
+    const int smem_attr = (int)std::max<size_t>(smem, 48 * 1024);
     if (!l2.empty() && a.ModuleLoadData(&mod, cubin.data()) == CUDA_SUCCESS && a.ModuleGetFunction(&fn, mod, l3.c_str()) == CUDA_SUCCESS &&
-        a.ModuleGetFunction(&fn2, mod, l2.c_str()) == CUDA_SUCCESS &&
-        a.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)std::max<size_t>(smem, 48 * 1024)) == CUDA_SUCCESS &&
-        a.FuncSetAttribute(fn2, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)std::max<size_t>(smem, 48 * 1024)) == CUDA_SUCCESS) {
+        a.ModuleGetFunction(&fn2, mod, l2.c_str()) == CUDA_SUCCESS && a.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem_attr) == CUDA_SUCCESS &&
+        a.FuncSetAttribute(fn2, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem_attr) == CUDA_SUCCESS &&
+        (!with5 || (!l5.empty() && a.ModuleGetFunction(&fn5, mod, l5.c_str()) == CUDA_SUCCESS &&
+                    a.FuncSetAttribute(fn5, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem_attr) == CUDA_SUCCESS))) {
+      e->jit_func5 = fn5;
       e->jit_module = mod;
       e->jit_func = fn;
       e->jit_func2 = fn2;
@@ -239,6 +257,7 @@ void jit_release(mdx_env* e) {
   e->jit_module = nullptr;
   e->jit_func = nullptr;
   e->jit_func2 = nullptr;
+  e->jit_func5 = nullptr;
 }
 
 int jit_launch(mdx_env* e, const KParams& kp, cudaStream_t st, int mode) {
@@ -247,7 +266,7 @@ int jit_launch(mdx_env* e, const KParams& kp, cudaStream_t st, int mode) {
   void* params[] = {&q};
   const size_t smem = 256 + (size_t)4 * e->base.smem_per_warp;
   const unsigned grid = (unsigned)((kp.n + 3) / 4);
-  const CUresult rc = api().LaunchKernel(static_cast<CUfunction>(mode == 2 ? e->jit_func2 : e->jit_func), grid, 1, 1, 128, 1, 1, (unsigned)smem, reinterpret_cast<CUstream>(st),
+  const CUresult rc = api().LaunchKernel(static_cast<CUfunction>(mode == 2 ? e->jit_func2 : mode == 5 ? e->jit_func5 : e->jit_func), grid, 1, 1, 128, 1, 1, (unsigned)smem, reinterpret_cast<CUstream>(st),
                                          params, nullptr);
   if (rc != CUDA_SUCCESS) return fail(MDX_E_CUDA, "launch of the run-time-specialised kernel failed (CUresult %d)", (int)rc);
   return MDX_OK;

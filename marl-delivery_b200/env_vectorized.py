@@ -118,6 +118,11 @@ class VectorizedEnv:
         """The batch as `parts` contiguous env ranges, each stepped on its own CUDA stream; see SplitRollout."""
         return SplitRollout(self, parts, out=out, feat_out=feat_out, auto_reset=auto_reset, featurize=featurize)
 
+    def split_idq(self, parts=2, out=None, feat_out=None, auto_reset=True, ops_as_int=False):
+        """`split()` for the IDQ trainer's iteration (IDQ/trainer.py:276-300: step, per-agent reward_shaping, convert_state of every
+        agent, 7-channel global tensor) -- one fused launch per env range, each range on its own stream; see SplitIdq."""
+        return SplitIdq(self, parts, out=out, feat_out=feat_out, auto_reset=auto_reset, ops_as_int=ops_as_int)
+
     def split_host(self, parts=2, feat_out=None, auto_reset=True):
         """`split()` for callers whose actions and results live in HOST memory; see SplitHostStepper."""
         return SplitHostStepper(self, parts, feat_out=feat_out, auto_reset=auto_reset)
@@ -232,6 +237,58 @@ class SplitRollout:
         for k in range(len(self.ranges)):
             self.step_part(k, actions)
         return self.out, self.feat
+
+
+class SplitIdq(SplitRollout):
+    """SplitRollout for `EnvBatch.step_idq_featurize`: `out` = (reward f64 [N], agent rewards f64 [N, R], done u8 [N]), `feat` =
+    (obs6 f32 [N, R, 6, H, W], gstate7 f32 [N, 7, H, W]); fork / step / step_part / join as in SplitRollout.  Only maps whose
+    planes are whole float4s have the fused kernel (the others are refused at the first step).  Results are identical to the
+    whole-batch call (tests/test_gpu_alt.py)."""
+
+    def __init__(self, ve, parts=2, out=None, feat_out=None, auto_reset=True, ops_as_int=False):
+        b = ve.batch
+        self.batch, self.auto_reset, self.featurize = b, auto_reset, True
+        N, R, dev = b.n_envs, b.n_robots, b.device
+        if not 1 <= parts <= N:
+            raise ValueError("parts must be in [1, n_envs]")
+        bounds = [N * i // parts for i in range(parts + 1)]
+        self.ranges = [(lo, hi) for lo, hi in zip(bounds[:-1], bounds[1:]) if hi > lo]
+        self.streams = [torch.cuda.Stream(dev) for _ in self.ranges]
+        H, W = b.rows_out, b.cols_out
+        self.out = out if out is not None else (torch.empty(N, dtype=torch.float64, device=dev), torch.empty((N, R), dtype=torch.float64, device=dev),
+                                                torch.empty(N, dtype=torch.uint8, device=dev))
+        self.feat = feat_out if feat_out is not None else (torch.empty((N, R, 6, H, W), dtype=torch.float32, device=dev),
+                                                           torch.empty((N, 7, H, W), dtype=torch.float32, device=dev))
+        self._args = self._bind(self.out, self.feat)
+        self._ev = [torch.cuda.Event() for _ in self.ranges]
+        self._fork_ev = torch.cuda.Event()
+        self._flags = 1 if auto_reset else 0
+        self._ops = 1 if ops_as_int else 0
+
+    def _bind(self, out, feat_out):
+        b = self.batch
+        N, R, HW = b.n_envs, b.n_robots, b.rows_out * b.cols_out
+        pr, pa, pd = b._check_out(out, b._rsd_specs(N, ("agent_rewards", N * R, torch.float64)))
+        po, pg = b._check_out(feat_out, b._alt_specs(N))
+        for lo, _ in self.ranges:
+            if (po + lo * 4 * R * 6 * HW) % 16 or (pg + lo * 4 * 7 * HW) % 16:
+                raise ValueError("a range would start at a feature row that is not 16-byte aligned: use a different number of parts")
+        return [(lo, hi - lo, pr + lo * 8, pa + lo * 8 * R, pd + lo, po + lo * 4 * R * 6 * HW, pg + lo * 4 * 7 * HW) for lo, hi in self.ranges]
+
+    def step_part(self, k, actions, out=None, feat_out=None):
+        b = self.batch
+        if not (actions.__class__ is torch.Tensor and actions.is_cuda and actions.is_contiguous()
+                and tuple(actions.shape) == (b.n_envs, b.n_robots) and actions.dtype in (torch.uint8, torch.int64)):
+            raise ValueError("actions must be a contiguous uint8 or int64 CUDA tensor [n_envs, n_robots]")
+        wide = actions.dtype is torch.int64
+        lo, n, pr, pa, pd, po, pg = (self._args if out is None else self._bind(out, feat_out))[k]
+        a = actions.data_ptr() + lo * b.n_robots * (8 if wide else 1)
+        rc = b._L.mdx_step_idq_featurize_range(b._h, a, lo, n, pr, pa, pd, po, pg, self._ops, self._flags | (2 if wide else 0),
+                                               self.streams[k].cuda_stream)
+        if rc:
+            from . import _lib
+            _lib.check(rc)
+        b._version += 1
 
 
 class SplitHostStepper:

@@ -127,6 +127,46 @@ def test_idq_fused_iteration_equals_two_launches(maps, R, P, T, unfused, monkeyp
     assert torch.equal(a_.state_dict(), b_.state_dict())
 
 
+@pytest.mark.parametrize("maps,R,P,T,spec", [(["map1.txt"], 5, 50, 40, False), (["map1.txt"], 7, 30, 25, True), (["map5.txt"], 32, 200, 45, True),
+                                             (["map1.txt", "map3.txt", "map5.txt"], 9, 80, 35, True), (["map.txt"], 6, 20, 30, False)])
+def test_idq_fused_iteration_by_env_ranges_and_run_time_specialised(maps, R, P, T, spec):
+    """mdx_step_idq_featurize_range: three contiguous env ranges of one instance, each on its own stream and writing its rows of the
+    full-batch tensors, against the whole-batch launch of a twin; with specialize=True the fused IDQ kernel is the one compiled at
+    run time for the shape (mdx_jit.cpp: mode 5).  map.txt has no fused kernel: the range entry point must refuse it."""
+    N = 44
+    kw = dict(map_file=maps if len(maps) > 1 else maps[0], n_robots=R, n_packages=P, max_time_steps=T, seed=31)
+    a_ = mdb.VectorizedEnv(mdb.Environment, N, specialize=spec, **kw).batch
+    b_ = mdb.VectorizedEnv(mdb.Environment, N, specialize=False, **kw).batch
+    if spec:
+        assert a_.jit_status()[0] == 1
+    for x in (a_, b_):
+        x.reset()
+    dev, H, W = a_.device, a_.rows_out, a_.cols_out
+    out = (torch.empty(N, dtype=torch.float64, device=dev), torch.empty((N, R), dtype=torch.float64, device=dev), torch.empty(N, dtype=torch.uint8, device=dev))
+    feat = (torch.empty((N, R, 6, H, W), dtype=torch.float32, device=dev), torch.empty((N, 7, H, W), dtype=torch.float32, device=dev))
+    ranges = [(0, 12), (12, 4), (16, 28)]
+    streams = [torch.cuda.Stream(dev) for _ in ranges]
+    rs = np.random.RandomState(5)
+    if maps == ["map.txt"]:
+        act = torch.zeros((N, R), dtype=torch.uint8, device=dev)
+        with pytest.raises(ValueError):
+            a_.step_idq_featurize(act[:12], env_range=(0, 12), out=tuple(t[:12] for t in out), feat_out=tuple(t[:12] for t in feat))
+        return
+    for s in range(2 * T + 5):
+        act = torch.from_numpy(rs.randint(0, 15, size=(N, R)).astype(np.uint8)).to(dev)
+        torch.cuda.synchronize()
+        for (lo, n), st in zip(ranges, streams):
+            a_.step_idq_featurize(act[lo:lo + n], auto_reset=True, ops_as_int=bool(s & 1), out=tuple(t[lo:lo + n] for t in out),
+                                  feat_out=tuple(t[lo:lo + n] for t in feat), env_range=(lo, n), stream=st)
+        torch.cuda.synchronize()
+        r2, g2, d2, o2, t2 = b_.step_idq_featurize(act, auto_reset=True, ops_as_int=bool(s & 1))
+        assert torch.equal(out[0], r2) and torch.equal(out[1], g2) and torch.equal(out[2], d2), s
+        assert torch.equal(feat[0], o2) and torch.equal(feat[1], t2), s
+    assert torch.equal(a_.episode_stats(), b_.episode_stats())
+    with pytest.raises(ValueError):
+        a_.step_idq_featurize(act[:4], env_range=(N - 2, 4), out=tuple(t[:4] for t in out), feat_out=tuple(t[:4] for t in feat))
+
+
 def _tracker_of(env):
     return {p.package_id: {"id": p.package_id, "start_pos": p.start, "target_pos": p.target, "start_time": p.start_time,
                            "deadline": p.deadline, "status": p.status}
