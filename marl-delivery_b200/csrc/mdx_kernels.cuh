@@ -761,25 +761,15 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
 #pragma unroll
             for (int j = k >> 1; j > 0; j >>= 1, ++st_) dirmask |= ((((sl & j) == 0) == ((sl & k) == 0)) ? 1u : 0u) << st_;
         }
-#pragma unroll 1
-        for (int i = i0; i < i0 + nrows; ++i) {
-          const uint32_t rci = w.rrc[i];
-          uint32_t sk = MDX_NONE32;
-          if (sl < R && sl != i) {
-            const uint32_t rcj = w.rrc[sl];
-            const int dr = (int)(rcj >> 8) - (int)(rci >> 8), dc = (int)(rcj & 255u) - (int)(rci & 255u);
-            sk = ((uint32_t)__ldg(map.rank + (dr + Hm1) * NC + (dc + Wm1)) << 5) | (uint32_t)sl;
-          }
-          {
-            int st_ = 0;
-#pragma unroll
-            for (int k = 2; k <= 32; k <<= 1)
-#pragma unroll
-              for (int j = k >> 1; j > 0; j >>= 1, ++st_) {
-                const uint32_t other = g.shfl_xor(sk, j);
-                sk = ((dirmask >> st_) & 1u) ? min(sk, other) : max(sk, other);
-              }
-          }
+        // Two robots per pass: their networks are independent chains of shuffles, issued back to back (each step waits ~25 cycles
+        // for its shuffle; C5 spent 11 % of its warp time here with one chain).
+        const uint32_t rcj_own = sl < R ? w.rrc[sl] : 0u;
+        auto key_of = [&](int i, uint32_t rci) -> uint32_t {
+          if (sl >= R || sl == i) return MDX_NONE32;
+          const int dr = (int)(rcj_own >> 8) - (int)(rci >> 8), dc = (int)(rcj_own & 255u) - (int)(rci & 255u);
+          return ((uint32_t)__ldg(map.rank + (dr + Hm1) * NC + (dc + Wm1)) << 5) | (uint32_t)sl;
+        };
+        auto emit = [&](int i, uint32_t rci, uint32_t sk) {
           const int jj = (int)(sk & 31u);
           const float cf_j = g.shfl(cflag, jj);
           const float otr_j = g.shfl(ot_r, jj), otc_j = g.shfl(ot_c, jj);
@@ -793,6 +783,26 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
             o[3] = otr_j;
             o[4] = otc_j;
           }
+        };
+#pragma unroll 1
+        for (int i = i0; i < i0 + nrows; i += 2) {
+          const bool two = i + 1 < i0 + nrows;
+          const uint32_t rci = w.rrc[i], rci1 = two ? w.rrc[i + 1] : 0u;
+          uint32_t sk = key_of(i, rci), sk1 = two ? key_of(i + 1, rci1) : MDX_NONE32;
+          {
+            int st_ = 0;
+#pragma unroll
+            for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+              for (int j = k >> 1; j > 0; j >>= 1, ++st_) {
+                const uint32_t other = g.shfl_xor(sk, j), other1 = g.shfl_xor(sk1, j);
+                const bool keep_min = (dirmask >> st_) & 1u;
+                sk = keep_min ? min(sk, other) : max(sk, other);
+                sk1 = keep_min ? min(sk1, other1) : max(sk1, other1);
+              }
+          }
+          emit(i, rci, sk);
+          if (two) emit(i + 1, rci1, sk1);
         }
       } else if (K_o > 0 && R > 1) {
 #pragma unroll 1
@@ -1011,46 +1021,72 @@ __device__ __forceinline__ void featurize_env(const KParams& p, const Env& w, co
         // own five smallest in sorted registers; a round is then one group arg-min over the lanes' heads and a
         // register shift in the winning lane -- no key array in shared memory, no rescans.
         if (use_cand) {
-#pragma unroll 2
-          for (int i = i0; i < i0 + nrows; ++i) {
-            const uint32_t rci = w.rrc[i];
+#pragma unroll 1
+          for (int i = i0; i < i0 + nrows; i += 2) {
+            const bool two = i + 1 < i0 + nrows;
+            const uint32_t rci = w.rrc[i], rci1 = w.rrc[two ? i + 1 : i];
             const int bi = (Hm1 - (int)(rci >> 8)) * NC + (Wm1 - (int)(rci & 255u));
+            const int bi1 = (Hm1 - (int)(rci1 >> 8)) * NC + (Wm1 - (int)(rci1 & 255u));
             uint16_t* selp = w.sel + (i - i0) * Ksel;
-            uint32_t key = c_k != MDX_NONE32 ? (((c_dlk + (uint32_t)__ldg(map.rank + c_off + bi)) << p.key_wbits) | c_k) : MDX_NONE32;
+            uint32_t key = MDX_NONE32, key1 = MDX_NONE32;
+            if (c_k != MDX_NONE32) {
+              key = ((c_dlk + (uint32_t)__ldg(map.rank + c_off + bi)) << p.key_wbits) | c_k;
+              key1 = ((c_dlk + (uint32_t)__ldg(map.rank + c_off + bi1)) << p.key_wbits) | c_k;
+            }
 #pragma unroll 1
             for (int q = 0; q < nsel; ++q) {
-              const uint32_t best = g.rmin(key);
+              const uint32_t best = g.rmin(key), best1 = g.rmin(key1);
               if (key == best) {  // exactly one lane: keys are unique
                 selp[q] = (uint16_t)(best & wmask);
                 key = MDX_NONE32;
               }
+              if (key1 == best1) {
+                if (two) selp[Ksel + q] = (uint16_t)(best1 & wmask);
+                key1 = MDX_NONE32;
+              }
             }
           }
         } else {
+        // two robots per pass over the waiting list: one read of an entry's cell / deadline feeds both robots' keys, and the two
+        // arg-min chains of the pop rounds are independent (the second robot of an odd tail repeats the first and is not written)
 #pragma unroll 1
-        for (int i = i0; i < i0 + nrows; ++i) {
-          const uint32_t rci = w.rrc[i];
+        for (int i = i0; i < i0 + nrows; i += 2) {
+          const bool two = i + 1 < i0 + nrows;
+          const uint32_t rci = w.rrc[i], rci1 = w.rrc[two ? i + 1 : i];
           const int bi = (Hm1 - (int)(rci >> 8)) * NC + (Wm1 - (int)(rci & 255u));
+          const int bi1 = (Hm1 - (int)(rci1 >> 8)) * NC + (Wm1 - (int)(rci1 & 255u));
           uint16_t* selp = w.sel + (i - i0) * Ksel;
           uint32_t a0 = MDX_NONE32, a1 = MDX_NONE32, a2 = MDX_NONE32, a3 = MDX_NONE32, a4 = MDX_NONE32;
-#pragma unroll 2
+          uint32_t b0 = MDX_NONE32, b1 = MDX_NONE32, b2 = MDX_NONE32, b3 = MDX_NONE32, b4 = MDX_NONE32;
+#pragma unroll 1
           for (int k = sl; k < nw; k += LPE) {
             const uint32_t rc = w.wrc[k];
-            const uint32_t rk = __ldg(map.rank + ((int)(rc >> 8) * NC + (int)(rc & 255u) + bi));
-            uint32_t x = (((uint32_t)w.wdl[k] * (uint32_t)p.nranks_max + rk) << p.key_wbits) | (uint32_t)k;
+            const int co = (int)(rc >> 8) * NC + (int)(rc & 255u);
+            const uint32_t rk = __ldg(map.rank + (co + bi)), rk1 = __ldg(map.rank + (co + bi1));
+            const uint32_t dk = (uint32_t)w.wdl[k] * (uint32_t)p.nranks_max;
+            uint32_t x = ((dk + rk) << p.key_wbits) | (uint32_t)k, y = ((dk + rk1) << p.key_wbits) | (uint32_t)k;
             uint32_t lo;
             lo = min(a0, x), x = max(a0, x), a0 = lo;
+            lo = min(b0, y), y = max(b0, y), b0 = lo;
             lo = min(a1, x), x = max(a1, x), a1 = lo;
+            lo = min(b1, y), y = max(b1, y), b1 = lo;
             lo = min(a2, x), x = max(a2, x), a2 = lo;
+            lo = min(b2, y), y = max(b2, y), b2 = lo;
             lo = min(a3, x), x = max(a3, x), a3 = lo;
+            lo = min(b3, y), y = max(b3, y), b3 = lo;
             a4 = min(a4, x);
+            b4 = min(b4, y);
           }
 #pragma unroll 1
           for (int q = 0; q < nsel; ++q) {
-            const uint32_t best = g.rmin(a0);
+            const uint32_t best = g.rmin(a0), best1 = g.rmin(b0);
             if (a0 == best) {  // exactly one lane: keys are unique
               selp[q] = (uint16_t)(best & wmask);
               a0 = a1, a1 = a2, a2 = a3, a3 = a4, a4 = MDX_NONE32;
+            }
+            if (b0 == best1) {
+              if (two) selp[Ksel + q] = (uint16_t)(best1 & wmask);
+              b0 = b1, b1 = b2, b2 = b3, b3 = b4, b4 = MDX_NONE32;
             }
           }
         }
