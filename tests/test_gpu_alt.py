@@ -167,6 +167,44 @@ def test_idq_fused_iteration_by_env_ranges_and_run_time_specialised(maps, R, P, 
         a_.step_idq_featurize(act[:4], env_range=(N - 2, 4), out=tuple(t[:4] for t in out), feat_out=tuple(t[:4] for t in feat))
 
 
+@pytest.mark.parametrize("wide", [False, True])
+def test_split_idq_equals_the_whole_batch_call(wide):
+    """VectorizedEnv.split_idq: fork / step / join over 3 env ranges (uint8 codes or the policy's int64 samples) against
+    step_idq_featurize on a twin; then other full-batch tensors passed per call (step_part(out=, feat_out=))."""
+    N, R, T = 36, 5, 30
+    kw = dict(map_file="map1.txt", n_robots=R, n_packages=40, max_time_steps=T, seed=8)
+    va, vb = mdb.VectorizedEnv(mdb.Environment, N, **kw), mdb.VectorizedEnv(mdb.Environment, N, **kw)
+    va.batch.reset(), vb.batch.reset()
+    dev = va.batch.device
+    si = va.split_idq(3, ops_as_int=True)
+    assert [hi - lo for lo, hi in si.ranges] == [12, 12, 12]
+    rs = np.random.RandomState(4)
+    for s in range(2 * T + 3):
+        codes = rs.randint(0, 15, size=(N, R)).astype(np.uint8)
+        act = torch.from_numpy(codes).to(dev)
+        a_in = act.to(torch.int64) if wide else act
+        si.fork()
+        si.step(a_in)
+        si.join()
+        r2, g2, d2, o2, t2 = vb.batch.step_idq_featurize(act, auto_reset=True, ops_as_int=True)
+        torch.cuda.synchronize()
+        assert torch.equal(si.out[0], r2) and torch.equal(si.out[1], g2) and torch.equal(si.out[2], d2), s
+        assert torch.equal(si.feat[0], o2) and torch.equal(si.feat[1], t2), s
+    H, W = va.batch.rows_out, va.batch.cols_out
+    out = (torch.empty(N, dtype=torch.float64, device=dev), torch.empty((N, R), dtype=torch.float64, device=dev), torch.empty(N, dtype=torch.uint8, device=dev))
+    feat = (torch.empty((N, R, 6, H, W), dtype=torch.float32, device=dev), torch.empty((N, 7, H, W), dtype=torch.float32, device=dev))
+    act = torch.from_numpy(rs.randint(0, 15, size=(N, R)).astype(np.uint8)).to(dev)
+    si.fork()
+    for k in range(3):
+        si.step_part(k, act, out=out, feat_out=feat)
+    si.join()
+    r2, g2, d2, o2, t2 = vb.batch.step_idq_featurize(act, auto_reset=True, ops_as_int=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out[0], r2) and torch.equal(out[1], g2) and torch.equal(out[2], d2)
+    assert torch.equal(feat[0], o2) and torch.equal(feat[1], t2)
+    assert torch.equal(va.batch.episode_stats(), vb.batch.episode_stats())
+
+
 def _tracker_of(env):
     return {p.package_id: {"id": p.package_id, "start_pos": p.start, "target_pos": p.target, "start_time": p.start_time,
                            "deadline": p.deadline, "status": p.status}
