@@ -155,13 +155,18 @@ def test_step_n_and_rollout_graph_equal_step_by_step():
         st1(acts[0].to(torch.int64))
 
 
-def test_split_rollout_on_two_streams_equals_whole_batch_steps():
+@pytest.mark.parametrize("extra", [{}, {"stale_tracker_compat": True}, {"specialize": True, "n_robots": 6},
+                                   {"stale_tracker_compat": True, "map_file": ["map1.txt", "map5.txt"], "n_robots": 9, "n_packages": 70}])
+def test_split_rollout_on_two_streams_equals_whole_batch_steps(extra):
+    """Also with the trainer's never-cleared tracker (its per-env table is read and written by the range's own lane groups only) and
+    with the kernel compiled at run time for the shape."""
     kw = dict(map_file="map1.txt", n_robots=5, n_packages=50, max_time_steps=25, seed=77, k_others=4, k_packages=5)
-    N, S = 600, 60
+    kw.update(extra)
+    N, S, R = 600, 60, kw["n_robots"]
     gen = torch.Generator(device="cuda").manual_seed(5)
-    acts = torch.randint(0, 15, (S, N, 5), dtype=torch.uint8, device="cuda", generator=gen)
+    acts = torch.randint(0, 15, (S, N, R), dtype=torch.uint8, device="cuda", generator=gen)
     for parts in (2, 3):
-        ref = mdb.VectorizedEnv(mdb.Environment, N, **kw)
+        ref = mdb.VectorizedEnv(mdb.Environment, N, **{**kw, "specialize": False})
         ref.batch.reset()
         ve = mdb.VectorizedEnv(mdb.Environment, N, **kw)
         ve.batch.reset()
