@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 O=gpurun_out
-T=r2g
+T=${TAG:-r2g}
 timeout 300 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > $O/${T}_ref1.json 2> $O/${T}_ref1.err
 timeout 400 python bench.py --gpus 1 --steps 20 --warmup 5 > $O/${T}_bench_n1.json 2> $O/${T}_bench_n1.err
 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 5 > $O/${T}_bench_n2.json 2> $O/${T}_bench_n2.err
