@@ -53,6 +53,8 @@ WORKLOADS = {
                MP=100, envs=16384, feat=True),
     "c5": dict(desc="C5: map5 20x20, 32 robots (full warp), 500 packages, T=1000, K_o=31, K_p=5",
                maps=["map5.txt"], R=32, P=500, T=1000, K_o=31, K_p=5, MR=100, MP=100, envs=32768, feat=True),
+    "c5lite": dict(desc="(diagnostic) C5's output geometry with light selection work: map5, 32 robots, 100 packages, K_o=4, K_p=5",
+                   maps=["map5.txt"], R=32, P=100, T=1000, K_o=4, K_p=5, MR=100, MP=100, envs=32768, feat=True),
     "c5step": dict(desc="C5 step only (SURVEY 8d: 'also report step-only'): map5, 32 robots, 500 packages, T=1000, transition + env reward + shaped "
                         "reward + auto-reset, no featurisation", maps=["map5.txt"], R=32, P=500, T=1000, K_o=31, K_p=5, MR=100, MP=100,
                    envs=32768, feat=False),
