@@ -60,7 +60,7 @@ def encode(move, op):
 
 
 def grid_of(map_name):
-    with open(os.path.join(REF, map_name)) as f:
+    with open(os.path.join(REF, map_name)) as f:  # (os.path.join keeps an absolute map_name as it is: the synthetic maps of gen_shapes)
         return np.array([[int(x) for x in line.strip().split(" ")] for line in f], dtype=np.uint8)
 
 
@@ -567,6 +567,28 @@ def main():
     run_traj("map3_small", "map3.txt", 7, 20, 100, 6, 250, 8, "mixed", 3, 3, MR=10, MP=20, feat_every=1)
 
 
+def gen_shapes():
+    """Maps the reference does not ship: non-square ones (the featurisers normalise rows by n_rows and columns by n_cols, deadlines
+    use n_rows only: SURVEY.md Q11), plane sizes that are not whole float4s, and planes beyond the sliced kernels' 512 cells.  The
+    map files are written to a temporary directory (the reference reads maps from files); the fixtures carry the grids."""
+    import tempfile
+
+    #        name          H   W  obstacle%  R   P   T  seed steps aseed policy  K_o K_p  kw
+    cases = [("rect_12x17", 12, 17, 18, 6, 40, 40, 31, 200, 21, "homing", 5, 5, dict(feat_every=1, big_vec_every=9)),
+             ("rect_9x7", 9, 7, 12, 4, 20, 30, 32, 160, 22, "mixed", 3, 5, dict(feat_every=1, big_vec_every=6, invalid_frac=0.02)),
+             ("rect_5x24", 5, 24, 10, 5, 25, 35, 33, 150, 23, "homing", 4, 5, dict(MR=10, MP=20, feat_every=1)),
+             ("big_40x28", 40, 28, 20, 12, 80, 60, 34, 150, 24, "mixed", 11, 5, dict(feat_every=3)),
+             ("big_23x23", 23, 23, 15, 7, 45, 50, 35, 130, 25, "homing", 6, 4, dict(feat_every=2))]
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, H, W, pct, R, P, T, seed, steps, aseed, policy, K_o, K_p, kw in cases:
+            rs = np.random.RandomState(1000 + seed)
+            g = (rs.rand(H, W) < pct / 100.0).astype(np.uint8)
+            path = os.path.join(tmp, f"{name}.txt")
+            with open(path, "w") as f:
+                f.write("\n".join(" ".join(str(int(x)) for x in row) for row in g) + "\n")
+            run_traj(name, path, R, P, T, seed, steps, aseed, policy, K_o, K_p, **kw)
+
+
 def gen_stale():
     """SURVEY.md Q7 / VERDICT r1 row J1: what MAPPO/trainer.py really feeds the featurisers after the first auto-reset."""
     np.savez_compressed(os.path.join(HERE, "kats_stale.npz"), **gen_kat_b(stale=True))
@@ -582,8 +604,11 @@ if __name__ == "__main__":
         gen_stale()
     elif len(sys.argv) > 1 and sys.argv[1] == "alt":
         gen_alt()
+    elif len(sys.argv) > 1 and sys.argv[1] == "shapes":
+        gen_shapes()
     else:
         main()
         gen_greedy()
         gen_alt()
         gen_stale()
+        gen_shapes()

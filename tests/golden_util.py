@@ -7,7 +7,9 @@ import numpy as np
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 TRAJ_NAMES = ["map1_c3", "map1_mix", "map7_odd", "map7_dense", "map7_done", "map5_c4", "map5_c5",
-              "map1_home", "map7_home", "map3_small"]
+              "map1_home", "map7_home", "map3_small",
+              # synthetic maps (make_golden.py shapes): non-square, planes that are not whole float4s, planes beyond 512 cells
+              "rect_12x17", "rect_9x7", "rect_5x24", "big_40x28", "big_23x23"]
 
 
 def load_traj(name):
