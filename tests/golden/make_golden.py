@@ -151,7 +151,7 @@ def gen_reset_blocks():
 
 
 def run_traj(name, map_name, R, P, T, seed, n_steps, act_seed, policy, K_o, K_p, MR=100, MP=100,
-             feat_every=1, big_vec_every=0, invalid_frac=0.0, stale=False):
+             feat_every=1, big_vec_every=0, invalid_frac=0.0, stale=False, rewards=None):
     """One env driven like one slot of MAPPO/trainer.py:collect_rollouts (auto-reset on done, the
     features recorded for a step are those of the state the NEXT action is taken from).
 
@@ -159,7 +159,8 @@ def run_traj(name, map_name, R, P, T, seed, n_steps, act_seed, policy, K_o, K_p,
     Q7), so 'waiting' entries of earlier episodes survive, shadow new packages with the same id and change the dict order;
     the tracker's ids (in dict order) and statuses are recorded per step as well."""
     path = os.path.join(REF, map_name)
-    e = ref_env.Environment(path, T, R, P, seed=seed)
+    # rewards = (move_cost, delivery_reward, delay_reward) other than the constructor's defaults (env.py:20-22)
+    e = ref_env.Environment(path, T, R, P, seed=seed) if rewards is None else ref_env.Environment(path, T, R, P, *rewards, seed=seed)
     H, W = e.n_rows, e.n_cols
     state = e.reset()
     trk = Tracker(1)
@@ -291,7 +292,7 @@ def run_traj(name, map_name, R, P, T, seed, n_steps, act_seed, policy, K_o, K_p,
             bi += 1
     assert stale or n_tracker_mismatch == 0, n_tracker_mismatch
     assert not stale or (n_tracker_mismatch > 0 and n_shadowed > 0), "the stale fixture must exercise the artefact"
-    meta = dict(stale=bool(stale), n_tracker_mismatch=n_tracker_mismatch, n_shadowed=n_shadowed, name=name, map=map_name, R=R, P=P, T=T, seed=seed, n_steps=n_steps, act_seed=act_seed,
+    meta = dict(rewards=(list(rewards) if rewards else None), stale=bool(stale), n_tracker_mismatch=n_tracker_mismatch, n_shadowed=n_shadowed, name=name, map=map_name, R=R, P=P, T=T, seed=seed, n_steps=n_steps, act_seed=act_seed,
                 policy=policy, K_o=K_o, K_p=K_p, MR=MR, MP=MP, feat_every=feat_every,
                 big_vec_every=big_vec_every, H=H, W=W, n_resets=len(reset_pkgs),
                 n_delivered_total=int((rec["reward"] > 0.5).sum()))
@@ -587,6 +588,10 @@ def gen_shapes():
             with open(path, "w") as f:
                 f.write("\n".join(" ".join(str(int(x)) for x in row) for row in g) + "\n")
             run_traj(name, path, R, P, T, seed, steps, aseed, policy, K_o, K_p, **kw)
+    # reward constants other than the defaults: the env reward is a float64 sum in the reference's order, so values
+    # that are not short decimals make every rounding step visible
+    run_traj("map1_rewards", "map1.txt", 5, 14, 120, 36, 420, 26, "homing", 4, 5, feat_every=5, rewards=(-0.0371, 7.3, 0.45))
+    run_traj("map7_rewards", "map.txt", 6, 10, 80, 37, 300, 27, "homing", 5, 5, feat_every=5, rewards=(-0.3, 1e-3, 123456.789))
 
 
 def gen_stale():

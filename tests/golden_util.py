@@ -9,7 +9,15 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TRAJ_NAMES = ["map1_c3", "map1_mix", "map7_odd", "map7_dense", "map7_done", "map5_c4", "map5_c5",
               "map1_home", "map7_home", "map3_small",
               # synthetic maps (make_golden.py shapes): non-square, planes that are not whole float4s, planes beyond 512 cells
-              "rect_12x17", "rect_9x7", "rect_5x24", "big_40x28", "big_23x23"]
+              "rect_12x17", "rect_9x7", "rect_5x24", "big_40x28", "big_23x23",
+              # move_cost / delivery_reward / delay_reward other than the constructor defaults
+              "map1_rewards", "map7_rewards"]
+
+
+def reward_kw(meta):
+    """Constructor keywords for the fixture's reward constants ({} = the reference's defaults)."""
+    rw = meta.get("rewards")
+    return dict(move_cost=rw[0], delivery_reward=rw[1], delay_reward=rw[2]) if rw else {}
 
 
 def load_traj(name):

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import marl_delivery_b200 as mdb
-from golden_util import TRAJ_NAMES, load_kats, load_traj, readme_random_actions
+from golden_util import TRAJ_NAMES, load_kats, load_traj, readme_random_actions, reward_kw
 from oracle import oracle_env as orc
 
 pytestmark = pytest.mark.gpu
@@ -24,7 +24,7 @@ def _batch_for(meta, z, n_envs=1, shaping=mdb.MAPPO_SHAPING, K=None, **kw):
     K_o, K_p, MR, MP = K if K else (meta["K_o"], meta["K_p"], meta["MR"], meta["MP"])
     return mdb.DeliveryBatch([z["grid"]], n_envs, meta["R"], meta["P"], meta["T"], seeds=[meta["seed"]] * n_envs,
                              k_others=K_o, k_packages=K_p, max_robots_in_state=MR, max_packages_in_state=MP,
-                             shaping=shaping, **kw)
+                             shaping=shaping, **reward_kw(meta), **kw)
 
 
 def _state_tuple(b, i=0):
@@ -348,7 +348,7 @@ def test_vectorized_env_reference_api_with_indices():
 def test_helper_dropins_match_golden():
     """The per-call helper functions (same signatures as MAPPO/helper.py) on state/tracker dicts."""
     meta, z = load_traj("map7_home")
-    e = orc.OracleEnv(z["grid"], meta["T"], meta["R"], meta["P"], seed=meta["seed"])
+    e = orc.OracleEnv(z["grid"], meta["T"], meta["R"], meta["P"], seed=meta["seed"], **reward_kw(meta))
     e.reset()
     fi = 0
     for step in range(60):

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from golden_util import TRAJ_NAMES, load_traj
+from golden_util import TRAJ_NAMES, load_traj, reward_kw
 from oracle import oracle_env as orc
 from oracle_c import COracleEnv, COracleVec
 
@@ -19,7 +19,7 @@ def test_c_oracle_golden_trajectory(name):
     meta, z = load_traj(name)
     R, P, T, W = meta["R"], meta["P"], meta["T"], meta["W"]
     K = (meta["K_o"], meta["K_p"], meta["MR"], meta["MP"])
-    e = COracleEnv(z["grid"], T, R, P, meta["seed"])
+    e = COracleEnv(z["grid"], T, R, P, meta["seed"], **reward_kw(meta))
     e.reset()
     assert np.array_equal(e.packages(), z["reset_pkgs"][0])
     o, v, g, gv = e.features(*K)

@@ -4,7 +4,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from golden_util import TRAJ_NAMES, load_kats, load_reset_blocks, load_traj, readme_random_actions
+from golden_util import TRAJ_NAMES, load_kats, load_reset_blocks, load_traj, readme_random_actions, reward_kw
 from oracle import oracle_env as orc
 
 
@@ -26,7 +26,7 @@ def test_trajectory(name):
     meta, z = load_traj(name)
     R, P, T = meta["R"], meta["P"], meta["T"]
     K_o, K_p, MR, MP = meta["K_o"], meta["K_p"], meta["MR"], meta["MP"]
-    e = orc.OracleEnv(z["grid"], T, R, P, seed=meta["seed"])
+    e = orc.OracleEnv(z["grid"], T, R, P, seed=meta["seed"], **reward_kw(meta))
     e.reset()
     W = e.W
     s0 = e.snapshot()
