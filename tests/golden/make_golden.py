@@ -469,8 +469,21 @@ def gen_alt():
     sizes (10 / 20)."""
     idq = _load_ref_module("idq_networks_ref", "IDQ/networks.py")
     legacy = _load_ref_module("legacy_qmix_networks_ref", "qmix/networks.py")
+    import tempfile
+
+    tmp = tempfile.mkdtemp()
+
+    def synthetic(name, H, W, pct, seed):  # a map the reference does not ship (non-square), written where the reference can read it
+        g = (np.random.RandomState(seed).rand(H, W) < pct / 100.0).astype(np.uint8)
+        path = os.path.join(tmp, f"{name}.txt")
+        with open(path, "w") as f:
+            f.write("\n".join(" ".join(str(int(x)) for x in row) for row in g) + "\n")
+        return path
+
     cases = [("alt_map1", "map1.txt", 5, 50, 120, 31, 200, "homing"), ("alt_map5", "map5.txt", 10, 100, 150, 32, 170, "random"),
-             ("alt_map7", "map.txt", 4, 12, 40, 33, 100, "homing"), ("alt_map3", "map3.txt", 6, 30, 90, 34, 120, "homing")]
+             ("alt_map7", "map.txt", 4, 12, 40, 33, 100, "homing"), ("alt_map3", "map3.txt", 6, 30, 90, 34, 120, "homing"),
+             ("alt_rect_10x14", synthetic("alt_rect_10x14", 10, 14, 15, 2001), 5, 30, 60, 35, 130, "homing"),
+             ("alt_rect_9x7", synthetic("alt_rect_9x7", 9, 7, 10, 2002), 3, 15, 40, 36, 100, "homing")]
     out, meta = {}, []
     for name, map_name, R, P, T, seed, n_steps, policy in cases:
         e = ref_env.Environment(os.path.join(REF, map_name), T, R, P, seed=seed)
@@ -535,7 +548,7 @@ def gen_alt():
         out.update({f"{name}_actions": acts_rec, f"{name}_obs6": obs6, f"{name}_g7": g7, f"{name}_shape_str": sh_str,
                     f"{name}_shape_int": sh_int, f"{name}_qvec": qvec, f"{name}_qgvec": qg, f"{name}_done": done_rec,
                     f"{name}_grid": grid_of(map_name)})
-        meta.append(dict(name=name, map=map_name, R=R, P=P, T=T, seed=seed, n_steps=n_steps,
+        meta.append(dict(name=name, map=os.path.basename(map_name), R=R, P=P, T=T, seed=seed, n_steps=n_steps,
                          urgency_cells=int((obs6[:, :, 1] > 0).sum()), frac_cells=int(((g7[:, 6] > 0) & (g7[:, 6] < 1)).sum()),
                          int_branches=sorted(set(np.round(sh_int.reshape(-1), 6).tolist()))))
         print("alt case", meta[-1])
