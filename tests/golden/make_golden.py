@@ -425,7 +425,19 @@ def gen_greedy():
         np.mean(rewards), np.std(rewards), np.mean(delivered), np.std(delivered)))
     out["readme_greedy_rewards"] = np.array(rewards, np.float64)
     out["readme_greedy_delivered"] = np.array(delivered, np.int32)
-    cases = [("map5.txt", 4, 30, 300, 3), ("map2.txt", 10, 60, 200, 8), ("map.txt", 3, 8, 80, 21), ("map4.txt", 7, 40, 150, 5)]
+    import tempfile
+
+    tmp = tempfile.mkdtemp()
+
+    def synthetic(name, H, W, pct, seed):  # non-square maps the reference does not ship, written where it can read them
+        g = (np.random.RandomState(seed).rand(H, W) < pct / 100.0).astype(np.uint8)
+        path = os.path.join(tmp, f"{name}.txt")
+        with open(path, "w") as f:
+            f.write("\n".join(" ".join(str(int(x)) for x in row) for row in g) + "\n")
+        return path
+
+    cases = [("map5.txt", 4, 30, 300, 3), ("map2.txt", 10, 60, 200, 8), ("map.txt", 3, 8, 80, 21), ("map4.txt", 7, 40, 150, 5),
+             (synthetic("greedy_rect_8x13", 8, 13, 15, 3001), 4, 20, 120, 9), (synthetic("greedy_rect_11x6", 11, 6, 12, 3002), 3, 10, 90, 10)]
     meta = []
     for k, (m, R, P, T, seed) in enumerate(cases):
         e = ref_env.Environment(os.path.join(REF, m), T, R, P, seed=seed)
@@ -443,7 +455,7 @@ def gen_greedy():
         out[f"greedy_actions_{k}"] = np.array(rec, np.uint8)
         out[f"greedy_rewards_{k}"] = np.array(rew, np.float64)
         out[f"greedy_grid_{k}"] = grid_of(m)
-        meta.append(dict(map=m, R=R, P=P, T=T, seed=seed, steps=len(rec), total=float(e.total_reward),
+        meta.append(dict(map=os.path.basename(m), R=R, P=P, T=T, seed=seed, steps=len(rec), total=float(e.total_reward),
                          delivered=int(sum(p.status == "delivered" for p in e.packages))))
         print("greedy case", meta[-1])
     out["greedy_meta"] = np.array(json.dumps(meta))
