@@ -625,6 +625,15 @@ def gen_stale():
     run_traj("map1_stale", "map1.txt", 5, 30, 40, 61, 420, 11, "homing", 4, 5, feat_every=1, big_vec_every=7, stale=True)
     run_traj("map7_stale", "map.txt", 4, 12, 25, 62, 300, 12, "mixed", 3, 5, MR=10, MP=20, feat_every=1, big_vec_every=5, stale=True)
     run_traj("map5_stale", "map5.txt", 10, 100, 60, 63, 250, 13, "homing", 9, 5, feat_every=2, invalid_frac=0.02, stale=True)
+    # and on a non-square map the reference does not ship (written to a temporary file: the reference reads maps from files)
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as tmp:
+        g = (np.random.RandomState(4001).rand(10, 15) < 0.14).astype(np.uint8)
+        path = os.path.join(tmp, "rect_10x15.txt")
+        with open(path, "w") as f:
+            f.write("\n".join(" ".join(str(int(x)) for x in row) for row in g) + "\n")
+        run_traj("rect_stale", path, 6, 24, 30, 64, 320, 14, "homing", 5, 5, feat_every=1, big_vec_every=6, stale=True)
 
 
 if __name__ == "__main__":

@@ -16,7 +16,7 @@ from oracle import tracker_oracle as trk
 
 pytestmark = pytest.mark.gpu
 
-STALE_NAMES = ["map1_stale", "map7_stale", "map5_stale"]
+STALE_NAMES = ["map1_stale", "map7_stale", "map5_stale", "rect_stale"]  # rect_stale: a non-square 10x15 map
 
 
 def _bits(x):

@@ -10,7 +10,7 @@ from golden_util import GOLDEN, load_kats, load_traj
 from oracle import oracle_env as orc
 from oracle import tracker_oracle as trk
 
-STALE_NAMES = ["map1_stale", "map7_stale", "map5_stale"]
+STALE_NAMES = ["map1_stale", "map7_stale", "map5_stale", "rect_stale"]  # rect_stale: a non-square 10x15 map
 
 
 def _bits(x):
